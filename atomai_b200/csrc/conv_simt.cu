@@ -1,0 +1,304 @@
+// conv_simt.cu — exact-fp32 (FFMA) convolution family: forward/dgrad and weight-gradient for ANY
+// channel count (Cin = 1 first layer, Cout = nb_classes head, 1-D signals as H = 1), reading its
+// input through the same normalise-on-load source loader as the tensor-core path.  This is the
+// AB_MATH_FP32 math mode: bit-for-bit it is still not the CPU reference (different summation
+// order) but it carries no TF32 rounding, so it is the mode the 1e-3 logit parity bound is pinned
+// with.  It also serves every layer shape the tcgen05 kernels do not take (C % 8 != 0, Cout % 16).
+//
+// Replaces nn.Conv2d/nn.Conv1d (+bias, LeakyReLU, BN statistics) of atomai/nets/blocks.py:61-76,
+// :302-319, :130-132 and autograd's bwd-filter for atomai/trainers/trainer.py:206.
+#include "common.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------ forward
+// CTA: 256 threads, output tile 8 rows x 32 cols (or 1 x 256 for 1-D), COT = 16 couts per pass.
+// thread -> 4 consecutive-w pixels x 4 couts... laid out as: pg = tid % 64 (8 rows x 8 groups of
+// 4 px), cg = tid / 64 (4 groups of 4 couts).
+constexpr int F_TH = 8, F_TW = 32, F_COT = 16, F_CIT = 8, F_THREADS = 256;
+
+struct ConvSimtParams {
+  SrcSet S;
+  int N, H, W, Cout;
+  int th, tw, dil;
+  const float* w;  // [tap][Cin][Cout]
+  const float* bias;
+  float alpha;
+  int act;
+  float* out;
+  int ld_out;
+  int out_nchw;
+  double* stats;
+  int tiles_h, tiles_w;
+};
+
+__global__ void __launch_bounds__(F_THREADS) conv_simt_fwd_kernel(const ConvSimtParams p) {
+  extern __shared__ float sm[];
+  const int taps = p.th * p.tw;
+  const int ph = p.dil * (p.th >> 1), pw = p.dil * (p.tw >> 1);
+  const int THp = F_TH + 2 * ph, TWp = F_TW + 2 * pw;
+  float* s_in = sm;                             // [F_CIT][THp][TWp]
+  float* s_w = sm + F_CIT * THp * TWp;          // [taps][F_CIT][F_COT]
+  __shared__ float s_red[2 * F_COT];
+
+  const int tile = blockIdx.x;
+  const int tw_i = tile % p.tiles_w;
+  const int th_i = (tile / p.tiles_w) % p.tiles_h;
+  const int n = tile / (p.tiles_w * p.tiles_h);
+  const int h0 = th_i * F_TH, w0 = tw_i * F_TW;
+  const int co0 = blockIdx.y * F_COT;
+
+  const int tid = threadIdx.x;
+  const int pg = tid & 63, cg = tid >> 6;
+  const int r = pg >> 3, wq = (pg & 7) * 4;  // row in tile, first of 4 pixels
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc[i][k] = 0.f;
+
+  const int Cin = p.S.Ctot;
+  for (int ci0 = 0; ci0 < Cin; ci0 += F_CIT) {
+    __syncthreads();
+    for (int i = tid; i < F_CIT * THp * TWp; i += F_THREADS) {
+      const int ww = i % TWp, hh = (i / TWp) % THp, c = i / (TWp * THp);
+      float v = 0.f;
+      if (ci0 + c < Cin) v = load_src1(p.S, n, h0 - ph + hh, w0 - pw + ww, p.H, p.W, ci0 + c);
+      s_in[i] = v;
+    }
+    for (int i = tid; i < taps * F_CIT * F_COT; i += F_THREADS) {
+      const int co = i % F_COT, c = (i / F_COT) % F_CIT, t = i / (F_COT * F_CIT);
+      float v = 0.f;
+      if (ci0 + c < Cin && co0 + co < p.Cout)
+        v = __ldg(p.w + ((size_t)t * Cin + ci0 + c) * p.Cout + co0 + co);
+      s_w[i] = v;
+    }
+    __syncthreads();
+    for (int c = 0; c < F_CIT; ++c) {
+      for (int t = 0; t < taps; ++t) {
+        const int ty = t / p.tw, tx = t - ty * p.tw;
+        const float* ip = s_in + (c * THp + r + ty * p.dil) * TWp + wq + tx * p.dil;
+        const float4 wv = *reinterpret_cast<const float4*>(s_w + (t * F_CIT + c) * F_COT + cg * 4);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float x = ip[i];
+          acc[i][0] = fmaf(x, wv.x, acc[i][0]);
+          acc[i][1] = fmaf(x, wv.y, acc[i][1]);
+          acc[i][2] = fmaf(x, wv.z, acc[i][2]);
+          acc[i][3] = fmaf(x, wv.w, acc[i][3]);
+        }
+      }
+    }
+  }
+
+  // epilogue
+  float ssum[4] = {0, 0, 0, 0}, ssq[4] = {0, 0, 0, 0};
+  const int gh = h0 + r;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int gw = w0 + wq + i;
+    const bool valid = gh < p.H && gw < p.W;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int co = co0 + cg * 4 + k;
+      if (co < p.Cout) {
+        float v = acc[i][k] + (p.bias ? __ldg(p.bias + co) : 0.f);
+        v = act_f(v, p.act, p.alpha);
+        if (valid) {
+          if (!p.out_nchw)
+            p.out[(((size_t)n * p.H + gh) * p.W + gw) * p.ld_out + co] = v;
+          else
+            p.out[(((size_t)n * p.Cout + co) * p.H + gh) * p.W + gw] = v;
+          ssum[k] += v;
+          ssq[k] += v * v;
+        }
+      }
+    }
+  }
+  if (p.stats) {
+    if (tid < 2 * F_COT) s_red[tid] = 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float a = warp_sum(ssum[k]), b = warp_sum(ssq[k]);
+      if ((tid & 31) == 0) {
+        atomicAdd(&s_red[cg * 4 + k], a);
+        atomicAdd(&s_red[F_COT + cg * 4 + k], b);
+      }
+    }
+    __syncthreads();
+    if (tid < F_COT && co0 + tid < p.Cout) {
+      atomicAdd(p.stats + co0 + tid, (double)s_red[tid]);
+      atomicAdd(p.stats + p.Cout + co0 + tid, (double)s_red[F_COT + tid]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ weight gradient
+// grid: (pixel ranges, taps, co-tiles*ci-tiles).  CTA accumulates dW[co 0..63][ci 0..63] of one
+// tap over its pixel range in registers (thread: 4 co x 4 ci), pixels streamed through smem in
+// slabs of 64, then atomically adds into dW (OIHW).
+constexpr int G_PX = 64, G_CT = 64, G_THREADS = 256;
+
+struct WgradSimtParams {
+  SrcSet S;
+  int N, H, W, Cout;
+  int th, tw, dil;
+  const float* dy;
+  int ld_dy;
+  float* dw;  // OIHW
+  int64_t npix;
+  int px_per_cta;
+  int co_tiles, ci_tiles;
+};
+
+__global__ void __launch_bounds__(G_THREADS) conv_simt_wgrad_kernel(const WgradSimtParams p) {
+  __shared__ float s_dy[G_PX][G_CT + 4];
+  __shared__ float s_x[G_PX][G_CT + 4];
+  const int t = blockIdx.y;
+  const int ty = t / p.tw, tx = t - ty * p.tw;
+  const int co_t = blockIdx.z / p.ci_tiles, ci_t = blockIdx.z % p.ci_tiles;
+  const int co0 = co_t * G_CT, ci0 = ci_t * G_CT;
+  const int Cin = p.S.Ctot;
+  const int dh = (ty - (p.th >> 1)) * p.dil, dwid = (tx - (p.tw >> 1)) * p.dil;
+  const int tid = threadIdx.x;
+  const int a = tid >> 4, b = tid & 15;  // co group, ci group (4 each)
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc[i][k] = 0.f;
+
+  const int64_t p_begin = (int64_t)blockIdx.x * p.px_per_cta;
+  int64_t p_end = p_begin + p.px_per_cta;
+  if (p_end > p.npix) p_end = p.npix;
+  for (int64_t pb = p_begin; pb < p_end; pb += G_PX) {
+    __syncthreads();
+    for (int i = tid; i < G_PX * G_CT; i += G_THREADS) {
+      const int c = i % G_CT, q = i / G_CT;
+      const int64_t pix = pb + q;
+      float vd = 0.f, vx = 0.f;
+      if (pix < p_end) {
+        if (co0 + c < p.Cout) vd = __ldg(p.dy + pix * p.ld_dy + co0 + c);
+        if (ci0 + c < Cin) {
+          const int w = (int)(pix % p.W);
+          const int h = (int)((pix / p.W) % p.H);
+          const int n = (int)(pix / ((int64_t)p.W * p.H));
+          vx = load_src1(p.S, n, h + dh, w + dwid, p.H, p.W, ci0 + c);
+        }
+      }
+      s_dy[q][c] = vd;
+      s_x[q][c] = vx;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int q = 0; q < G_PX; ++q) {
+      const float4 d4 = *reinterpret_cast<const float4*>(&s_dy[q][a * 4]);
+      const float4 x4 = *reinterpret_cast<const float4*>(&s_x[q][b * 4]);
+      const float dv[4] = {d4.x, d4.y, d4.z, d4.w};
+      const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[i][k] = fmaf(dv[i], xv[k], acc[i][k]);
+    }
+  }
+  const int taps = p.th * p.tw;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int co = co0 + a * 4 + i;
+    if (co >= p.Cout) continue;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int ci = ci0 + b * 4 + k;
+      if (ci < Cin) atomicAdd(p.dw + ((size_t)co * Cin + ci) * taps + t, acc[i][k]);
+    }
+  }
+}
+
+// W[co][ci][ty][tx] -> [tap][Cin][Cout] (FWD) ; dgrad: out[tap][co][ci] with flipped taps
+__global__ void pack_weights_simt_kernel(const float* __restrict__ w, int Cout, int Cin, int th,
+                                         int tw, int mode, float* __restrict__ out,
+                                         int64_t total) {
+  const int taps = th * tw;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    if (mode == AB_WMODE_FWD) {
+      const int co = i % Cout, ci = (i / Cout) % Cin, t = (int)(i / ((int64_t)Cout * Cin));
+      out[i] = w[((int64_t)co * Cin + ci) * taps + t];
+    } else {  // conv input = dy (Cout ch), output = dx (Cin ch): out[tap][co][ci]
+      const int ci = i % Cin, co = (i / Cin) % Cout, t = (int)(i / ((int64_t)Cout * Cin));
+      out[i] = w[((int64_t)co * Cin + ci) * taps + (taps - 1 - t)];
+    }
+  }
+}
+
+}  // namespace
+
+int ab_pack_weights_simt(const float* w, int Cout, int Cin, int th, int tw, int mode, float* out,
+                         cudaStream_t stream) {
+  const int64_t total = (int64_t)Cout * Cin * th * tw;
+  const int threads = 256;
+  int64_t blocks = (total + threads - 1) / threads;
+  if (blocks > 4096) blocks = 4096;
+  pack_weights_simt_kernel<<<(int)blocks, threads, 0, stream>>>(w, Cout, Cin, th, tw, mode, out,
+                                                                total);
+  AB_LAUNCH_CHECK();
+  return 0;
+}
+
+int ab_conv_simt_fwd(const ab_conv_t* d, const float* w, const float* bias, float* y, int ld_y,
+                     double* stats, cudaStream_t stream) {
+  ConvSimtParams p;
+  if (ab_make_srcset(d, &p.S)) return 1;
+  p.N = d->N; p.H = d->H; p.W = d->W; p.Cout = d->Cout;
+  p.th = d->ks_h; p.tw = d->ks_w; p.dil = d->dil;
+  p.w = w; p.bias = bias; p.alpha = d->lrelu; p.act = d->act; p.out = y; p.ld_out = ld_y;
+  p.out_nchw = d->out_nchw; p.stats = stats;
+  p.tiles_h = (d->H + F_TH - 1) / F_TH;
+  p.tiles_w = (d->W + F_TW - 1) / F_TW;
+  const int ph = d->dil * (d->ks_h >> 1), pw = d->dil * (d->ks_w >> 1);
+  const int smem = (F_CIT * (F_TH + 2 * ph) * (F_TW + 2 * pw) + d->ks_h * d->ks_w * F_CIT * F_COT) *
+                   (int)sizeof(float);
+  AB_CHECK(smem <= 200 * 1024, "conv_simt: dilation %d too large", d->dil);
+  static int configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    AB_CUDA(cudaFuncSetAttribute(conv_simt_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 200 * 1024));
+    configured = 200 * 1024;
+  }
+  const int64_t tiles = (int64_t)d->N * p.tiles_h * p.tiles_w;
+  AB_CHECK(tiles < (1ll << 31), "conv_simt: too many tiles");
+  if (tiles == 0) return 0;
+  dim3 grid((unsigned)tiles, (d->Cout + F_COT - 1) / F_COT);
+  conv_simt_fwd_kernel<<<grid, F_THREADS, smem, stream>>>(p);
+  AB_LAUNCH_CHECK();
+  return 0;
+}
+
+int ab_conv_simt_wgrad(const ab_conv_t* d, const float* dy, int ld_dy, float* dw,
+                       cudaStream_t stream) {
+  WgradSimtParams p;
+  if (ab_make_srcset(d, &p.S)) return 1;
+  p.N = d->N; p.H = d->H; p.W = d->W; p.Cout = d->Cout;
+  p.th = d->ks_h; p.tw = d->ks_w; p.dil = d->dil;
+  p.dy = dy; p.ld_dy = ld_dy; p.dw = dw;
+  p.npix = (int64_t)d->N * d->H * d->W;
+  if (p.npix == 0) return 0;
+  p.co_tiles = (d->Cout + G_CT - 1) / G_CT;
+  p.ci_tiles = (p.S.Ctot + G_CT - 1) / G_CT;
+  const int taps = d->ks_h * d->ks_w;
+  const int64_t per_range_ctas = (int64_t)taps * p.co_tiles * p.ci_tiles;
+  int64_t ranges = (4ll * ab_num_sms() + per_range_ctas - 1) / per_range_ctas;  // ~4 waves
+  int64_t max_ranges = (p.npix + G_PX - 1) / G_PX;
+  if (ranges > max_ranges) ranges = max_ranges;
+  if (ranges < 1) ranges = 1;
+  int64_t ppc = (p.npix + ranges - 1) / ranges;
+  ppc = (ppc + G_PX - 1) / G_PX * G_PX;
+  ranges = (p.npix + ppc - 1) / ppc;
+  p.px_per_cta = (int)ppc;
+  dim3 grid((unsigned)ranges, taps, p.co_tiles * p.ci_tiles);
+  conv_simt_wgrad_kernel<<<grid, G_THREADS, 0, stream>>>(p);
+  AB_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,434 @@
+// conv_tc.cu — implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05, TF32 operands,
+// fp32 accumulators in TMEM).  One persistent, warp-specialised CTA per SM:
+//
+//   warps 0-3   epilogue   TMEM -> regs -> bias + LeakyReLU -> NHWC/NCHW store + BN statistics
+//   warp  4     MMA issue  one elected lane issues tcgen05.mma for every (k-chunk, tap, k-step)
+//   warp  5     weights    TMEM alloc + cp.async.bulk of pre-packed weight blobs (L2 -> smem)
+//   warps 6-13  loaders    HBM/L2 -> regs -> [BN affine, 2x2 max-pool, zero pad, RN->TF32] -> smem
+//
+// GEMM view: M = 128 output pixels (a 16 x 8 tile), N = Cout, K = taps * Cin.
+// The activation halo tile is loaded ONCE per 32-channel chunk and re-used by all nine taps: it
+// is stored as UMMA "interleave" (no-swizzle) K-major core matrices, one plane per 4 channels,
+// rows = halo pixels at 16 B pitch.  A tap is then just a different start address
+// ((ty*d*TWp + tx*d) * 16 B) with SBO = TWp*16 B (next image row = next 8-row group) and
+// LBO = plane stride (next 4 channels).  No im2col buffer ever exists.
+//
+// Replaces nn.Conv2d(+bias) -> nn.LeakyReLU -> (batch statistics of) nn.BatchNorm2d of
+// atomai/nets/blocks.py:61-76,302-319, the preceding BatchNorm2d/max_pool2d/cat passes
+// (normalise-on-load, atomai/nets/fcnn.py:123-138) and, with flipped weights, autograd's dgrad.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kTileH = 16;
+constexpr int kTileW = 8;
+constexpr int kNumEpiWarps = 4;
+constexpr int kMmaWarp = 4;
+constexpr int kWgtWarp = 5;
+constexpr int kFirstLoadWarp = 6;
+constexpr int kNumLoadWarps = 8;
+constexpr int kNumLoadThreads = kNumLoadWarps * 32;
+constexpr int kThreads = (kFirstLoadWarp + kNumLoadWarps) * 32;  // 448
+constexpr int kMaxAStages = 4;
+constexpr int kMaxBStages = 6;
+constexpr int kMaxLoadsPerThread = 8;  // register-staged 16B loads per thread per chunk
+
+struct ConvTcParams {
+  SrcSet S;
+  int N, H, W, Cout;
+  int taps_h, taps_w, dil;
+  const float* wblob;
+  const float* bias;
+  float alpha;
+  int act;
+  float* out;
+  int ld_out;
+  int out_nchw;
+  double* stats;
+  int tiles_h, tiles_w, num_tiles;
+  int KC;            // channels per k-chunk (8, 16 or 32)
+  int n_chunks;      // Ctot / KC
+  int TWp, THp, HP;  // halo tile extent and pixel count
+  int plane_bytes;   // stride between 4-channel planes (== 128/P mod 128 -> conflict-free STS)
+  int a_stage_bytes, b_stage_bytes;
+  int n_a, n_b;      // pipeline depths
+  int tmem_cols;     // power of two >= 2*Cout
+};
+
+struct __align__(8) SharedCtl {
+  uint64_t full_a[kMaxAStages], empty_a[kMaxAStages];
+  uint64_t full_b[kMaxBStages], empty_b[kMaxBStages];
+  uint64_t tmem_full[2], tmem_empty[2];
+  uint32_t tmem_base;
+  uint32_t pad;
+};
+
+__global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  SharedCtl* ctl = reinterpret_cast<SharedCtl*>(smem);
+  float* s_stats = reinterpret_cast<float*>(smem + 256);  // [4 warps][2][Cout]
+  const uint32_t stats_bytes = kNumEpiWarps * 2 * p.Cout * sizeof(float);
+  const uint32_t a_base = smem_u32(smem) + ((256 + stats_bytes + 127) & ~127u);
+  const uint32_t b_base = a_base + p.n_a * p.a_stage_bytes;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int taps = p.taps_h * p.taps_w;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.n_a; ++i) {
+      mbar_init(smem_u32(&ctl->full_a[i]), kNumLoadWarps);
+      mbar_init(smem_u32(&ctl->empty_a[i]), 1);
+    }
+    for (int i = 0; i < p.n_b; ++i) {
+      mbar_init(smem_u32(&ctl->full_b[i]), 1);
+      mbar_init(smem_u32(&ctl->empty_b[i]), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&ctl->tmem_full[i]), 1);
+      mbar_init(smem_u32(&ctl->tmem_empty[i]), kNumEpiWarps);
+    }
+    fence_barrier_init();
+  }
+  if (warp == kWgtWarp) tmem_alloc(smem_u32(&ctl->tmem_base), p.tmem_cols);
+  if (warp < kNumEpiWarps) {
+    for (int i = lane; i < 2 * p.Cout; i += 32) s_stats[warp * 2 * p.Cout + i] = 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = ctl->tmem_base;
+
+  if (warp >= kFirstLoadWarp) {
+    // ===================== activation loaders =====================
+    const int lt = threadIdx.x - kFirstLoadWarp * 32;
+    const int P = p.KC >> 2;                   // planes per chunk
+    const int elems = p.HP * P;                // 16B elements per chunk stage
+    const int j = lt % P;                      // this thread's plane (constant: 256 % P == 0)
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int tw_i = tile % p.tiles_w;
+      const int th_i = (tile / p.tiles_w) % p.tiles_h;
+      const int n = tile / (p.tiles_w * p.tiles_h);
+      const int h_org = th_i * kTileH - p.dil * (p.taps_h >> 1);
+      const int w_org = tw_i * kTileW - p.dil * (p.taps_w >> 1);
+      for (int ch = 0; ch < p.n_chunks; ++ch, ++it) {
+        const int c = ch * p.KC + j * 4;
+        float4 v[kMaxLoadsPerThread];
+#pragma unroll
+        for (int u = 0; u < kMaxLoadsPerThread; ++u) {
+          const int e = lt + u * kNumLoadThreads;
+          if (e < elems) {
+            const int q = e / P;
+            const int hh = q / p.TWp, ww = q - hh * p.TWp;
+            v[u] = load_src4(p.S, n, h_org + hh, w_org + ww, p.H, p.W, c);
+          }
+        }
+        const uint32_t st = it % p.n_a;
+        mbar_wait(smem_u32(&ctl->empty_a[st]), ((it / p.n_a) & 1) ^ 1);
+        const uint32_t dst = a_base + st * p.a_stage_bytes + j * p.plane_bytes;
+#pragma unroll
+        for (int u = 0; u < kMaxLoadsPerThread; ++u) {
+          const int e = lt + u * kNumLoadThreads;
+          if (e < elems) {
+            const int q = e / P;
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + q * 16),
+                         "f"(to_tf32(v[u].x)), "f"(to_tf32(v[u].y)), "f"(to_tf32(v[u].z)),
+                         "f"(to_tf32(v[u].w))
+                         : "memory");
+          }
+        }
+        // remaining elements (large dilation halos) go through a plain loop
+        for (int e = lt + kMaxLoadsPerThread * kNumLoadThreads; e < elems;
+             e += kNumLoadThreads) {
+          const int q = e / P;
+          const int hh = q / p.TWp, ww = q - hh * p.TWp;
+          const float4 x = load_src4(p.S, n, h_org + hh, w_org + ww, p.H, p.W, c);
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + q * 16),
+                       "f"(to_tf32(x.x)), "f"(to_tf32(x.y)), "f"(to_tf32(x.z)), "f"(to_tf32(x.w))
+                       : "memory");
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&ctl->full_a[st]));
+      }
+    }
+  } else if (warp == kWgtWarp) {
+    // ===================== weight producer =====================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        for (int ch = 0; ch < p.n_chunks; ++ch) {
+          for (int t = 0; t < taps; ++t, ++it) {
+            const uint32_t st = it % p.n_b;
+            mbar_wait(smem_u32(&ctl->empty_b[st]), ((it / p.n_b) & 1) ^ 1);
+            const uint32_t bar = smem_u32(&ctl->full_b[st]);
+            mbar_arrive_expect_tx(bar, p.b_stage_bytes);
+            const int ksteps = p.KC >> 3;
+            const uint32_t piece = p.Cout * 32;  // bytes of one (k-step, tap) piece
+            for (int ks = 0; ks < ksteps; ++ks)
+              bulk_g2s(b_base + st * p.b_stage_bytes + ks * piece,
+                       p.wblob + ((size_t)(ch * ksteps + ks) * taps + t) * (piece >> 2), piece,
+                       bar);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == kMmaWarp) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_tf32(128, p.Cout, 0, 0);
+      const uint32_t a_sbo = p.TWp * 16, a_lbo = p.plane_bytes;
+      const uint32_t b_sbo = 128, b_lbo = p.Cout * 16;
+      const int ksteps = p.KC >> 3;
+      uint32_t ita = 0, itb = 0, acc = 0, acc_phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        mbar_wait(smem_u32(&ctl->tmem_empty[acc]), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * p.Cout;
+        uint32_t first = 1;
+        for (int ch = 0; ch < p.n_chunks; ++ch, ++ita) {
+          const uint32_t sa = ita % p.n_a;
+          mbar_wait(smem_u32(&ctl->full_a[sa]), (ita / p.n_a) & 1);
+          tc_fence_after();
+          const uint32_t a_st = a_base + sa * p.a_stage_bytes;
+          for (int t = 0; t < taps; ++t, ++itb) {
+            const uint32_t sb = itb % p.n_b;
+            mbar_wait(smem_u32(&ctl->full_b[sb]), (itb / p.n_b) & 1);
+            tc_fence_after();
+            const int ty = t / p.taps_w, tx = t - ty * p.taps_w;
+            const uint32_t a_tap = a_st + (ty * p.dil * p.TWp + tx * p.dil) * 16;
+            const uint32_t b_st = b_base + sb * p.b_stage_bytes;
+            for (int ks = 0; ks < ksteps; ++ks) {
+              const uint64_t ad = umma_desc(a_tap + ks * 2 * p.plane_bytes, a_lbo, a_sbo);
+              const uint64_t bd = umma_desc(b_st + ks * 2 * b_lbo, b_lbo, b_sbo);
+              umma_tf32(d_tmem, ad, bd, idesc, first ? 0u : 1u);
+              first = 0;
+            }
+            umma_commit(smem_u32(&ctl->empty_b[sb]));
+          }
+          umma_commit(smem_u32(&ctl->empty_a[sa]));
+        }
+        umma_commit(smem_u32(&ctl->tmem_full[acc]));
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue =====================
+    uint32_t acc = 0, acc_phase = 0;
+    float* my_stats = s_stats + warp * 2 * p.Cout;
+    const int row = warp * 32 + lane;
+    const int r_h = row >> 3, r_w = row & 7;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int tw_i = tile % p.tiles_w;
+      const int th_i = (tile / p.tiles_w) % p.tiles_h;
+      const int n = tile / (p.tiles_w * p.tiles_h);
+      const int gh = th_i * kTileH + r_h, gw = tw_i * kTileW + r_w;
+      const bool valid = gh < p.H && gw < p.W;
+      mbar_wait(smem_u32(&ctl->tmem_full[acc]), acc_phase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + acc * p.Cout + ((uint32_t)(warp * 32) << 16);
+      const size_t pix = ((size_t)n * p.H + gh) * p.W + gw;
+      for (int c0 = 0; c0 < p.Cout; c0 += 16) {
+        float v[16];
+        tmem_ld16(t_addr + c0, v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float x = v[i] + (p.bias ? __ldg(p.bias + c0 + i) : 0.f);
+          x = act_f(x, p.act, p.alpha);
+          v[i] = valid ? x : 0.f;
+        }
+        if (valid) {
+          if (!p.out_nchw) {
+            float4* o = reinterpret_cast<float4*>(p.out + pix * p.ld_out + c0);
+            o[0] = make_float4(v[0], v[1], v[2], v[3]);
+            o[1] = make_float4(v[4], v[5], v[6], v[7]);
+            o[2] = make_float4(v[8], v[9], v[10], v[11]);
+            o[3] = make_float4(v[12], v[13], v[14], v[15]);
+          } else {
+            const size_t hw = (size_t)p.H * p.W;
+            float* o = p.out + ((size_t)n * p.Cout + c0) * hw + (size_t)gh * p.W + gw;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i * hw] = v[i];
+          }
+        }
+        if (p.stats) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float s1 = warp_sum(v[i]);
+            const float s2 = warp_sum(v[i] * v[i]);
+            if (lane == i) {
+              my_stats[c0 + i] += s1;
+              my_stats[p.Cout + c0 + i] += s2;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&ctl->tmem_empty[acc]));
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+    if (p.stats) {
+      __syncwarp();
+      for (int i = lane; i < 2 * p.Cout; i += 32) atomicAdd(p.stats + i, (double)my_stats[i]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kWgtWarp) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// ---------------------------------------------------------------- weight packing (TF32 blobs)
+// blob[k-step s (8 channels)][tap][plane j (2)][n][4]  <-  W, RN-rounded to TF32.  One (s, tap)
+// piece is a ready-made UMMA K-major B operand for one tcgen05.mma (N rows x 8 k).
+//   FWD  : B[n = co][k = ci]            = W[co][ci][ty][tx]
+//   DGRAD: B[n = ci][k = co] (roles swap) = W[co][ci][Th-1-ty][Tw-1-tx]
+__global__ void pack_weights_tc_kernel(const float* __restrict__ w, int Cout, int Cin, int th,
+                                       int tw, int mode, float* __restrict__ out,
+                                       int64_t total) {
+  const int taps = th * tw;
+  const int Nn = mode == AB_WMODE_FWD ? Cout : Cin;   // GEMM N (rows of B)
+  const int Kk = mode == AB_WMODE_FWD ? Cin : Cout;   // GEMM K per tap
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i;
+    const int e = r % 4; r /= 4;
+    const int nn = r % Nn; r /= Nn;
+    const int j = r % 2; r /= 2;
+    const int t = r % taps; r /= taps;
+    const int ks = (int)r;
+    const int k = ks * 8 + j * 4 + e;
+    float v = 0.f;
+    if (k < Kk) {
+      const int ty = t / tw, tx = t % tw;
+      if (mode == AB_WMODE_FWD) {
+        v = w[(((int64_t)nn * Cin + k) * th + ty) * tw + tx];
+      } else {
+        v = w[(((int64_t)k * Cin + nn) * th + (th - 1 - ty)) * tw + (tw - 1 - tx)];
+      }
+    }
+    out[i] = to_tf32(v);
+  }
+}
+
+int pick_kc(int Ctot) { return Ctot % 32 == 0 ? 32 : (Ctot % 16 == 0 ? 16 : 8); }
+
+}  // namespace
+
+// exported to api.cu ---------------------------------------------------------------
+int ab_conv_tc_supported(const ab_conv_t* d) {
+  int ctot = 0;
+  for (int i = 0; i < d->nsrc; ++i) {
+    if (d->src[i].C % 4 != 0 || d->src[i].ld % 4 != 0) return 0;
+    if (((uintptr_t)d->src[i].ptr & 15) != 0) return 0;
+    ctot += d->src[i].C;
+  }
+  if (ctot % 8 != 0) return 0;
+  if (d->Cout % 16 != 0 || d->Cout < 16 || d->Cout > 256) return 0;
+  return 1;
+}
+
+int64_t ab_pack_weights_tc_elems(int Cout, int Cin, int th, int tw, int mode) {
+  const int Nn = mode == AB_WMODE_FWD ? Cout : Cin;
+  const int Kk = mode == AB_WMODE_FWD ? Cin : Cout;
+  return (int64_t)(Kk / 8) * th * tw * 8 * Nn;
+}
+
+int ab_pack_weights_tc(const float* w, int Cout, int Cin, int th, int tw, int mode, float* out,
+                       cudaStream_t stream) {
+  const int Kk = mode == AB_WMODE_FWD ? Cin : Cout;
+  AB_CHECK(Kk % 8 == 0, "tf32 weight pack: K=%d not a multiple of 8", Kk);
+  const int64_t total = ab_pack_weights_tc_elems(Cout, Cin, th, tw, mode);
+  const int threads = 256;
+  const int blocks = (int)((total + threads - 1) / threads);
+  pack_weights_tc_kernel<<<blocks > 4096 ? 4096 : blocks, threads, 0, stream>>>(
+      w, Cout, Cin, th, tw, mode, out, total);
+  AB_LAUNCH_CHECK();
+  return 0;
+}
+
+static int conv_tc_plan(const ab_conv_t* d, ConvTcParams* p, int* smem_bytes) {
+  SrcSet S;
+  if (ab_make_srcset(d, &S)) return 1;
+  p->S = S;
+  p->N = d->N; p->H = d->H; p->W = d->W; p->Cout = d->Cout;
+  p->taps_h = d->ks_h; p->taps_w = d->ks_w; p->dil = d->dil;
+  p->alpha = d->lrelu;
+  p->act = d->act;
+  p->out_nchw = d->out_nchw;
+  p->tiles_h = (d->H + kTileH - 1) / kTileH;
+  p->tiles_w = (d->W + kTileW - 1) / kTileW;
+  p->num_tiles = d->N * p->tiles_h * p->tiles_w;
+  p->THp = kTileH + d->dil * (d->ks_h - 1);
+  p->TWp = kTileW + d->dil * (d->ks_w - 1);
+  p->HP = p->THp * p->TWp;
+  int KC = pick_kc(S.Ctot);
+  const int budget = 200 * 1024;
+  const int stats_bytes = ((kNumEpiWarps * 2 * d->Cout * 4 + 127) & ~127) + 256 + 128;
+  for (;; KC >>= 1) {
+    AB_CHECK(KC >= 8, "conv_tc: halo tile too large for shared memory (dil=%d)", d->dil);
+    if (S.Ctot % KC != 0) continue;
+    const int P = KC / 4;
+    int plane = p->HP * 16;
+    const int want = (128 / P) % 128;  // plane stride mod 128 that spreads the P planes over banks
+    plane += ((want - plane % 128) + 128) % 128;
+    p->KC = KC;
+    p->plane_bytes = plane;
+    p->a_stage_bytes = P * plane;
+    p->b_stage_bytes = KC * d->Cout * 4;
+    p->n_b = 4;
+    int avail = budget - stats_bytes - p->n_b * p->b_stage_bytes;
+    int na = avail / p->a_stage_bytes;
+    if (na >= 2) {
+      p->n_a = na > kMaxAStages ? kMaxAStages : na;
+      break;
+    }
+  }
+  p->n_chunks = S.Ctot / p->KC;
+  AB_CHECK(p->plane_bytes / 16 < (1 << 14) && p->TWp < (1 << 14), "conv_tc: descriptor overflow");
+  int cols = 32;
+  while (cols < 2 * d->Cout) cols <<= 1;
+  p->tmem_cols = cols;
+  *smem_bytes = stats_bytes + p->n_a * p->a_stage_bytes + p->n_b * p->b_stage_bytes;
+  return 0;
+}
+
+int ab_conv_tc_info(const ab_conv_t* d, int* grid, int* block, int* smem_bytes) {
+  ConvTcParams p;
+  if (conv_tc_plan(d, &p, smem_bytes)) return 1;
+  const int sms = ab_num_sms();
+  *grid = p.num_tiles < sms ? p.num_tiles : sms;
+  *block = kThreads;
+  return 0;
+}
+
+int ab_conv_tc_fwd(const ab_conv_t* d, const float* wblob, const float* bias, float* y, int ld_y,
+                   double* stats, cudaStream_t stream) {
+  ConvTcParams p;
+  int smem_bytes = 0;
+  if (conv_tc_plan(d, &p, &smem_bytes)) return 1;
+  AB_CHECK(((uintptr_t)wblob & 15) == 0 && ((uintptr_t)y & 15) == 0 && ld_y % 4 == 0,
+           "conv_tc: unaligned weight blob / output");
+  p.wblob = wblob; p.bias = bias; p.out = y; p.ld_out = ld_y; p.stats = stats;
+  static int configured_smem = 0;
+  if (smem_bytes > configured_smem) {
+    AB_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 220 * 1024));
+    configured_smem = 220 * 1024;
+  }
+  const int sms = ab_num_sms();
+  const int grid = p.num_tiles < sms ? p.num_tiles : sms;
+  if (grid == 0) return 0;
+  conv_tc_kernel<<<grid, kThreads, smem_bytes, stream>>>(p);
+  AB_LAUNCH_CHECK();
+  return 0;
+}

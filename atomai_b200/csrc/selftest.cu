@@ -1,0 +1,122 @@
+// selftest.cu — a single-CTA tcgen05 GEMM used by tests/ to pin the UMMA shared-memory
+// descriptor conventions the convolution kernels rely on (no-swizzle "interleave" core matrices,
+// K-major and MN-major, shifted starts and non-128B group strides as used by the halo-tile tap
+// addressing).  D[128][N] = A[128][K] * B[N][K]^T with TF32 operands.
+//
+// variant bit 0: swap the LBO/SBO fields (a mismatch with the documented convention shows up as a
+//                wrong result here instead of inside a convolution);
+// variant bit 1: MN-major operands (A given as A^T [K][128], B as B^T [K][N]);
+// variant bit 2: "halo" addressing — K-major A rows stored with 8-row groups at a 160 B stride and
+//                a 48 B start offset (what a tap of a 10-pixel-wide halo tile looks like).
+#include "common.cuh"
+
+namespace {
+
+__global__ void __launch_bounds__(128, 1)
+    selftest_umma_kernel(const float* __restrict__ A, const float* __restrict__ B,
+                         float* __restrict__ D, int N, int K, int variant) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const bool swap = variant & 1, mn = variant & 2, halo = variant & 4;
+
+  uint32_t a_plane, a_group, a_off, b_plane;
+  const uint32_t a_base = smem_u32(smem);
+  if (!mn) {
+    a_group = halo ? 160 : 128;                                  // bytes between 8-row groups
+    a_off = halo ? 48 : 0;
+    a_plane = 16 * a_group + 16 + (halo ? 64 : 0);               // plane = 4 k-columns
+    b_plane = N * 16 + 16;
+  } else {
+    a_group = 128; a_off = 0;
+    a_plane = K * 16 + 16;                                       // plane = 4 m-rows, K rows of 16B
+    b_plane = K * 16 + 16;
+  }
+  const uint32_t a_bytes = (mn ? 32u : (uint32_t)(K / 4)) * a_plane + 256;
+  const uint32_t b_base = a_base + ((a_bytes + 127) & ~127u);
+
+  if (!mn) {
+    for (int i = tid; i < 128 * K; i += 128) {  // A[r][k]
+      const int r = i / K, k = i % K;
+      const uint32_t addr = (k / 4) * a_plane + a_off + (r / 8) * a_group + (r % 8) * 16 + (k % 4) * 4;
+      *reinterpret_cast<float*>(smem + addr) = to_tf32(A[i]);
+    }
+    for (int i = tid; i < N * K; i += 128) {  // B[n][k]
+      const int n = i / K, k = i % K;
+      const uint32_t addr = (k / 4) * b_plane + n * 16 + (k % 4) * 4;
+      *reinterpret_cast<float*>(smem + (b_base - a_base) + addr) = to_tf32(B[i]);
+    }
+  } else {
+    for (int i = tid; i < 128 * K; i += 128) {  // A^T[k][m]
+      const int k = i / 128, m = i % 128;
+      const uint32_t addr = (m / 4) * a_plane + k * 16 + (m % 4) * 4;
+      *reinterpret_cast<float*>(smem + addr) = to_tf32(A[i]);
+    }
+    for (int i = tid; i < N * K; i += 128) {  // B^T[k][n]
+      const int k = i / N, n = i % N;
+      const uint32_t addr = (n / 4) * b_plane + k * 16 + (n % 4) * 4;
+      *reinterpret_cast<float*>(smem + (b_base - a_base) + addr) = to_tf32(B[i]);
+    }
+  }
+  if (tid == 0) {
+    mbar_init(smem_u32(&bar), 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(smem_u32(&tmem_base_s), 256);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (tid == 0) {
+    const uint32_t idesc = umma_idesc_tf32(128, N, mn ? 1 : 0, mn ? 1 : 0);
+    for (int ks = 0; ks < K / 8; ++ks) {
+      uint64_t ad, bd;
+      if (!mn) {
+        uint32_t lbo_a = a_plane, sbo_a = a_group, lbo_b = b_plane, sbo_b = 128;
+        if (swap) { uint32_t t = lbo_a; lbo_a = sbo_a; sbo_a = t; t = lbo_b; lbo_b = sbo_b; sbo_b = t; }
+        ad = umma_desc(a_base + a_off + ks * 2 * a_plane, lbo_a, sbo_a);
+        bd = umma_desc(b_base + ks * 2 * b_plane, lbo_b, sbo_b);
+      } else {
+        uint32_t lbo_a = 128, sbo_a = a_plane, lbo_b = 128, sbo_b = b_plane;
+        if (swap) { uint32_t t = lbo_a; lbo_a = sbo_a; sbo_a = t; t = lbo_b; lbo_b = sbo_b; sbo_b = t; }
+        ad = umma_desc(a_base + ks * 128, lbo_a, sbo_a);
+        bd = umma_desc(b_base + ks * 128, lbo_b, sbo_b);
+      }
+      umma_tf32(tmem_base, ad, bd, idesc, ks > 0 ? 1u : 0u);
+    }
+    umma_commit(smem_u32(&bar));
+  }
+  __syncwarp();
+  mbar_wait(smem_u32(&bar), 0);
+  tc_fence_after();
+  const int row = tid;
+  for (int c0 = 0; c0 < N; c0 += 16) {
+    float v[16];
+    tmem_ld16(tmem_base + c0 + ((uint32_t)(warp * 32) << 16), v);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) D[row * N + c0 + i] = v[i];
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+}  // namespace
+
+extern "C" int atomai_b200_selftest_umma(const float* A, const float* B, float* D, int N, int K,
+                                         int variant, void* stream) {
+  AB_CHECK(N % 16 == 0 && N >= 16 && N <= 256 && K % 8 == 0 && K >= 8 && K <= 64,
+           "selftest_umma: N=%d K=%d out of range", N, K);
+  const int smem = 160 * 1024;
+  AB_CUDA(cudaFuncSetAttribute(selftest_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               smem));
+  selftest_umma_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(A, B, D, N, K, variant);
+  AB_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,320 @@
+// vae.cu — the non-convolutional pieces of the VAE / rVAE / ImSpec / DKL paths:
+//   * a strided fp32 GEMM with optional split-K (skinny nn.Linear layers: 524288 -> latent
+//     heads of convEncoderNet, latent -> 524288 of convDecoderNet, the fcFeatureExtractor MLP);
+//   * coord_latent fused with transform_coordinates (rVAE spatial decoder, first layer).
+// Reference call sites: atomai/nets/ed.py:64,273-274,503-505 (Linear), :672-687 (coord_latent),
+// atomai/utils/coords.py:47-83, atomai/models/dgm/rvae.py:118-145, atomai/nets/gp.py:14-26.
+#include "common.cuh"
+
+namespace {
+
+constexpr int TM = 64, TN = 64, TK = 16, GT = 256;
+
+struct GemmParams {
+  const float* A; int64_t a_sm, a_sk;
+  const float* B; int64_t b_sk, b_sn;
+  float* C; int64_t c_sm;
+  int M, N, K;
+  const float* bias;
+  int act; float slope;
+  int accumulate;  // C += result (plain add when split_k == 1, atomics otherwise)
+  int split_k, k_per_split;
+};
+
+// C tile 64x64, 256 threads, 4x4 micro-tile.  Tile loads walk the contiguous axis of each
+// operand with consecutive threads (decided from the strides) so they stay coalesced for
+// NN / NT / TN shapes alike.
+__global__ void __launch_bounds__(GT) gemm_kernel(const GemmParams p) {
+  __shared__ float sA[TK][TM + 4];
+  __shared__ float sB[TK][TN + 4];
+  const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
+  const int k_begin = blockIdx.z * p.k_per_split;
+  const int k_end = min(p.K, k_begin + p.k_per_split);
+  const int tid = threadIdx.x;
+  const int tm = (tid >> 4) * 4, tn = (tid & 15) * 4;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  const bool a_k_fast = p.a_sk == 1;  // A contiguous along k
+  const bool b_n_fast = p.b_sn == 1;  // B contiguous along n
+
+  for (int k0 = k_begin; k0 < k_end; k0 += TK) {
+    __syncthreads();
+    for (int i = tid; i < TM * TK; i += GT) {
+      int m, k;
+      if (a_k_fast) { k = i % TK; m = i / TK; } else { m = i % TM; k = i / TM; }
+      float v = 0.f;
+      if (m0 + m < p.M && k0 + k < k_end) v = __ldg(p.A + (int64_t)(m0 + m) * p.a_sm + (int64_t)(k0 + k) * p.a_sk);
+      sA[k][m] = v;
+    }
+    for (int i = tid; i < TN * TK; i += GT) {
+      int n, k;
+      if (b_n_fast) { n = i % TN; k = i / TN; } else { k = i % TK; n = i / TK; }
+      float v = 0.f;
+      if (n0 + n < p.N && k0 + k < k_end) v = __ldg(p.B + (int64_t)(k0 + k) * p.b_sk + (int64_t)(n0 + n) * p.b_sn);
+      sB[k][n] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < TK; ++k) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&sA[k][tm]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&sB[k][tn]);
+      const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+      const float bv[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + tm + i;
+    if (m >= p.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tn + j;
+      if (n >= p.N) continue;
+      float* c = p.C + (int64_t)m * p.c_sm + n;
+      if (p.split_k > 1) {
+        atomicAdd(c, acc[i][j]);
+      } else {
+        float v = acc[i][j] + (p.bias ? __ldg(p.bias + n) : 0.f);
+        v = act_f(v, p.act, p.slope);
+        *c = p.accumulate ? *c + v : v;
+      }
+    }
+  }
+}
+
+__global__ void bias_fill_kernel(float* C, int64_t c_sm, int M, int N, const float* bias) {
+  const int64_t total = (int64_t)M * N;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int n = (int)(i % N);
+    C[(i / N) * c_sm + n] = bias ? bias[n] : 0.f;
+  }
+}
+
+// ---------------------------------------------------------------- coord_latent
+struct CoordDev {
+  int B, H, W, zdim, hid, tanh_act;
+  const float *z, *phi, *dx, *wc, *bc, *wz;
+};
+
+__device__ __forceinline__ void grid_xy(const CoordDev& d, int p, float& gx, float& gy) {
+  // imcoordgrid (atomai/utils/coords.py:47-54): x = linspace(-1,1,H)[i] slowest, y = linspace(1,-1,W)[j]
+  const int i = p / d.W, j = p - i * d.W;
+  gx = d.H > 1 ? -1.f + 2.f * i / (float)(d.H - 1) : -1.f;
+  gy = d.W > 1 ? 1.f - 2.f * j / (float)(d.W - 1) : 1.f;
+}
+__device__ __forceinline__ void xform(const CoordDev& d, int b, float gx, float gy, float& x,
+                                      float& y, float& c, float& s) {
+  c = 1.f; s = 0.f;
+  if (d.phi) { sincosf(d.phi[b], &s, &c); }
+  // coord @ [[c, s], [-s, c]] + dx  (atomai/utils/coords.py:78-83)
+  x = gx * c - gy * s;
+  y = gx * s + gy * c;
+  if (d.dx) { x += d.dx[b * 2]; y += d.dx[b * 2 + 1]; }
+}
+
+// grid: (pixel chunks, B); block 128 threads = hidden lanes (hid <= 1024 handled by a loop)
+__global__ void coord_latent_fwd_kernel(const CoordDev d, float* __restrict__ h0, int px_per_cta) {
+  extern __shared__ float s_hz[];  // [hid]: bc + Wz z_b
+  const int b = blockIdx.y, HW = d.H * d.W;
+  for (int h = threadIdx.x; h < d.hid; h += blockDim.x) {
+    float acc = d.bc ? d.bc[h] : 0.f;
+    for (int k = 0; k < d.zdim; ++k) acc = fmaf(d.wz[h * d.zdim + k], d.z[b * d.zdim + k], acc);
+    s_hz[h] = acc;
+  }
+  __syncthreads();
+  const int p0 = blockIdx.x * px_per_cta, p1 = min(HW, p0 + px_per_cta);
+  for (int p = p0; p < p1; ++p) {
+    float gx, gy, x, y, c, s;
+    grid_xy(d, p, gx, gy);
+    xform(d, b, gx, gy, x, y, c, s);
+    float* o = h0 + ((int64_t)b * HW + p) * d.hid;
+    for (int h = threadIdx.x; h < d.hid; h += blockDim.x) {
+      float v = fmaf(d.wc[h * 2], x, fmaf(d.wc[h * 2 + 1], y, s_hz[h]));
+      o[h] = d.tanh_act ? tanhf(v) : v;
+    }
+  }
+}
+
+__global__ void coord_latent_bwd_kernel(const CoordDev d, const float* __restrict__ dpre,
+                                        float* dwc, float* dbc, float* sb, float* dphi,
+                                        float* ddx, int px_per_cta) {
+  extern __shared__ float s_red[];  // [3][blockDim] scratch for (gxsum, gysum, gphi)
+  const int b = blockIdx.y, HW = d.H * d.W;
+  const int p0 = blockIdx.x * px_per_cta, p1 = min(HW, p0 + px_per_cta);
+  float a_dx = 0.f, a_dy = 0.f, a_phi = 0.f;
+  // per hidden lane partials (thread h owns lanes h, h+blockDim, ...; hid <= 4*blockDim)
+  float s0[4] = {0, 0, 0, 0}, sx[4] = {0, 0, 0, 0}, sy[4] = {0, 0, 0, 0};
+  for (int p = p0; p < p1; ++p) {
+    float gx, gy, x, y, c, s;
+    grid_xy(d, p, gx, gy);
+    xform(d, b, gx, gy, x, y, c, s);
+    const float* g = dpre + ((int64_t)b * HW + p) * d.hid;
+    float px = 0.f, py = 0.f;
+    int u = 0;
+    for (int h = threadIdx.x; h < d.hid; h += blockDim.x, ++u) {
+      const float gv = g[h];
+      s0[u] += gv;
+      sx[u] = fmaf(gv, x, sx[u]);
+      sy[u] = fmaf(gv, y, sy[u]);
+      px = fmaf(gv, d.wc[h * 2], px);
+      py = fmaf(gv, d.wc[h * 2 + 1], py);
+    }
+    // this thread's share of d(loss)/d(x', y') for pixel p; reduced over threads at the end
+    a_dx += px;
+    a_dy += py;
+    a_phi += px * (-gx * s - gy * c) + py * (gx * c - gy * s);
+  }
+  int u = 0;
+  for (int h = threadIdx.x; h < d.hid; h += blockDim.x, ++u) {
+    atomicAdd(dbc + h, s0[u]);
+    atomicAdd(dwc + h * 2, sx[u]);
+    atomicAdd(dwc + h * 2 + 1, sy[u]);
+    atomicAdd(sb + (int64_t)b * d.hid + h, s0[u]);
+  }
+  s_red[threadIdx.x] = a_dx;
+  s_red[blockDim.x + threadIdx.x] = a_dy;
+  s_red[2 * blockDim.x + threadIdx.x] = a_phi;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+    for (int i = 0; i < (int)blockDim.x; ++i) {
+      t0 += s_red[i];
+      t1 += s_red[blockDim.x + i];
+      t2 += s_red[2 * blockDim.x + i];
+    }
+    if (ddx) { atomicAdd(ddx + b * 2, t0); atomicAdd(ddx + b * 2 + 1, t1); }
+    if (dphi) atomicAdd(dphi + b, t2);
+  }
+}
+
+int to_dev(const ab_coordlat_t* d, CoordDev* o) {
+  AB_CHECK(d && d->B > 0 && d->H > 0 && d->W > 0 && d->hid > 0 && d->zdim >= 0, "coord_latent: bad dims");
+  AB_CHECK(d->hid <= 512, "coord_latent: hid=%d > 512 unsupported", d->hid);
+  AB_CHECK(d->wc && (d->zdim == 0 || (d->z && d->wz)), "coord_latent: null weights");
+  o->B = d->B; o->H = d->H; o->W = d->W; o->zdim = d->zdim; o->hid = d->hid;
+  o->tanh_act = d->tanh_act; o->z = d->z; o->phi = d->phi; o->dx = d->dx; o->wc = d->wc;
+  o->bc = d->bc; o->wz = d->wz;
+  return 0;
+}
+
+}  // namespace
+
+int ab_colsum(const float* dy, int B, int O, float* db, cudaStream_t st);  // db[o] = sum_b dy[b][o]
+
+extern "C" {
+
+int atomai_b200_gemm(const float* A, int64_t a_sm, int64_t a_sk, const float* B, int64_t b_sk,
+                     int64_t b_sn, float* C, int64_t c_sm, int M, int N, int K, const float* bias,
+                     int act, float slope, int accumulate, int split_k, void* stream) {
+  AB_CHECK(A && B && C, "gemm: null pointer");
+  AB_CHECK(M >= 0 && N >= 0 && K >= 0, "gemm: negative dims");
+  if (M == 0 || N == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (split_k < 1) split_k = 1;
+  GemmParams p{A, a_sm, a_sk, B, b_sk, b_sn, C, c_sm, M, N, K, bias, act, slope, accumulate,
+               split_k, 0};
+  int kps = (K + split_k - 1) / split_k;
+  kps = (kps + TK - 1) / TK * TK;
+  if (kps < TK) kps = TK;
+  p.k_per_split = kps;
+  p.split_k = (K + kps - 1) / kps;
+  if (p.split_k < 1) p.split_k = 1;
+  if (p.split_k > 1) {
+    AB_CHECK(act == AB_ACT_LRELU && slope == 1.f, "gemm: split-K needs an identity epilogue");
+    if (!accumulate) {
+      bias_fill_kernel<<<ab_num_sms(), 256, 0, st>>>(C, c_sm, M, N, bias);
+      AB_LAUNCH_CHECK();
+    }
+  }
+  dim3 grid((N + TN - 1) / TN, (M + TM - 1) / TM, p.split_k);
+  AB_CHECK(grid.y <= 65535 && grid.z <= 65535, "gemm: grid too large");
+  gemm_kernel<<<grid, GT, 0, st>>>(p);
+  AB_LAUNCH_CHECK();
+  return 0;
+}
+
+// y[B][O] = x[B][K] W[O][K]^T + b   — nn.Linear forward
+int atomai_b200_linear_fwd(const float* x, const float* w, const float* b, float* y, int B, int K,
+                           int O, void* stream) {
+  // split K so that roughly 2 waves of CTAs exist even for a 100 x 5 output
+  const int tiles = ((B + TM - 1) / TM) * ((O + TN - 1) / TN);
+  int split = (2 * ab_num_sms() + tiles - 1) / tiles;
+  const int max_split = (K + 4 * TK - 1) / (4 * TK);
+  if (split > max_split) split = max_split;
+  if (split < 1) split = 1;
+  return atomai_b200_gemm(x, K, 1, w, 1, K, y, O, B, O, K, b, AB_ACT_LRELU, 1.f, 0, split, stream);
+}
+
+// dx[B][K] = dy[B][O] W[O][K];  dW[O][K] = dy^T x;  db[O] = sum_b dy   (all overwrite)
+int atomai_b200_linear_bwd(const float* x, const float* w, const float* dy, float* dx, float* dw,
+                           float* db, int B, int K, int O, void* stream) {
+  if (dx) {
+    if (atomai_b200_gemm(dy, O, 1, w, K, 1, dx, K, B, K, O, nullptr, AB_ACT_LRELU, 1.f, 0, 1, stream))
+      return 1;
+  }
+  if (dw) {
+    if (atomai_b200_gemm(dy, 1, O, x, K, 1, dw, K, O, K, B, nullptr, AB_ACT_LRELU, 1.f, 0, 1, stream))
+      return 1;
+  }
+  if (db) {
+    if (ab_colsum(dy, B, O, db, (cudaStream_t)stream)) return 1;
+  }
+  return 0;
+}
+
+int atomai_b200_coord_latent_fwd(const ab_coordlat_t* d, float* h0, void* stream) {
+  CoordDev dev;
+  if (to_dev(d, &dev)) return 1;
+  AB_CHECK(h0, "coord_latent_fwd: null output");
+  const int HW = d->H * d->W;
+  int chunks = (4 * ab_num_sms() + d->B - 1) / d->B;
+  if (chunks > HW) chunks = HW;
+  if (chunks < 1) chunks = 1;
+  const int ppc = (HW + chunks - 1) / chunks;
+  dim3 grid((HW + ppc - 1) / ppc, d->B);
+  coord_latent_fwd_kernel<<<grid, 128, d->hid * sizeof(float), (cudaStream_t)stream>>>(dev, h0, ppc);
+  AB_LAUNCH_CHECK();
+  return 0;
+}
+
+int atomai_b200_coord_latent_bwd(const ab_coordlat_t* d, const float* dpre0, float* dwc, float* dbc,
+                                 float* sb, float* dphi, float* ddx, void* stream) {
+  CoordDev dev;
+  if (to_dev(d, &dev)) return 1;
+  AB_CHECK(dpre0 && dwc && dbc && sb, "coord_latent_bwd: null pointer");
+  const int HW = d->H * d->W;
+  int chunks = (4 * ab_num_sms() + d->B - 1) / d->B;
+  if (chunks > HW) chunks = HW;
+  if (chunks < 1) chunks = 1;
+  const int ppc = (HW + chunks - 1) / chunks;
+  dim3 grid((HW + ppc - 1) / ppc, d->B);
+  coord_latent_bwd_kernel<<<grid, 128, 3 * 128 * sizeof(float), (cudaStream_t)stream>>>(
+      dev, dpre0, dwc, dbc, sb, dphi, ddx, ppc);
+  AB_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"
+
+namespace {
+__global__ void colsum_kernel(const float* __restrict__ dy, int B, int O, float* __restrict__ db) {
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= O) return;
+  float acc = 0.f;
+  for (int b = 0; b < B; ++b) acc += dy[(int64_t)b * O + o];
+  db[o] = acc;
+}
+}  // namespace
+int ab_colsum(const float* dy, int B, int O, float* db, cudaStream_t st) {
+  colsum_kernel<<<(O + 127) / 128, 128, 0, st>>>(dy, B, O, db);
+  AB_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,229 @@
+"""
+Thin tensor-level wrappers over the C ABI (include/atomai_b200.h).
+
+torch is used here for device memory and the current stream only; every
+function launches hand-written sm_100a kernels from libatomai_b200.so and
+raises if that library is unavailable.  Activations are NHWC fp32 tensors of
+shape (N, H, W, C); a channel slice of a wider tensor is passed as a view whose
+last-dim stride is 1 (its pixel stride `ld` is read from the strides).
+"""
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _C
+from ._C import (ACT_LRELU, ACT_TANH, MATH_FP32, MATH_TF32, WMODE_DGRAD, WMODE_FWD, check,
+                 lib, ptr, stream_ptr)
+
+
+def _ld(t: torch.Tensor) -> int:
+    """Pixel stride of an NHWC (view) tensor; validates the layout."""
+    assert t.dtype == torch.float32 and t.is_cuda, "fp32 CUDA tensor expected"
+    assert t.dim() == 4 and t.stride(3) == 1, f"NHWC view expected, strides {t.stride()}"
+    ld = t.stride(2)
+    assert t.stride(1) == ld * t.shape[2] and t.stride(0) == ld * t.shape[2] * t.shape[1], \
+        f"pixel-major layout expected, got shape {tuple(t.shape)} strides {t.stride()}"
+    return ld
+
+
+class Source:
+    """One conv input: NHWC tensor + optional pending BN affine + optional pending 2x2 pool."""
+    __slots__ = ("t", "scale", "shift", "pool")
+
+    def __init__(self, t, scale=None, shift=None, pool=False):
+        self.t, self.scale, self.shift, self.pool = t, scale, shift, bool(pool)
+
+    @property
+    def C(self):
+        return self.t.shape[3]
+
+
+def conv_desc(srcs: Sequence[Source], N, H, W, Cout, ks=(3, 3), dil=1, lrelu=1.0,
+              math=MATH_TF32, out_nchw=False, act=ACT_LRELU) -> _C.Conv:
+    d = _C.Conv()
+    d.N, d.H, d.W, d.Cout = N, H, W, Cout
+    d.ks_h, d.ks_w, d.dil = ks[0], ks[1], dil
+    d.nsrc = len(srcs)
+    for i, s in enumerate(srcs):
+        e = d.src[i]
+        e.ptr = s.t.data_ptr()
+        e.scale = ptr(s.scale)
+        e.shift = ptr(s.shift)
+        e.C = s.t.shape[3]
+        e.ld = _ld(s.t)
+        e.pool = 1 if s.pool else 0
+        sh, sw = s.t.shape[1], s.t.shape[2]
+        if s.pool:
+            assert (sh, sw) == (2 * H, 2 * W), f"pooled source must be {(2*H, 2*W)}, got {(sh, sw)}"
+        else:
+            assert (sh, sw) == (H, W), f"source spatial {(sh, sw)} != {(H, W)}"
+        assert s.t.shape[0] == N
+    d.lrelu = float(lrelu)
+    d.math = math
+    d.out_nchw = 1 if out_nchw else 0
+    d.act = act
+    return d
+
+
+def tc_supported(srcs: Sequence[Source], Cout: int) -> bool:
+    """Shapes the tcgen05 conv path takes (mirrors ab_conv_tc_supported)."""
+    ctot = sum(s.C for s in srcs)
+    return (all(s.C % 4 == 0 and _ld(s.t) % 4 == 0 and s.t.data_ptr() % 16 == 0 for s in srcs)
+            and ctot % 8 == 0 and Cout % 16 == 0 and 16 <= Cout <= 256)
+
+
+def wgrad_tc_supported(srcs: Sequence[Source], Cout: int, ks, dil) -> bool:
+    ctot = sum(s.C for s in srcs)
+    return (all(s.C % 4 == 0 and _ld(s.t) % 4 == 0 and s.t.data_ptr() % 16 == 0 for s in srcs)
+            and ctot % 16 == 0 and Cout % 4 == 0 and dil <= 2)
+
+
+def prep_weights(w_oihw: torch.Tensor, mode: int, math: int) -> torch.Tensor:
+    """OIHW (or OIW for 1-D) conv weight -> kernel layout for `math` / `mode`."""
+    w = w_oihw.detach()
+    if w.dim() == 3:
+        w = w.unsqueeze(2)
+    w = w.contiguous()
+    Cout, Cin, kh, kw = w.shape
+    n = lib().atomai_b200_prep_weights_elems(Cout, Cin, kh, kw, mode, math)
+    out = torch.empty(n, device=w.device, dtype=torch.float32)
+    check(lib().atomai_b200_prep_weights(ptr(w), Cout, Cin, kh, kw, mode, math, ptr(out),
+                                         stream_ptr()))
+    return out
+
+
+def conv_fwd(d: _C.Conv, w_prepped, bias, out: torch.Tensor, stats=None) -> None:
+    ld_y = d.Cout if d.out_nchw else _ld(out)
+    check(lib().atomai_b200_conv_fwd(C.byref(d), ptr(w_prepped), ptr(bias), ptr(out), ld_y,
+                                     ptr(stats), stream_ptr()))
+
+
+def conv_wgrad(d: _C.Conv, dy: torch.Tensor, dw_oihw: torch.Tensor) -> None:
+    check(lib().atomai_b200_conv_wgrad(C.byref(d), ptr(dy), _ld(dy), ptr(dw_oihw), stream_ptr()))
+
+
+def bn_finalize(stats, count, gamma, beta, rmean, rvar, momentum, eps, training, scale, shift,
+                mean=None, invstd=None) -> None:
+    check(lib().atomai_b200_bn_finalize(ptr(stats), scale.numel(), float(count), ptr(gamma),
+                                        ptr(beta), ptr(rmean), ptr(rvar), momentum, eps,
+                                        1 if training else 0, ptr(scale), ptr(shift), ptr(mean),
+                                        ptr(invstd), stream_ptr()))
+
+
+def affine(a: torch.Tensor, scale, shift, out: torch.Tensor, out_nchw=False) -> None:
+    N, H, W, Cc = a.shape
+    check(lib().atomai_b200_affine(ptr(a), _ld(a), ptr(scale), ptr(shift), ptr(out),
+                                   Cc if out_nchw else _ld(out), N * H * W, Cc,
+                                   H * W if out_nchw else 0, stream_ptr()))
+
+
+def bn_bwd_reduce(dy, a, mean, invstd, sums) -> None:
+    N, H, W, Cc = a.shape
+    check(lib().atomai_b200_bn_bwd_reduce(ptr(dy), _ld(dy), ptr(a), _ld(a), ptr(mean),
+                                          ptr(invstd), N * H * W, Cc, ptr(sums), stream_ptr()))
+
+
+def bn_act_bwd(dy, a, mean, invstd, scale, sums, count, extra, act, slope, dpre, dbias) -> None:
+    N, H, W, Cc = a.shape
+    check(lib().atomai_b200_bn_lrelu_bwd(
+        ptr(dy), _ld(dy) if dy is not None else 0, ptr(a), _ld(a), ptr(mean), ptr(invstd),
+        ptr(scale), ptr(sums), float(count), ptr(extra), _ld(extra) if extra is not None else 0,
+        act, float(slope), ptr(dpre), _ld(dpre), ptr(dbias), N * H * W, Cc, stream_ptr()))
+
+
+def pool_fwd(a, scale, shift, out) -> None:
+    N, Ho, Wo, Cc = out.shape
+    check(lib().atomai_b200_pool2x2_fwd(ptr(a), _ld(a), ptr(scale), ptr(shift), ptr(out),
+                                        _ld(out), N, Ho, Wo, Cc, stream_ptr()))
+
+
+def pool_bwd(dp, a, scale, shift, dfull, accumulate) -> None:
+    N, Ho, Wo, Cc = dp.shape
+    check(lib().atomai_b200_pool2x2_bwd(ptr(dp), _ld(dp), ptr(a), _ld(a), ptr(scale), ptr(shift),
+                                        ptr(dfull), _ld(dfull), 1 if accumulate else 0, N, Ho, Wo,
+                                        Cc, stream_ptr()))
+
+
+def upsample_fwd(x, out, bilinear=True) -> None:
+    N, h, w, Cc = x.shape
+    check(lib().atomai_b200_upsample2x_fwd(ptr(x), _ld(x), ptr(out), _ld(out), N, h, w, Cc,
+                                           1 if bilinear else 0, stream_ptr()))
+
+
+def upsample_bwd(dy, dx, bilinear=True) -> None:
+    N, h, w, Cc = dx.shape
+    check(lib().atomai_b200_upsample2x_bwd(ptr(dy), _ld(dy), ptr(dx), _ld(dx), N, h, w, Cc,
+                                           1 if bilinear else 0, stream_ptr()))
+
+
+def add_slice(src, dst, accumulate) -> None:
+    N, H, W, Cc = src.shape
+    check(lib().atomai_b200_add_slice(ptr(src), _ld(src), ptr(dst), _ld(dst),
+                                      1 if accumulate else 0, N * H * W, Cc, stream_ptr()))
+
+
+def dilated_sum(a_list, scale_list, shift_list, slope, out) -> None:
+    n = len(a_list)
+    arr = C.c_void_p * n
+    a = arr(*[t.data_ptr() for t in a_list])
+    sc = arr(*[ptr(t) for t in scale_list])
+    sh = arr(*[ptr(t) for t in shift_list])
+    check(lib().atomai_b200_dilated_sum(a, sc, sh, n, float(slope), ptr(out), out.numel(),
+                                        out.shape[-1], stream_ptr()))
+
+
+def ce_fwd_bwd(logits_nhwc, labels, loss_sum, dlogits=None, gscale=1.0) -> None:
+    N, H, W, Cc = logits_nhwc.shape
+    assert labels.dtype == torch.int64 and labels.is_contiguous()
+    check(lib().atomai_b200_ce_fwd_bwd(ptr(logits_nhwc), _ld(logits_nhwc), ptr(labels),
+                                       N * H * W, Cc, ptr(loss_sum), ptr(dlogits),
+                                       _ld(dlogits) if dlogits is not None else 0, float(gscale),
+                                       stream_ptr()))
+
+
+def pointwise_loss(pred, target, kind, loss_sum, dpred=None, gscale=1.0) -> None:
+    assert pred.is_contiguous() and target.is_contiguous() and pred.numel() == target.numel()
+    check(lib().atomai_b200_pointwise_loss(ptr(pred), ptr(target), pred.numel(), kind,
+                                           ptr(loss_sum), ptr(dpred), float(gscale), stream_ptr()))
+
+
+def sqerr_reduce(x, xhat, out, dxhat=None, gscale=1.0) -> None:
+    check(lib().atomai_b200_sqerr_reduce(ptr(x), ptr(xhat), x.numel(), ptr(out), ptr(dxhat),
+                                         float(gscale), stream_ptr()))
+
+
+def adam_multi(table_dev, n, max_numel, lr, b1, b2, eps, wd, step, grad_scale=1.0) -> None:
+    check(lib().atomai_b200_adam_multi(ptr(table_dev), n, max_numel, lr, b1, b2, eps, wd, step,
+                                       grad_scale, stream_ptr()))
+
+
+def gemm(A, a_sm, a_sk, B, b_sk, b_sn, Cm, c_sm, M, N, K, bias=None, act=ACT_LRELU, slope=1.0,
+         accumulate=False, split_k=1) -> None:
+    check(lib().atomai_b200_gemm(ptr(A), a_sm, a_sk, ptr(B), b_sk, b_sn, ptr(Cm), c_sm, M, N, K,
+                                 ptr(bias), act, float(slope), 1 if accumulate else 0, split_k,
+                                 stream_ptr()))
+
+
+def linear_fwd(x, w, b, y) -> None:
+    Bn, K = x.shape
+    O = w.shape[0]
+    check(lib().atomai_b200_linear_fwd(ptr(x), ptr(w), ptr(b), ptr(y), Bn, K, O, stream_ptr()))
+
+
+def linear_bwd(x, w, dy, dx, dw, db) -> None:
+    Bn, K = x.shape
+    O = w.shape[0]
+    check(lib().atomai_b200_linear_bwd(ptr(x), ptr(w), ptr(dy), ptr(dx), ptr(dw), ptr(db), Bn, K,
+                                       O, stream_ptr()))
+
+
+def gram(x1, x2, inv_ls, outputscale, kind, out) -> None:
+    n1, d = x1.shape
+    n2 = x2.shape[0]
+    check(lib().atomai_b200_gram(ptr(x1), ptr(x2), ptr(inv_ls), float(outputscale), n1, n2, d,
+                                 kind, ptr(out), out.stride(0), stream_ptr()))
+
+
+def selftest_umma(A, B, D, N, K, variant) -> None:
+    check(lib().atomai_b200_selftest_umma(ptr(A), ptr(B), ptr(D), N, K, variant, stream_ptr()))
