@@ -90,8 +90,8 @@ SIGNATURES = {
     "atomai_b200_add_slice": (_i, [_vp, _i, _vp, _i, _i, _i64, _i, _vp]),
     "atomai_b200_dilated_sum": (_i, [C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), _i, _f, _vp,
                                      _i64, _i, _vp]),
-    "atomai_b200_ce_fwd_bwd": (_i, [_vp, _i, _vp, _i64, _i, _vp, _vp, _i, _f, _vp]),
-    "atomai_b200_pointwise_loss": (_i, [_vp, _vp, _i64, _i, _vp, _vp, _f, _vp]),
+    "atomai_b200_ce_fwd_bwd": (_i, [_vp, _i, _vp, _i64, _i, _vp, _vp, _i, _f, _vp, _vp]),
+    "atomai_b200_pointwise_loss": (_i, [_vp, _vp, _i64, _i, _vp, _vp, _f, _vp, _vp]),
     "atomai_b200_adam_multi": (_i, [_vp, _i, _i64, _f, _f, _f, _f, _f, _i, _f, _vp]),
     "atomai_b200_linear_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "atomai_b200_linear_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
@@ -100,7 +100,7 @@ SIGNATURES = {
     "atomai_b200_coord_latent_fwd": (_i, [C.POINTER(CoordLat), _vp, _vp]),
     "atomai_b200_coord_latent_bwd": (_i, [C.POINTER(CoordLat), _vp, _vp, _vp, _vp, _vp, _vp,
                                           _vp]),
-    "atomai_b200_sqerr_reduce": (_i, [_vp, _vp, _i64, _vp, _vp, _f, _vp]),
+    "atomai_b200_sqerr_reduce": (_i, [_vp, _vp, _i64, _vp, _vp, _f, _vp, _vp]),
     "atomai_b200_gram": (_i, [_vp, _vp, _vp, _f, _i, _i, _i, _i, _vp, _i64, _vp]),
     "atomai_b200_selftest_umma": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
 }

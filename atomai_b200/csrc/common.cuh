@@ -171,6 +171,18 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
   d |= (uint64_t)1 << 46;
   return d;
 }
+// Same, with an explicit layout type (1 = SWIZZLE_128B_BASE32B, the only legal layout for
+// MN-major TF32 operands) and swizzle base offset.
+__device__ __forceinline__ uint64_t umma_desc_ex(uint32_t saddr, uint32_t lbo_bytes,
+                                                 uint32_t sbo_bytes, uint32_t layout_type,
+                                                 uint32_t base_offset) {
+  uint64_t d = umma_desc(saddr, lbo_bytes, sbo_bytes);
+  d |= (uint64_t)(base_offset & 7) << 49;
+  d |= (uint64_t)(layout_type & 7) << 61;
+  return d;
+}
+// byte-address swizzle of SWIZZLE_128B_BASE32B: 32 B chunk index ^= (128 B row index mod 4)
+__device__ __forceinline__ uint32_t swz128_32(uint32_t a) { return a ^ (((a >> 7) & 3u) << 5); }
 // Instruction descriptor, kind::tf32, fp32 accumulate.
 __host__ __device__ __forceinline__ uint32_t umma_idesc_tf32(int M, int N, int a_mn_major,
                                                              int b_mn_major) {

@@ -338,8 +338,9 @@ __global__ void __launch_bounds__(kT) ce_kernel(const float* __restrict__ logits
                                                 const int64_t* __restrict__ labels, int64_t npix,
                                                 int C, double* loss_sum,
                                                 float* __restrict__ dlogits, int ld_d,
-                                                float gscale) {
+                                                float gscale, const float* gscale_dev) {
   float local = 0.f;
+  if (gscale_dev) gscale *= __ldg(gscale_dev);
   for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < npix;
        p += (int64_t)gridDim.x * blockDim.x) {
     const float* l = logits + p * ld;
@@ -365,7 +366,7 @@ __global__ void __launch_bounds__(kT) ce_kernel(const float* __restrict__ logits
   if (threadIdx.x == 0) {
     float t = 0.f;
     for (int i = 0; i < kT / 32; ++i) t += red[i];
-    atomicAdd(loss_sum, (double)t);
+    if (loss_sum) atomicAdd(loss_sum, (double)t);
   }
 }
 
@@ -373,8 +374,10 @@ __global__ void __launch_bounds__(kT) pointwise_loss_kernel(const float* __restr
                                                             const float* __restrict__ tgt,
                                                             int64_t n, int kind, double* loss_sum,
                                                             float* __restrict__ dpred,
-                                                            float gscale) {
+                                                            float gscale,
+                                                            const float* gscale_dev) {
   float local = 0.f;
+  if (gscale_dev) gscale *= __ldg(gscale_dev);
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x) {
     const float x = pred[i], t = tgt[i];
@@ -394,15 +397,16 @@ __global__ void __launch_bounds__(kT) pointwise_loss_kernel(const float* __restr
   if (threadIdx.x == 0) {
     float t = 0.f;
     for (int i = 0; i < kT / 32; ++i) t += red[i];
-    atomicAdd(loss_sum, (double)t);
+    if (loss_sum) atomicAdd(loss_sum, (double)t);
   }
 }
 
 __global__ void __launch_bounds__(kT) sqerr_kernel(const float* __restrict__ x,
                                                    const float* __restrict__ xhat, int64_t n,
                                                    double* out, float* __restrict__ dxhat,
-                                                   float gscale) {
+                                                   float gscale, const float* gscale_dev) {
   float local = 0.f;
+  if (gscale_dev) gscale *= __ldg(gscale_dev);
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x) {
     const float d = xhat[i] - x[i];
@@ -416,7 +420,7 @@ __global__ void __launch_bounds__(kT) sqerr_kernel(const float* __restrict__ x,
   if (threadIdx.x == 0) {
     float t = 0.f;
     for (int i = 0; i < kT / 32; ++i) t += red[i];
-    atomicAdd(out, 0.5 * (double)t);
+    if (out) atomicAdd(out, 0.5 * (double)t);
   }
 }
 
@@ -570,28 +574,29 @@ int atomai_b200_dilated_sum(const float* const* a_ptrs, const float* const* scal
 
 int atomai_b200_ce_fwd_bwd(const float* logits, int ld, const int64_t* labels, int64_t npix, int C,
                            double* loss_sum, float* dlogits, int ld_d, float gscale,
-                           void* stream) {
+                           const float* gscale_dev, void* stream) {
   if (npix == 0) return 0;
   ce_kernel<<<grid_for(npix), kT, 0, STREAM>>>(logits, ld, labels, npix, C, loss_sum, dlogits,
-                                               ld_d, gscale);
+                                               ld_d, gscale, gscale_dev);
   AB_LAUNCH_CHECK();
   return 0;
 }
 
 int atomai_b200_pointwise_loss(const float* pred, const float* target, int64_t n, int kind,
-                               double* loss_sum, float* dpred, float gscale, void* stream) {
+                               double* loss_sum, float* dpred, float gscale,
+                               const float* gscale_dev, void* stream) {
   AB_CHECK(kind == 0 || kind == 1, "pointwise_loss: kind=%d", kind);
   if (n == 0) return 0;
   pointwise_loss_kernel<<<grid_for(n), kT, 0, STREAM>>>(pred, target, n, kind, loss_sum, dpred,
-                                                        gscale);
+                                                        gscale, gscale_dev);
   AB_LAUNCH_CHECK();
   return 0;
 }
 
 int atomai_b200_sqerr_reduce(const float* x, const float* xhat, int64_t n, double* out,
-                             float* dxhat, float gscale, void* stream) {
+                             float* dxhat, float gscale, const float* gscale_dev, void* stream) {
   if (n == 0) return 0;
-  sqerr_kernel<<<grid_for(n), kT, 0, STREAM>>>(x, xhat, n, out, dxhat, gscale);
+  sqerr_kernel<<<grid_for(n), kT, 0, STREAM>>>(x, xhat, n, out, dxhat, gscale, gscale_dev);
   AB_LAUNCH_CHECK();
   return 0;
 }

@@ -6,6 +6,10 @@
 // variant bit 0: swap the LBO/SBO fields (a mismatch with the documented convention shows up as a
 //                wrong result here instead of inside a convolution);
 // variant bit 1: MN-major operands (A given as A^T [K][128], B as B^T [K][N]);
+// variant >= 8: MN-major operands in the SWIZZLE_128B_BASE32B layout (rows = k at a 128 B pitch,
+//                32 m/n elements per row, 32 B chunks XOR-swizzled by row index mod 4):
+//                bit 0 swaps LBO/SBO, bits 1-2 shift the tile start by 1..3 rows (tap addressing),
+//                bit 4 (variant >= 16) additionally sets the descriptor base_offset to (start>>7)&7;
 // variant bit 2: "halo" addressing — K-major A rows stored with 8-row groups at a 160 B stride and
 //                a 48 B start offset (what a tap of a 10-pixel-wide halo tile looks like).
 #include "common.cuh"
@@ -19,6 +23,59 @@ __global__ void __launch_bounds__(128, 1)
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5;
+  if (variant >= 8) {
+    // ---------------- MN-major, SWIZZLE_128B_BASE32B ----------------
+    const bool swap8 = variant & 1;
+    const uint32_t shift = (variant >> 1) & 3, use_bo = (variant >> 4) & 1;
+    const uint32_t base0 = (smem_u32(smem) + 1023) & ~1023u;
+    const uint32_t chunk = ((uint32_t)K + 8) * 128;               // stride between 32-wide m/n chunks
+    const uint32_t lboA = (chunk + 1023) & ~1023u;
+    const uint32_t a0 = base0 + shift * 128;
+    const uint32_t b0 = base0 + 4 * lboA + 1024 + shift * 128;
+    uint8_t* gen0 = smem - smem_u32(smem);                         // generic pointer of smem offset 0
+    for (int i = tid; i < 128 * K; i += 128) {                     // A^T[k][m]
+      const int k = i / 128, m = i % 128;
+      const uint32_t la = a0 + (m / 32) * lboA + k * 128 + (m % 32) * 4;
+      *reinterpret_cast<float*>(gen0 + swz128_32(la)) = to_tf32(A[i]);
+    }
+    for (int i = tid; i < N * K; i += 128) {                       // B^T[k][n]
+      const int k = i / N, n = i % N;
+      const uint32_t la = b0 + (n / 32) * lboA + k * 128 + (n % 32) * 4;
+      *reinterpret_cast<float*>(gen0 + swz128_32(la)) = to_tf32(B[i]);
+    }
+    if (tid == 0) { mbar_init(smem_u32(&bar), 1); fence_barrier_init(); }
+    if (warp == 0) tmem_alloc(smem_u32(&tmem_base_s), 256);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+    if (tid == 0) {
+      const uint32_t idesc = umma_idesc_tf32(128, N, 1, 1);
+      for (int ks = 0; ks < K / 8; ++ks) {
+        uint32_t lbo = lboA, sbo = 512;
+        if (swap8) { lbo = 512; sbo = lboA; }
+        const uint32_t sa = a0 + ks * 1024, sb = b0 + ks * 1024;
+        const uint64_t ad = umma_desc_ex(sa, lbo, sbo, 1, use_bo ? (sa >> 7) & 7 : 0);
+        const uint64_t bd = umma_desc_ex(sb, lbo, sbo, 1, use_bo ? (sb >> 7) & 7 : 0);
+        umma_tf32(tmem_base, ad, bd, idesc, ks > 0 ? 1u : 0u);
+      }
+      umma_commit(smem_u32(&bar));
+    }
+    __syncwarp();
+    mbar_wait(smem_u32(&bar), 0);
+    tc_fence_after();
+    for (int c0 = 0; c0 < N; c0 += 16) {
+      float v[16];
+      tmem_ld16(tmem_base + c0 + ((uint32_t)(warp * 32) << 16), v);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) D[tid * N + c0 + i] = v[i];
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, 256); }
+    return;
+  }
   const bool swap = variant & 1, mn = variant & 2, halo = variant & 4;
 
   uint32_t a_plane, a_group, a_off, b_plane;
@@ -113,7 +170,8 @@ extern "C" int atomai_b200_selftest_umma(const float* A, const float* B, float* 
                                          int variant, void* stream) {
   AB_CHECK(N % 16 == 0 && N >= 16 && N <= 256 && K % 8 == 0 && K >= 8 && K <= 64,
            "selftest_umma: N=%d K=%d out of range", N, K);
-  const int smem = 160 * 1024;
+  AB_CHECK(variant < 8 || N % 32 == 0, "selftest_umma: MN-major SW128_32B needs N %% 32 == 0");
+  const int smem = 200 * 1024;
   AB_CUDA(cudaFuncSetAttribute(selftest_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                smem));
   selftest_umma_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(A, B, D, N, K, variant);

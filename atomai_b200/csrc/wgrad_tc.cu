@@ -3,14 +3,16 @@
 //   dW[co][ci][tap] = sum_p dy[p][co] * x[p + tap][ci]        
 //
 // GEMM view per tap: D[M = co][N = ci] += A[M][K] * B[N][K]^T with K = pixels.  Both operands are
-// contiguous along their M/N (channel) axis in NHWC memory, i.e. "MN-major" for the tensor core:
-// the very same shared-memory image the forward kernel builds (one plane per 4 channels, rows =
-// pixels at a 16 B pitch) is consumed here with the roles of the axes exchanged.  One
-// tcgen05.mma covers 8 pixels (one 8-wide row of the 16 x 8 tile); a tap is again only a start
-// address into the halo tile.
+// contiguous along their channel (M / N) axis in NHWC memory, i.e. "MN-major" for the tensor
+// core.  For 32-bit operands the only legal MN-major shared-memory layout is
+// SWIZZLE_128B_BASE32B: rows = k (pixels) at a 128 B pitch, 32 channels per row, the four 32 B
+// chunks of a row XOR-ed with (row index mod 4) — which is exactly a pixel-major NHWC tile.  The
+// swizzle is a function of the absolute shared-memory address (pinned by tests/test_umma_layouts),
+// so a convolution tap is again only a different start address into the halo tile, and one
+// tcgen05.mma consumes 8 pixels (one 8-wide row of the 16 x 8 tile).
 //
-// A CTA owns one block of NB <= 32 input channels and a contiguous range of pixel tiles; its
-// taps x NB accumulators live in TMEM for the whole kernel and are flushed once, with atomics,
+// A CTA owns one block of 32 input channels and a contiguous range of pixel tiles; its
+// taps x 32 accumulators live in TMEM for the whole kernel and are flushed once, with atomics,
 // into dW (OIHW).  Warp roles: 0-3 epilogue, 4 MMA issue, 5 TMEM alloc, 6-13 loaders.
 //
 // Replaces autograd's cuDNN bwd-filter behind loss.backward(), atomai/trainers/trainer.py:206.
@@ -23,7 +25,9 @@ constexpr int kNumEpiWarps = 4, kMmaWarp = 4, kAllocWarp = 5, kFirstLoadWarp = 6
 constexpr int kNumLoadWarps = 8, kNumLoadThreads = 256;
 constexpr int kThreads = (kFirstLoadWarp + kNumLoadWarps) * 32;
 constexpr int kStages = 2;
-constexpr int kMPlanes = 32;  // M = 128 rows = 32 planes of 4 output channels (zero padded)
+constexpr int kNB = 32;                       // input channels per CTA (one 128 B swizzle row)
+constexpr int kDChunk = 128 * 128;            // bytes between 32-channel chunks of the dy tile
+constexpr int kDBytes = 4 * kDChunk;          // M = 128 output channels (zero padded)
 
 struct WgradTcParams {
   SrcSet S;
@@ -33,12 +37,11 @@ struct WgradTcParams {
   int ld_dy;
   float* dw;
   int tiles_h, tiles_w, num_tiles;
-  int NB, n_cc;          // input-channel block width and count
+  int n_cc;              // input-channel blocks
   int co_blocks;         // ceil(Cout / 128)
   int ranges;            // pixel-tile ranges per (cc, co_block)
   int TWp, THp, HP;
-  int x_plane, d_plane;  // plane strides (bytes)
-  int x_bytes, d_bytes, stage_bytes;
+  int x_bytes, stage_bytes;
   int tmem_cols;
 };
 
@@ -47,14 +50,21 @@ struct __align__(8) Ctl {
   uint32_t tmem_base, pad;
 };
 
+__device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y),
+               "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
 __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const WgradTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   Ctl* ctl = reinterpret_cast<Ctl*>(smem);
-  const uint32_t base = smem_u32(smem) + 128;
+  const uint32_t base = (smem_u32(smem) + 128 + 1023) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int taps = p.taps_h * p.taps_w;
 
-  // work assignment: blockIdx.x -> (range r, channel block cc, cout block cb)
+  // work assignment: blockIdx.x -> (range r, cout block cb, channel block cc); cc fastest so the
+  // CTAs that share a pixel range (and therefore the dy tiles) run at the same time.
   const int cc = blockIdx.x % p.n_cc;
   const int cb = (blockIdx.x / p.n_cc) % p.co_blocks;
   const int r = blockIdx.x / (p.n_cc * p.co_blocks);
@@ -62,9 +72,9 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const WgradTcPara
   const int t_begin = r * per;
   const int t_end = min(p.num_tiles, t_begin + per);
   const int co0 = cb * 128;
-  const int co_n = min(128, p.Cout - co0);  // valid output channels in this block
-  const int PD = (co_n + 3) >> 2;           // dy planes actually loaded
-  const int PX = p.NB >> 2;
+  const int co_n = min(128, p.Cout - co0);      // valid output channels in this block
+  const int ci_n = min(kNB, p.Cin - cc * kNB);  // valid input channels in this block
+  const int PD = co_n >> 2, PX = ci_n >> 2;     // 16 B pieces per pixel
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kStages; ++i) {
@@ -75,14 +85,9 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const WgradTcPara
     fence_barrier_init();
   }
   if (warp == kAllocWarp) tmem_alloc(smem_u32(&ctl->tmem_base), p.tmem_cols);
-  // zero the padding planes of both dy stages once (rows co >= co_n contribute exact zeros)
-  for (int s = 0; s < kStages; ++s) {
-    const uint32_t d0 = base + s * p.stage_bytes;
-    for (int i = threadIdx.x; i < (kMPlanes - PD) * (p.d_plane / 16); i += kThreads)
-      asm volatile("st.shared.v4.f32 [%0], {%1, %1, %1, %1};" ::"r"(d0 + PD * p.d_plane + i * 16),
-                   "f"(0.f)
-                   : "memory");
-  }
+  // zero both stages once: channel padding (co >= co_n, ci >= ci_n) must contribute exact zeros
+  for (int i = threadIdx.x; i < kStages * p.stage_bytes / 16; i += kThreads)
+    sts128(base + i * 16, make_float4(0.f, 0.f, 0.f, 0.f));
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -92,8 +97,8 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const WgradTcPara
   if (warp >= kFirstLoadWarp) {
     // ===================== loaders: dy tile + x halo tile =====================
     const int lt = threadIdx.x - kFirstLoadWarp * 32;
-    const int n_d = PD * 128;     // 16B elements of the dy tile
-    const int n_x = PX * p.HP;    // 16B elements of the x halo block
+    const int n_d = PD * 128;     // 16 B pieces of the dy tile
+    const int n_x = PX * p.HP;    // 16 B pieces of the x halo block
     uint32_t it = 0;
     for (int tile = t_begin; tile < t_end; ++tile, ++it) {
       const int tw_i = tile % p.tiles_w;
@@ -103,33 +108,23 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const WgradTcPara
       const int h_org = h0 - p.dil * (p.taps_h >> 1), w_org = w0 - p.dil * (p.taps_w >> 1);
       const uint32_t st = it % kStages;
       mbar_wait(smem_u32(&ctl->empty[st]), ((it / kStages) & 1) ^ 1);
-      const uint32_t d0 = base + st * p.stage_bytes, x0 = d0 + p.d_bytes;
+      const uint32_t d0 = base + st * p.stage_bytes, x0 = d0 + kDBytes;
       for (int e = lt; e < n_d; e += kNumLoadThreads) {
         const int j = e % PD, q = e / PD;
         const int gh = h0 + (q >> 3), gw = w0 + (q & 7);
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (gh < p.H && gw < p.W) {
-          const float* src = p.dy + (((size_t)n * p.H + gh) * p.W + gw) * p.ld_dy + co0 + j * 4;
-          if (j * 4 + 4 <= co_n) {
-            v = __ldg(reinterpret_cast<const float4*>(src));
-          } else {  // ragged last plane (Cout % 4 != 0 never happens on this path, kept safe)
-            float t[4] = {0.f, 0.f, 0.f, 0.f};
-            for (int k = 0; k < 4 && j * 4 + k < co_n; ++k) t[k] = __ldg(src + k);
-            v = make_float4(t[0], t[1], t[2], t[3]);
-          }
-        }
-        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(d0 + j * p.d_plane + q * 16),
-                     "f"(to_tf32(v.x)), "f"(to_tf32(v.y)), "f"(to_tf32(v.z)), "f"(to_tf32(v.w))
-                     : "memory");
+        if (gh < p.H && gw < p.W)
+          v = __ldg(reinterpret_cast<const float4*>(
+              p.dy + (((size_t)n * p.H + gh) * p.W + gw) * p.ld_dy + co0 + j * 4));
+        sts128(swz128_32(d0 + (j >> 3) * kDChunk + q * 128 + (j & 7) * 16),
+               make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w)));
       }
       for (int e = lt; e < n_x; e += kNumLoadThreads) {
         const int j = e % PX, q = e / PX;
         const int hh = q / p.TWp, ww = q - hh * p.TWp;
-        const float4 v =
-            load_src4(p.S, n, h_org + hh, w_org + ww, p.H, p.W, cc * p.NB + j * 4);
-        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(x0 + j * p.x_plane + q * 16),
-                     "f"(to_tf32(v.x)), "f"(to_tf32(v.y)), "f"(to_tf32(v.z)), "f"(to_tf32(v.w))
-                     : "memory");
+        const float4 v = load_src4(p.S, n, h_org + hh, w_org + ww, p.H, p.W, cc * kNB + j * 4);
+        sts128(swz128_32(x0 + q * 128 + j * 16),
+               make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w)));
       }
       fence_proxy_async_smem();
       __syncwarp();
@@ -137,20 +132,20 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const WgradTcPara
     }
   } else if (warp == kMmaWarp) {
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc_tf32(128, p.NB, 1, 1);
+      const uint32_t idesc = umma_idesc_tf32(128, kNB, 1, 1);
       uint32_t it = 0;
       for (int tile = t_begin; tile < t_end; ++tile, ++it) {
         const uint32_t st = it % kStages;
         mbar_wait(smem_u32(&ctl->full[st]), (it / kStages) & 1);
         tc_fence_after();
-        const uint32_t d0 = base + st * p.stage_bytes, x0 = d0 + p.d_bytes;
+        const uint32_t d0 = base + st * p.stage_bytes, x0 = d0 + kDBytes;
         for (int t = 0; t < taps; ++t) {
           const int ty = t / p.taps_w, tx = t - ty * p.taps_w;
           for (int h = 0; h < kTileH; ++h) {
-            const uint64_t ad = umma_desc(d0 + h * 128, 128, p.d_plane);
-            const uint64_t bd =
-                umma_desc(x0 + ((h + ty * p.dil) * p.TWp + tx * p.dil) * 16, 128, p.x_plane);
-            umma_tf32(tmem_base + t * p.NB, ad, bd, idesc, (it > 0 || h > 0) ? 1u : 0u);
+            const uint64_t ad = umma_desc_ex(d0 + h * 1024, kDChunk, 512, 1, 0);
+            const uint64_t bd = umma_desc_ex(
+                x0 + ((h + ty * p.dil) * p.TWp + tx * p.dil) * 128, 1024, 512, 1, 0);
+            umma_tf32(tmem_base + t * kNB, ad, bd, idesc, (it > 0 || h > 0) ? 1u : 0u);
           }
         }
         umma_commit(smem_u32(&ctl->empty[st]));
@@ -165,13 +160,13 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const WgradTcPara
       tc_fence_after();
       const int co = co0 + warp * 32 + lane;
       for (int t = 0; t < taps; ++t) {
-        for (int c0 = 0; c0 < p.NB; c0 += 16) {
+        for (int c0 = 0; c0 < kNB; c0 += 16) {
           float v[16];
-          tmem_ld16(tmem_base + t * p.NB + c0 + ((uint32_t)(warp * 32) << 16), v);
+          tmem_ld16(tmem_base + t * kNB + c0 + ((uint32_t)(warp * 32) << 16), v);
           if (co < p.Cout) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-              const int ci = cc * p.NB + c0 + i;
+              const int ci = cc * kNB + c0 + i;
               if (ci < p.Cin) atomicAdd(p.dw + ((size_t)co * p.Cin + ci) * taps + t, v[i]);
             }
           }
@@ -200,27 +195,16 @@ int wgrad_plan(const ab_conv_t* d, WgradTcParams* p, int* smem_bytes) {
   p->HP = p->THp * p->TWp;
   const int taps = d->ks_h * d->ks_w;
   p->co_blocks = (d->Cout + 127) / 128;
-  const int pd = ((d->Cout < 128 ? d->Cout : 128) + 3) / 4;
-  p->d_plane = 128 * 16 + 128 / (pd < 8 ? pd : 8);
-  p->d_bytes = kMPlanes * p->d_plane;
-  for (int nb = (p->Cin % 32 == 0) ? 32 : 16;; nb >>= 1) {
-    AB_CHECK(nb >= 16, "wgrad_tc: halo tile too large for shared memory (dil=%d)", d->dil);
-    if (p->Cin % nb != 0 || taps * nb > 512) continue;
-    const int px = nb / 4;
-    int plane = p->HP * 16;
-    const int want = (128 / px) % 128;
-    plane += ((want - plane % 128) + 128) % 128;
-    p->NB = nb;
-    p->x_plane = plane;
-    p->x_bytes = (px * plane + 127) & ~127;
-    p->stage_bytes = p->d_bytes + p->x_bytes;
-    if (kStages * p->stage_bytes + 256 <= 220 * 1024) break;
-  }
-  p->n_cc = p->Cin / p->NB;
+  p->x_bytes = (p->HP * 128 + 1023) & ~1023;
+  p->stage_bytes = kDBytes + p->x_bytes;
+  *smem_bytes = kStages * p->stage_bytes + 128 + 1024;
+  AB_CHECK(*smem_bytes <= 225 * 1024, "wgrad_tc: halo tile too large for shared memory (dil=%d)",
+           d->dil);
+  p->n_cc = (p->Cin + kNB - 1) / kNB;
   int cols = 32;
-  while (cols < taps * p->NB) cols <<= 1;
+  while (cols < taps * kNB) cols <<= 1;
+  AB_CHECK(cols <= 512, "wgrad_tc: too many taps");
   p->tmem_cols = cols;
-  *smem_bytes = kStages * p->stage_bytes + 256;
   const int groups = p->n_cc * p->co_blocks;
   int ranges = ab_num_sms() / groups;
   if (ranges < 1) ranges = 1;
@@ -232,15 +216,11 @@ int wgrad_plan(const ab_conv_t* d, WgradTcParams* p, int* smem_bytes) {
 }  // namespace
 
 int ab_wgrad_tc_supported(const ab_conv_t* d) {
-  int ctot = 0;
   for (int i = 0; i < d->nsrc; ++i) {
     if (d->src[i].C % 4 != 0 || d->src[i].ld % 4 != 0) return 0;
     if (((uintptr_t)d->src[i].ptr & 15) != 0) return 0;
-    ctot += d->src[i].C;
   }
-  if (ctot % 16 != 0) return 0;
   if (d->Cout % 4 != 0) return 0;
-  if (d->ks_h * d->ks_w * 16 > 512) return 0;
   WgradTcParams p;
   int smem = 0;
   if (wgrad_plan(d, &p, &smem)) return 0;
@@ -258,7 +238,7 @@ int ab_conv_tc_wgrad(const ab_conv_t* d, const float* dy, int ld_dy, float* dw,
   static int configured = 0;
   if (!configured) {
     AB_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 220 * 1024));
+                                 226 * 1024));
     configured = 1;
   }
   const int grid = p.ranges * p.n_cc * p.co_blocks;

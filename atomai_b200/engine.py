@@ -1,0 +1,460 @@
+"""
+Define-by-run native graph ("tape") that executes a network as a sequence of sm_100a kernels and
+replays it backwards.  It is the host-side orchestration of the C ABI, not a compute path of its
+own: torch supplies device memory, the current stream and the autograd *boundary* (one
+torch.autograd.Function per network call); all arithmetic on activations happens in
+libatomai_b200.so.
+
+Key idea: an activation handle (`Act`) stores the post-activation,
+pre-BatchNorm tensor `a` in NHWC together with a *pending* per-channel affine (the BatchNorm
+normalisation) and a *pending* 2x2 max-pool.  Consumers apply both while loading their input, so
+BatchNorm outputs, pooled tensors and torch.cat results are never written to HBM
+(atomai/nets/fcnn.py:117-142 materialises all of them).
+"""
+from typing import List, Optional, Sequence, Union
+
+import torch
+
+from . import ops
+from .ops import ACT_LRELU, ACT_TANH, MATH_FP32, MATH_TF32, Source
+
+_MATH = {"mode": MATH_TF32, "wgrad_tc": False}
+
+
+def set_math(mode: str = "tf32", wgrad_tc: Optional[bool] = None) -> None:
+    """'tf32' (tcgen05 tensor cores, default) or 'fp32' (exact FFMA kernels)."""
+    assert mode in ("tf32", "fp32")
+    _MATH["mode"] = MATH_TF32 if mode == "tf32" else MATH_FP32
+    if wgrad_tc is not None:
+        _MATH["wgrad_tc"] = bool(wgrad_tc)
+
+
+def get_math() -> str:
+    return "tf32" if _MATH["mode"] == MATH_TF32 else "fp32"
+
+
+class Act:
+    """Activation handle: NHWC tensor + pending affine + pending pool (see module docstring)."""
+    __slots__ = ("t", "scale", "shift", "pool", "parent", "grad", "extra", "needs_grad")
+
+    def __init__(self, t, scale=None, shift=None, pool=False, parent=None, needs_grad=True):
+        self.t, self.scale, self.shift, self.pool = t, scale, shift, pool
+        self.parent = parent          # set for lazy-pooled views: gradients go to the parent
+        self.grad = None              # d loss / d (affine(a)), full resolution of t
+        self.extra = None             # DilatedBlock direct taps (d loss / d a and d pre)
+        self.needs_grad = needs_grad
+
+    @property
+    def shape(self):                  # logical NHWC shape seen by a consumer
+        n, h, w, c = self.t.shape
+        return (n, h // 2, w // 2, c) if self.pool else (n, h, w, c)
+
+    @property
+    def C(self):
+        return self.t.shape[3]
+
+    def source(self) -> Source:
+        return Source(self.t, self.scale, self.shift, self.pool)
+
+    def pending(self) -> bool:
+        return self.pool or self.scale is not None
+
+
+def _acc_grad(act: Act, g: torch.Tensor) -> None:
+    """act.grad (+)= g (g may be a channel-slice view)."""
+    if act.grad is None:
+        act.grad = g
+    else:
+        if not _owns(act.grad):
+            own = torch.empty(act.grad.shape, device=g.device, dtype=torch.float32)
+            ops.add_slice(act.grad, own, False)
+            act.grad = own
+        ops.add_slice(g, act.grad, True)
+
+
+def _owns(t: torch.Tensor) -> bool:
+    return t.is_contiguous()
+
+
+class _ConvRec:
+    __slots__ = ("srcs", "out", "conv", "bn", "ks", "dil", "act", "slope", "math", "mean",
+                 "invstd", "scale", "count", "needs_in_grad")
+
+
+class Tape:
+    def __init__(self, training: bool, record: bool, comm=None):
+        self.training = training      # BatchNorm uses batch statistics
+        self.record = record          # keep what backward needs
+        self.comm = comm              # optional: object with allreduce_sum_(tensor) for SyncBN
+        self.ops = []                 # recorded (kind, payload) in forward order
+        self.param_grads = {}         # nn.Parameter -> grad tensor
+        self.widths = []              # feature-map widths seen (get_downsample_factor)
+
+    # ------------------------------------------------------------------ helpers
+    def input(self, x_nhwc: torch.Tensor, needs_grad: bool = False) -> Act:
+        return Act(x_nhwc, needs_grad=needs_grad)
+
+    def _math_for(self, srcs: Sequence[Act], cout: int) -> int:
+        if _MATH["mode"] == MATH_TF32 and ops.tc_supported([s.source() for s in srcs], cout):
+            return MATH_TF32
+        return MATH_FP32
+
+    def _add_pgrad(self, p, g: torch.Tensor) -> None:
+        if p is None:
+            return
+        g = g.reshape(p.shape)
+        if p in self.param_grads:
+            self.param_grads[p] = self.param_grads[p] + g
+        else:
+            self.param_grads[p] = g
+
+    # ------------------------------------------------------------------ convolution layer
+    def conv(self, srcs: Union[Act, Sequence[Act]], conv_mod, bn_mod=None, slope: float = 1.0,
+             act: int = ACT_LRELU, out_nchw: bool = False) -> Act:
+        """conv (+bias) -> activation -> [BatchNorm as a pending affine].
+        conv_mod: nn.Conv2d / nn.Conv1d (k in {1,3}, stride 1, padding = dilation*(k//2));
+        bn_mod: nn.BatchNorm2d/1d or None.  Reference: atomai/nets/blocks.py:61-76, 302-319."""
+        if isinstance(srcs, Act):
+            srcs = [srcs]
+        srcs = list(srcs)
+        n, h, w, _ = srcs[0].shape
+        wt = conv_mod.weight
+        cout = wt.shape[0]
+        if wt.dim() == 4:
+            ks = (wt.shape[2], wt.shape[3])
+            dil = conv_mod.dilation[0]
+        else:                          # Conv1d: signals are (N, 1, L, C)
+            ks = (1, wt.shape[2])
+            dil = conv_mod.dilation[0]
+        _check_conv(conv_mod, ks, dil)
+        ctot = sum(s.C for s in srcs)
+        assert ctot == wt.shape[1], f"conv expects {wt.shape[1]} input channels, got {ctot}"
+        math = self._math_for(srcs, cout)
+        d = ops.conv_desc([s.source() for s in srcs], n, h, w, cout, ks, dil, slope, math,
+                          out_nchw, act)
+        wp = ops.prep_weights(wt, ops.WMODE_FWD, math)
+        dev = wt.device
+        if out_nchw:
+            out_t = torch.empty((n, cout, h, w), device=dev, dtype=torch.float32)
+        else:
+            out_t = torch.empty((n, h, w, cout), device=dev, dtype=torch.float32)
+        use_batch_stats = bn_mod is not None and (self.training or bn_mod.running_mean is None)
+        stats = torch.zeros(2 * cout, device=dev, dtype=torch.float64) if use_batch_stats else None
+        bias = conv_mod.bias
+        ops.conv_fwd(d, wp, None if bias is None else bias.detach(), out_t, stats)
+        self.widths.append(w)
+        scale = shift = mean = invstd = None
+        count = n * h * w
+        if bn_mod is not None:
+            assert not out_nchw
+            scale = torch.empty(cout, device=dev, dtype=torch.float32)
+            shift = torch.empty(cout, device=dev, dtype=torch.float32)
+            if use_batch_stats:
+                if self.comm is not None:
+                    count = self.comm.allreduce_count(count)
+                    self.comm.allreduce_sum_(stats)
+                mean = torch.empty(cout, device=dev, dtype=torch.float32)
+                invstd = torch.empty(cout, device=dev, dtype=torch.float32)
+                mom = bn_mod.momentum if bn_mod.momentum is not None else 0.1
+                ops.bn_finalize(stats, count, _d(bn_mod.weight), _d(bn_mod.bias),
+                                bn_mod.running_mean, bn_mod.running_var, mom, bn_mod.eps, True,
+                                scale, shift, mean, invstd)
+                if bn_mod.num_batches_tracked is not None:
+                    bn_mod.num_batches_tracked.add_(1)
+            else:
+                ops.bn_finalize(None, count, _d(bn_mod.weight), _d(bn_mod.bias),
+                                bn_mod.running_mean, bn_mod.running_var, 0.0, bn_mod.eps, False,
+                                scale, shift, None, None)
+        out = Act(out_t, scale, shift)
+        if self.record:
+            r = _ConvRec()
+            r.srcs, r.out, r.conv, r.bn, r.ks, r.dil = srcs, out, conv_mod, bn_mod, ks, dil
+            r.act, r.slope, r.math, r.mean, r.invstd, r.scale, r.count = \
+                act, slope, math, mean, invstd, scale, count
+            r.needs_in_grad = any(s.needs_grad for s in srcs)
+            assert not (bn_mod is not None and not use_batch_stats), \
+                "backward through eval-mode BatchNorm is not supported"
+            assert not out_nchw or True
+            self.ops.append(("conv", r))
+        return out
+
+    def _conv_bwd(self, r: _ConvRec) -> None:
+        out = r.out
+        a = out.t
+        if a.dim() == 4 and a.shape[-1] != r.conv.weight.shape[0]:
+            # NCHW output (flatten -> Linear consumers): gradient arrives NCHW; bring to NHWC
+            raise NotImplementedError("backward through an NCHW-stored conv output")
+        dy = out.grad
+        n, h, w, cout = a.shape
+        dev = a.device
+        sums = None
+        if r.bn is not None:
+            assert dy is not None, "BatchNorm output has no gradient"
+            sums = torch.zeros(2 * cout, device=dev, dtype=torch.float64)
+            ops.bn_bwd_reduce(dy, a, r.mean, r.invstd, sums)
+            if self.comm is not None:
+                self.comm.allreduce_sum_(sums)
+            self._add_pgrad(r.bn.bias, sums[:cout].float())
+            self._add_pgrad(r.bn.weight, sums[cout:].float())
+        dpre = torch.empty((n, h, w, cout), device=dev, dtype=torch.float32)
+        dbias = torch.zeros(cout, device=dev, dtype=torch.float64) if r.conv.bias is not None else None
+        ops.bn_act_bwd(dy, a, r.mean, r.invstd, r.scale if r.bn is not None else None, sums,
+                       r.count, out.extra, r.act, r.slope, dpre, dbias)
+        out.grad = None
+        out.extra = None
+        if dbias is not None:
+            self._add_pgrad(r.conv.bias, dbias.float())
+        # weight gradient
+        wt = r.conv.weight
+        srcs_s = [s.source() for s in r.srcs]
+        wmath = r.math
+        if wmath == MATH_TF32 and not (_MATH["wgrad_tc"] and
+                                       ops.wgrad_tc_supported(srcs_s, cout, r.ks, r.dil)):
+            wmath = MATH_FP32
+        dw = torch.zeros((wt.shape[0], wt.shape[1], r.ks[0], r.ks[1]), device=dev,
+                         dtype=torch.float32)
+        dsc = ops.conv_desc(srcs_s, n, h, w, cout, r.ks, r.dil, 1.0, wmath)
+        ops.conv_wgrad(dsc, dpre, dw)
+        self._add_pgrad(wt, dw)
+        # data gradient
+        if r.needs_in_grad:
+            ctot = wt.shape[1]
+            dsrc = [Source(dpre)]
+            dmath = MATH_TF32 if (_MATH["mode"] == MATH_TF32 and ops.tc_supported(dsrc, ctot)) \
+                else MATH_FP32
+            wpd = ops.prep_weights(wt, ops.WMODE_DGRAD, dmath)
+            dd = ops.conv_desc(dsrc, n, h, w, ctot, r.ks, r.dil, 1.0, dmath)
+            dx = torch.empty((n, h, w, ctot), device=dev, dtype=torch.float32)
+            ops.conv_fwd(dd, wpd, None, dx, None)
+            c0 = 0
+            for s in r.srcs:
+                view = dx[..., c0:c0 + s.C] if len(r.srcs) > 1 else dx
+                c0 += s.C
+                if not s.needs_grad:
+                    continue
+                if s.pool:
+                    tgt = s.parent
+                    acc = tgt.grad is not None
+                    if not acc:
+                        fh, fw = tgt.t.shape[1], tgt.t.shape[2]
+                        alloc = torch.zeros if (fh % 2 or fw % 2) else torch.empty
+                        tgt.grad = alloc(tgt.t.shape, device=dev, dtype=torch.float32)
+                    elif not _owns(tgt.grad):
+                        own = torch.empty(tgt.t.shape, device=dev, dtype=torch.float32)
+                        ops.add_slice(tgt.grad, own, False)
+                        tgt.grad = own
+                    ops.pool_bwd(view, tgt.t, tgt.scale, tgt.shift, tgt.grad, acc)
+                else:
+                    _acc_grad(s, view)
+
+    # ------------------------------------------------------------------ pooling / upsampling
+    def pool(self, x: Act) -> Act:
+        """F.max_pool2d(x, 2, 2) as a pending transform (atomai/nets/fcnn.py:123-127)."""
+        if x.pool:
+            x = self.materialize(x)
+        assert x.t.shape[1] % 2 == 0 and x.t.shape[2] % 2 == 0, \
+            "2x2 max-pool needs even spatial dimensions"
+        return Act(x.t, x.scale, x.shift, pool=True, parent=x, needs_grad=x.needs_grad)
+
+    def upsample(self, x: Act, mode: str = "bilinear") -> Act:
+        """F.interpolate(scale_factor=2, mode) (atomai/nets/blocks.py:130-131)."""
+        if x.pending():
+            x = self.materialize(x)
+        n, h, w, c = x.t.shape
+        out_t = torch.empty((n, 2 * h, 2 * w, c), device=x.t.device, dtype=torch.float32)
+        bil = mode == "bilinear"
+        ops.upsample_fwd(x.t, out_t, bil)
+        out = Act(out_t, needs_grad=x.needs_grad)
+        if self.record:
+            self.ops.append(("up", (x, out, bil)))
+        return out
+
+    def _up_bwd(self, rec) -> None:
+        x, out, bil = rec
+        if not x.needs_grad or out.grad is None:
+            return
+        g = out.grad
+        if not _owns(g):
+            own = torch.empty(out.t.shape, device=g.device, dtype=torch.float32)
+            ops.add_slice(g, own, False)
+            g = own
+        dx = torch.empty(x.t.shape, device=g.device, dtype=torch.float32)
+        ops.upsample_bwd(g, dx, bil)
+        out.grad = None
+        _acc_grad(x, dx)
+
+    def materialize(self, x: Act, nchw: bool = False) -> Act:
+        """Apply the pending affine / pool and write the result (module boundaries only)."""
+        if not x.pending() and not nchw:
+            return x
+        n, h, w, c = x.shape
+        dev = x.t.device
+        if x.pool:
+            assert not nchw
+            out_t = torch.empty((n, h, w, c), device=dev, dtype=torch.float32)
+            ops.pool_fwd(x.t, x.scale, x.shift, out_t)
+        elif nchw:
+            out_t = torch.empty((n, c, h, w), device=dev, dtype=torch.float32)
+            ops.affine(x.t, x.scale, x.shift, out_t, out_nchw=True)
+        else:
+            out_t = torch.empty((n, h, w, c), device=dev, dtype=torch.float32)
+            ops.affine(x.t, x.scale, x.shift, out_t)
+        out = Act(out_t, needs_grad=x.needs_grad)
+        if self.record:
+            self.ops.append(("mat", (x, out, nchw)))
+        return out
+
+    def _mat_bwd(self, rec) -> None:
+        x, out, nchw = rec
+        if not x.needs_grad or out.grad is None:
+            return
+        g = out.grad
+        if nchw:                       # gradient arrives as (N,C,H,W); view it as NHWC
+            g = g.permute(0, 2, 3, 1)
+            if not (g.stride(3) == 1):
+                g = g.contiguous()
+        out.grad = None
+        if x.pool:
+            tgt = x.parent
+            acc = tgt.grad is not None
+            if not acc:
+                tgt.grad = torch.empty(tgt.t.shape, device=g.device, dtype=torch.float32)
+            ops.pool_bwd(g, tgt.t, tgt.scale, tgt.shift, tgt.grad, acc)
+        else:
+            _acc_grad(x, g)
+
+    # ------------------------------------------------------------------ DilatedBlock sum
+    def dilated_sum(self, layers: List[Act], slope: float) -> Act:
+        """sum over layers of (conv out + LeakyReLU out + [BN out]) — blocks.py:321-329."""
+        n, h, w, c = layers[0].t.shape
+        out_t = torch.empty((n, h, w, c), device=layers[0].t.device, dtype=torch.float32)
+        ops.dilated_sum([l.t for l in layers], [l.scale for l in layers],
+                        [l.shift for l in layers], slope, out_t)
+        out = Act(out_t)
+        if self.record:
+            self.ops.append(("dsum", (layers, out)))
+        return out
+
+    def _dsum_bwd(self, rec) -> None:
+        layers, out = rec
+        g = out.grad
+        if g is None:
+            return
+        if not _owns(g):
+            own = torch.empty(out.t.shape, device=g.device, dtype=torch.float32)
+            ops.add_slice(g, own, False)
+            g = own
+        out.grad = None
+        for l in layers:
+            l.extra = g                # direct taps on a_l and pre_l
+            if l.scale is not None:    # BN output also enters the sum
+                _acc_grad(l, g)
+
+    # ------------------------------------------------------------------ backward driver
+    def backward(self, out: Act, grad_out_nhwc: torch.Tensor) -> None:
+        out.grad = grad_out_nhwc
+        for kind, rec in reversed(self.ops):
+            if kind == "conv":
+                self._conv_bwd(rec)
+            elif kind == "up":
+                self._up_bwd(rec)
+            elif kind == "mat":
+                self._mat_bwd(rec)
+            elif kind == "dsum":
+                self._dsum_bwd(rec)
+            elif kind == "custom":
+                rec.backward(self)
+            else:
+                raise RuntimeError(kind)
+        self.ops = []
+
+
+def _d(p):
+    return None if p is None else p.detach()
+
+
+def _check_conv(m, ks, dil) -> None:
+    k = ks[1]
+    stride = m.stride[0] if isinstance(m.stride, tuple) else m.stride
+    pad = m.padding[-1] if isinstance(m.padding, tuple) else m.padding
+    if k not in (1, 3) or ks[0] not in (1, 3):
+        raise NotImplementedError(f"native conv supports kernel sizes 1 and 3, got {ks}")
+    if stride != 1:
+        raise NotImplementedError("native conv supports stride 1 only")
+    if pad != dil * (k // 2):
+        raise NotImplementedError(f"native conv needs 'same' padding (padding={pad}, "
+                                  f"dilation={dil}, kernel={k})")
+
+
+# ---------------------------------------------------------------------- autograd boundary
+class _NetFn(torch.autograd.Function):
+    """One network call = one autograd node.  inputs: (module, comm, x, *params)."""
+
+    @staticmethod
+    def forward(ctx, module, comm, grad_on, x, *params):
+        # (autograd disables grad mode inside forward, so the caller passes it in)
+        record = grad_on and any(p.requires_grad for p in params)
+        x_needs = grad_on and x.requires_grad
+        tape = Tape(module.training, record or x_needs, comm)
+        xin = _to_nhwc(x)
+        a_in = tape.input(xin, needs_grad=x_needs)
+        out = module._emit(tape, a_in)
+        out = tape.materialize(out)
+        ctx.tape, ctx.out, ctx.a_in, ctx.params = tape, out, a_in, params
+        ctx.x_needs = x_needs
+        ctx.nparams = len(params)
+        res = out.t.permute(0, 3, 1, 2)
+        if getattr(module, "_squeeze_h", False):
+            res = res.squeeze(2)
+        return res
+
+    @staticmethod
+    def backward(ctx, g):
+        tape, out = ctx.tape, ctx.out
+        if getattr(g, "dim", None) and g.dim() == 3:
+            g = g.unsqueeze(2)
+        g = g.permute(0, 2, 3, 1)
+        if not g.is_contiguous():
+            g = g.contiguous()
+        tape.backward(out, g)
+        grads = tuple(tape.param_grads.get(p) for p in ctx.params)
+        gx = None
+        if ctx.x_needs and ctx.a_in.grad is not None:
+            gx = ctx.a_in.grad.permute(0, 3, 1, 2)
+        tape.param_grads = {}
+        return (None, None, None, gx) + grads
+
+
+def _to_nhwc(x: torch.Tensor) -> torch.Tensor:
+    """(N,C,H,W) or (N,C,L) -> contiguous (N,H,W,C) without a copy when C == 1 or channels_last."""
+    if x.dim() == 3:
+        x = x.unsqueeze(2)
+    assert x.dim() == 4, f"expected NCHW input, got shape {tuple(x.shape)}"
+    if not x.is_cuda:
+        raise RuntimeError("atomai_b200 networks run on CUDA (sm_100a) only; there is no CPU path")
+    if x.dtype != torch.float32:
+        x = x.float()
+    xp = x.permute(0, 2, 3, 1)
+    if not xp.is_contiguous():
+        xp = xp.contiguous()
+    return xp
+
+
+def run(module, x: torch.Tensor, comm=None) -> torch.Tensor:
+    """Execute `module` (anything with _emit(tape, Act) -> Act) natively on x."""
+    params = [p for p in module.parameters()]
+    return _NetFn.apply(module, comm if comm is not None else getattr(module, "_comm", None),
+                        torch.is_grad_enabled(), x, *params)
+
+
+def probe_downsample_factor(model, dims=(1, 64, 64)) -> float:
+    """max/min feature-map width of a network (utils.nn.get_downsample_factor)."""
+    p = next(model.parameters())
+    x = torch.randn(1, *dims, device=p.device)
+    was_training = model.training
+    model.eval()
+    tape = Tape(False, False)
+    with torch.no_grad():
+        model._emit(tape, tape.input(_to_nhwc(x)))
+    model.train(was_training)
+    return max(tape.widths) / min(tape.widths)

@@ -18,12 +18,18 @@ from ._C import (ACT_LRELU, ACT_TANH, MATH_FP32, MATH_TF32, WMODE_DGRAD, WMODE_F
 
 
 def _ld(t: torch.Tensor) -> int:
-    """Pixel stride of an NHWC (view) tensor; validates the layout."""
+    """Pixel stride of an NHWC (view) tensor; validates the layout (size-1 dims are free)."""
     assert t.dtype == torch.float32 and t.is_cuda, "fp32 CUDA tensor expected"
-    assert t.dim() == 4 and t.stride(3) == 1, f"NHWC view expected, strides {t.stride()}"
-    ld = t.stride(2)
-    assert t.stride(1) == ld * t.shape[2] and t.stride(0) == ld * t.shape[2] * t.shape[1], \
-        f"pixel-major layout expected, got shape {tuple(t.shape)} strides {t.stride()}"
+    assert t.dim() == 4, f"NHWC tensor expected, got shape {tuple(t.shape)}"
+    if t.is_contiguous():
+        return t.shape[3]
+    N, H, W, Cc = t.shape
+    st = t.stride()
+    assert Cc == 1 or st[3] == 1, f"channels must be innermost, strides {st}"
+    ld = st[2] if W > 1 else (st[1] if H > 1 else (st[0] if N > 1 else Cc))
+    assert ld >= Cc and (W == 1 or st[2] == ld) and (H == 1 or st[1] == ld * W) and \
+        (N == 1 or st[0] == ld * W * H), \
+        f"pixel-major layout expected, got shape {tuple(t.shape)} strides {st}"
     return ld
 
 
@@ -76,7 +82,7 @@ def tc_supported(srcs: Sequence[Source], Cout: int) -> bool:
 def wgrad_tc_supported(srcs: Sequence[Source], Cout: int, ks, dil) -> bool:
     ctot = sum(s.C for s in srcs)
     return (all(s.C % 4 == 0 and _ld(s.t) % 4 == 0 and s.t.data_ptr() % 16 == 0 for s in srcs)
-            and ctot % 16 == 0 and Cout % 4 == 0 and dil <= 2)
+            and ctot % 4 == 0 and Cout % 4 == 0 and (dil <= 2 or max(ks) == 1))
 
 
 def prep_weights(w_oihw: torch.Tensor, mode: int, math: int) -> torch.Tensor:
@@ -173,24 +179,25 @@ def dilated_sum(a_list, scale_list, shift_list, slope, out) -> None:
                                         out.shape[-1], stream_ptr()))
 
 
-def ce_fwd_bwd(logits_nhwc, labels, loss_sum, dlogits=None, gscale=1.0) -> None:
+def ce_fwd_bwd(logits_nhwc, labels, loss_sum, dlogits=None, gscale=1.0, gscale_dev=None) -> None:
     N, H, W, Cc = logits_nhwc.shape
     assert labels.dtype == torch.int64 and labels.is_contiguous()
     check(lib().atomai_b200_ce_fwd_bwd(ptr(logits_nhwc), _ld(logits_nhwc), ptr(labels),
                                        N * H * W, Cc, ptr(loss_sum), ptr(dlogits),
                                        _ld(dlogits) if dlogits is not None else 0, float(gscale),
-                                       stream_ptr()))
+                                       ptr(gscale_dev), stream_ptr()))
 
 
-def pointwise_loss(pred, target, kind, loss_sum, dpred=None, gscale=1.0) -> None:
+def pointwise_loss(pred, target, kind, loss_sum, dpred=None, gscale=1.0, gscale_dev=None) -> None:
     assert pred.is_contiguous() and target.is_contiguous() and pred.numel() == target.numel()
     check(lib().atomai_b200_pointwise_loss(ptr(pred), ptr(target), pred.numel(), kind,
-                                           ptr(loss_sum), ptr(dpred), float(gscale), stream_ptr()))
+                                           ptr(loss_sum), ptr(dpred), float(gscale),
+                                           ptr(gscale_dev), stream_ptr()))
 
 
-def sqerr_reduce(x, xhat, out, dxhat=None, gscale=1.0) -> None:
+def sqerr_reduce(x, xhat, out, dxhat=None, gscale=1.0, gscale_dev=None) -> None:
     check(lib().atomai_b200_sqerr_reduce(ptr(x), ptr(xhat), x.numel(), ptr(out), ptr(dxhat),
-                                         float(gscale), stream_ptr()))
+                                         float(gscale), ptr(gscale_dev), stream_ptr()))
 
 
 def adam_multi(table_dev, n, max_numel, lr, b1, b2, eps, wd, step, grad_scale=1.0) -> None:

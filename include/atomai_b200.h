@@ -147,13 +147,16 @@ int atomai_b200_dilated_sum(const float* const* a_ptrs, const float* const* scal
 /* ---- losses -----------------------------------------------------------------
  * nn.CrossEntropyLoss (mean) over NHWC logits + int64 labels:
  * atomai/losses_metrics/losses.py:154-155, called at trainers/trainer.py:205.
- * loss_sum: double[1] (caller zeroes); dlogits (nullable) = (softmax-onehot)*gscale. */
+ * loss_sum: double[1] (nullable; caller zeroes); dlogits (nullable) = (softmax-onehot)*g with
+ * g = gscale * (gscale_dev ? *gscale_dev : 1) — the device scalar carries autograd's upstream
+ * gradient without a host sync. */
 int atomai_b200_ce_fwd_bwd(const float* logits, int ld, const int64_t* labels, int64_t npix,
                            int C, double* loss_sum, float* dlogits, int ld_d, float gscale,
-                           void* stream);
+                           const float* gscale_dev, void* stream);
 /* kind 0: MSE (losses.py:163-164), 1: BCE-with-logits (losses.py:157-158); elementwise over n */
 int atomai_b200_pointwise_loss(const float* pred, const float* target, int64_t n, int kind,
-                               double* loss_sum, float* dpred, float gscale, void* stream);
+                               double* loss_sum, float* dpred, float gscale,
+                               const float* gscale_dev, void* stream);
 
 /* ---- optimizer --------------------------------------------------------------
  * torch.optim.Adam step over a table of tensors (trainers/trainer.py:207,539).
@@ -199,7 +202,7 @@ int atomai_b200_coord_latent_bwd(const ab_coordlat_t* d, const float* dpre0, flo
 /* ELBO pieces (atomai/losses_metrics/vi_losses.py:13-57,77-137):
  * out[0] = sum_b 0.5*sum_px (xhat-x)^2 ; dxhat = (xhat - x)*gscale (nullable). */
 int atomai_b200_sqerr_reduce(const float* x, const float* xhat, int64_t n, double* out,
-                             float* dxhat, float gscale, void* stream);
+                             float* dxhat, float gscale, const float* gscale_dev, void* stream);
 
 /* ---- DKL ----------------------------------------------------------------------
  * Dense Gram K[i][j] = os * k(||(x1_i - x2_j) * inv_ls||), kind 0 = RBF,

@@ -9,7 +9,7 @@ import traceback
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-GROUPS = ["selftest", "simt", "tc_basic", "tc_fused", "tc_dgrad", "wgrad_simt", "wgrad_tc",
+GROUPS = ["selftest", "simt", "tc_basic", "tc_fused", "tc_dgrad", "dgrad_diag", "wgrad_simt", "wgrad_tc",
           "elementwise", "vae", "bigshape"]
 
 
@@ -104,9 +104,9 @@ def run_group(name):
         res[tag] = {"rel": rel(dw, w.grad)}
 
     if name == "selftest":
-        for variant in range(8):
-            for (N, K) in [(64, 32), (16, 8), (128, 64)]:
-                if variant & 2:
+        for variant in [0, 4] + list(range(8, 24)):
+            for (N, K) in [(64, 32), (32, 8), (128, 64)]:
+                if variant >= 8 or (variant & 2):
                     At = rnd(K, 128)
                     Bt = rnd(K, N)
                     ref = At.t() @ Bt
@@ -168,6 +168,35 @@ def run_group(name):
                 ops.conv_fwd(d, wp, None, out, None)
                 torch.cuda.synchronize()
                 res[f"{tag}_{ci}_{co}_d{dil}"] = {"rel": rel(nchw(out), x.grad)}
+    elif name == "dgrad_diag":
+        # first-launch / shape sensitivity of the tcgen05 path: each case twice, TC vs SIMT
+        for rep in range(2):
+            for (ci, co, dil) in [(32, 64, 1), (64, 32, 1), (32, 64, 1), (16, 32, 1)]:
+                N, H, W = 2, 32, 32
+                w = rnd(co, ci, 3, 3, scale=0.1)
+                dy = nhwc(rnd(N, co, H, W))
+                outs = {}
+                for math, tag in [(ops.MATH_TF32, "tc"), (ops.MATH_FP32, "simt")]:
+                    d = ops.conv_desc([Source(dy)], N, H, W, ci, (3, 3), dil, 1.0, math)
+                    wp = ops.prep_weights(w, ops.WMODE_DGRAD, math)
+                    out = torch.full((N, H, W, ci), float("nan"), device=dev)
+                    ops.conv_fwd(d, wp, None, out, None)
+                    torch.cuda.synchronize()
+                    outs[tag] = out
+                diff = (outs["tc"] - outs["simt"]).abs()
+                bad = diff > 1e-2 * outs["simt"].abs().max()
+                info = {"rel": rel(outs["tc"], outs["simt"]), "nbad": int(bad.sum()),
+                        "nan": int(torch.isnan(outs["tc"]).sum())}
+                if bad.any():
+                    idx = bad.nonzero()
+                    info["bad_n"] = sorted(set(idx[:, 0].tolist()))
+                    info["bad_h"] = [int(idx[:, 1].min()), int(idx[:, 1].max())]
+                    info["bad_w"] = [int(idx[:, 2].min()), int(idx[:, 2].max())]
+                    info["bad_c"] = [int(idx[:, 3].min()), int(idx[:, 3].max())]
+                res[f"rep{rep}_{ci}_{co}"] = info
+        # same through the forward weight mode (K = 64 -> N = 32)
+        conv_case("fwd_64to32", ops.MATH_TF32, 2, 32, 32, [64], 32)
+        conv_case("fwd_64to32_again", ops.MATH_TF32, 2, 32, 32, [64], 32)
     elif name == "wgrad_simt":
         M = ops.MATH_FP32
         wgrad_case("1to16", M, 2, 40, 48, [1], 16)
