@@ -128,9 +128,18 @@ class NativeError(RuntimeError):
     pass
 
 
+_LAUNCHES = [0]
+
+
 def check(status: int) -> None:
+    """Every kernel-launching ABI call funnels through here (count = lower bound on launches)."""
+    _LAUNCHES[0] += 1
     if status != 0:
         raise NativeError(lib().atomai_b200_last_error().decode())
+
+
+def launch_count() -> int:
+    return _LAUNCHES[0]
 
 
 def ptr(t):

@@ -8,6 +8,7 @@ convolutions + HBM-bound fused kernels); there is no CPU or eager-PyTorch fallba
 """
 from .__version__ import version as __version__
 from .engine import get_math, set_math
-from . import nets, losses_metrics
+from . import losses_metrics, models, nets, predictors, trainers, utils
 
-__all__ = ["nets", "losses_metrics", "set_math", "get_math", "__version__"]
+__all__ = ["nets", "losses_metrics", "trainers", "predictors", "models", "utils", "set_math",
+           "get_math", "__version__"]

@@ -18,7 +18,7 @@ import torch
 from . import ops
 from .ops import ACT_LRELU, ACT_TANH, MATH_FP32, MATH_TF32, Source
 
-_MATH = {"mode": MATH_TF32, "wgrad_tc": False}
+_MATH = {"mode": MATH_TF32, "wgrad_tc": True}
 
 
 def set_math(mode: str = "tf32", wgrad_tc: Optional[bool] = None) -> None:
@@ -35,12 +35,14 @@ def get_math() -> str:
 
 class Act:
     """Activation handle: NHWC tensor + pending affine + pending pool (see module docstring)."""
-    __slots__ = ("t", "scale", "shift", "pool", "parent", "grad", "extra", "needs_grad")
+    __slots__ = ("t", "scale", "shift", "pool", "parent", "grad", "grad_owned", "extra",
+                 "needs_grad")
 
     def __init__(self, t, scale=None, shift=None, pool=False, parent=None, needs_grad=True):
         self.t, self.scale, self.shift, self.pool = t, scale, shift, pool
         self.parent = parent          # set for lazy-pooled views: gradients go to the parent
         self.grad = None              # d loss / d (affine(a)), full resolution of t
+        self.grad_owned = False       # True: grad buffer is exclusively ours (in-place add ok)
         self.extra = None             # DilatedBlock direct taps (d loss / d a and d pre)
         self.needs_grad = needs_grad
 
@@ -60,20 +62,27 @@ class Act:
         return self.pool or self.scale is not None
 
 
-def _acc_grad(act: Act, g: torch.Tensor) -> None:
-    """act.grad (+)= g (g may be a channel-slice view)."""
+def _acc_grad(act: Act, g: torch.Tensor, owned: bool) -> None:
+    """act.grad (+)= g.  g may be a channel-slice view; `owned` says whether the caller hands over
+    exclusive ownership of g's memory.  A buffer that is not exclusively ours (e.g. the gradient of
+    a DilatedBlock sum shared by all its layers) is never written in place."""
     if act.grad is None:
-        act.grad = g
-    else:
-        if not _owns(act.grad):
-            own = torch.empty(act.grad.shape, device=g.device, dtype=torch.float32)
-            ops.add_slice(act.grad, own, False)
-            act.grad = own
-        ops.add_slice(g, act.grad, True)
+        act.grad, act.grad_owned = g, owned
+        return
+    if not act.grad_owned:
+        own = torch.empty(act.grad.shape, device=g.device, dtype=torch.float32)
+        ops.add_slice(act.grad, own, False)
+        act.grad, act.grad_owned = own, True
+    ops.add_slice(g, act.grad, True)
 
 
-def _owns(t: torch.Tensor) -> bool:
-    return t.is_contiguous()
+def _dense(g: torch.Tensor) -> torch.Tensor:
+    """Contiguous NHWC copy of a channel-slice view (kernels that need ld == C)."""
+    if g.is_contiguous():
+        return g
+    own = torch.empty(g.shape, device=g.device, dtype=torch.float32)
+    ops.add_slice(g, own, False)
+    return own
 
 
 class _ConvRec:
@@ -233,19 +242,22 @@ class Tape:
                 if not s.needs_grad:
                     continue
                 if s.pool:
-                    tgt = s.parent
-                    acc = tgt.grad is not None
-                    if not acc:
-                        fh, fw = tgt.t.shape[1], tgt.t.shape[2]
-                        alloc = torch.zeros if (fh % 2 or fw % 2) else torch.empty
-                        tgt.grad = alloc(tgt.t.shape, device=dev, dtype=torch.float32)
-                    elif not _owns(tgt.grad):
-                        own = torch.empty(tgt.t.shape, device=dev, dtype=torch.float32)
-                        ops.add_slice(tgt.grad, own, False)
-                        tgt.grad = own
-                    ops.pool_bwd(view, tgt.t, tgt.scale, tgt.shift, tgt.grad, acc)
+                    self._pool_grad(s.parent, view)
                 else:
-                    _acc_grad(s, view)
+                    _acc_grad(s, view, True)
+
+    @staticmethod
+    def _pool_grad(tgt: Act, gp: torch.Tensor) -> None:
+        """tgt.grad (+)= unpool(gp): scatter to the arg-max positions of tgt's affine'd windows."""
+        acc = tgt.grad is not None
+        if not acc:
+            tgt.grad = torch.empty(tgt.t.shape, device=gp.device, dtype=torch.float32)
+            tgt.grad_owned = True
+        elif not (tgt.grad_owned and tgt.grad.is_contiguous()):
+            own = torch.empty(tgt.t.shape, device=gp.device, dtype=torch.float32)
+            ops.add_slice(tgt.grad, own, False)
+            tgt.grad, tgt.grad_owned = own, True
+        ops.pool_bwd(gp, tgt.t, tgt.scale, tgt.shift, tgt.grad, acc)
 
     # ------------------------------------------------------------------ pooling / upsampling
     def pool(self, x: Act) -> Act:
@@ -274,14 +286,10 @@ class Tape:
         if not x.needs_grad or out.grad is None:
             return
         g = out.grad
-        if not _owns(g):
-            own = torch.empty(out.t.shape, device=g.device, dtype=torch.float32)
-            ops.add_slice(g, own, False)
-            g = own
         dx = torch.empty(x.t.shape, device=g.device, dtype=torch.float32)
         ops.upsample_bwd(g, dx, bil)
         out.grad = None
-        _acc_grad(x, dx)
+        _acc_grad(x, dx, True)
 
     def materialize(self, x: Act, nchw: bool = False) -> Act:
         """Apply the pending affine / pool and write the result (module boundaries only)."""
@@ -313,15 +321,12 @@ class Tape:
             g = g.permute(0, 2, 3, 1)
             if not (g.stride(3) == 1):
                 g = g.contiguous()
+        owned = out.grad_owned
         out.grad = None
         if x.pool:
-            tgt = x.parent
-            acc = tgt.grad is not None
-            if not acc:
-                tgt.grad = torch.empty(tgt.t.shape, device=g.device, dtype=torch.float32)
-            ops.pool_bwd(g, tgt.t, tgt.scale, tgt.shift, tgt.grad, acc)
+            self._pool_grad(x.parent, g)
         else:
-            _acc_grad(x, g)
+            _acc_grad(x, g, owned)
 
     # ------------------------------------------------------------------ DilatedBlock sum
     def dilated_sum(self, layers: List[Act], slope: float) -> Act:
@@ -340,19 +345,16 @@ class Tape:
         g = out.grad
         if g is None:
             return
-        if not _owns(g):
-            own = torch.empty(out.t.shape, device=g.device, dtype=torch.float32)
-            ops.add_slice(g, own, False)
-            g = own
+        g = _dense(g)
         out.grad = None
         for l in layers:
-            l.extra = g                # direct taps on a_l and pre_l
+            l.extra = g                # direct taps on a_l and pre_l (read-only, shared)
             if l.scale is not None:    # BN output also enters the sum
-                _acc_grad(l, g)
+                _acc_grad(l, g, False)
 
     # ------------------------------------------------------------------ backward driver
     def backward(self, out: Act, grad_out_nhwc: torch.Tensor) -> None:
-        out.grad = grad_out_nhwc
+        out.grad, out.grad_owned = grad_out_nhwc, False
         for kind, rec in reversed(self.ops):
             if kind == "conv":
                 self._conv_bwd(rec)

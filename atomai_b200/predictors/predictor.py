@@ -1,0 +1,213 @@
+"""
+Inference wrappers and NN-output -> atom coordinates, with the reference's interface
+(atomai/predictors/predictor.py:23-298, 531-639).  The network forward and the softmax run on the
+GPU (native sm_100a graph); the Locator post-processing (threshold -> connected components ->
+centre of mass -> edge filter) is the reference's CPU algorithm and is bit-exact with it
+(tests/golden/locator_crop.npz).
+"""
+import time
+from typing import Dict, List, Tuple, Type, Union
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from ..utils.coords import find_com
+from ..utils.img import cv_thresh, img_pad, img_resize
+from ..utils.nn import get_downsample_factor, get_nb_classes, set_train_rng
+from ..utils.preproc import torch_format_image
+
+
+class BasePredictor:
+    """Base predictor class (atomai/predictors/predictor.py:23-121)."""
+    def __init__(self, model: Type[torch.nn.Module] = None, use_gpu: bool = False,
+                 **kwargs: Union[bool, str]) -> None:
+        self.model = model
+        self.device = "cpu"
+        if use_gpu and torch.cuda.is_available():
+            self.device = kwargs.get("device") or "cuda"
+        if self.model is not None:
+            self.model.to(self.device)
+        self.verbose = kwargs.get("verbose", False)
+
+    def preprocess(self, data: Union[torch.Tensor, np.ndarray]) -> torch.Tensor:
+        if isinstance(data, np.ndarray):
+            data = torch.from_numpy(data).float()
+        return data
+
+    def _model2device(self, device: str = None) -> None:
+        self.model.to(self.device if device is None else device)
+
+    def _data2device(self, data: torch.Tensor, device: str = None) -> torch.Tensor:
+        return data.to(self.device if device is None else device)
+
+    def forward_(self, xnew: torch.Tensor) -> torch.Tensor:
+        self.model.eval()
+        with torch.no_grad():
+            out = self.model(xnew.to(self.device))
+        return out
+
+    def batch_predict(self, data: torch.Tensor, out_shape: Tuple[int],
+                      num_batches: int) -> torch.Tensor:
+        """Batch-by-batch prediction into a CPU tensor (predictor.py:82-106)."""
+        batch_size = len(data) // num_batches
+        if batch_size < 1:
+            num_batches = batch_size = 1
+        prediction_all = torch.zeros(out_shape)
+        stop = num_batches * batch_size
+        for i in range(num_batches):
+            if self.verbose:
+                print("\rBatch {}/{}".format(i + 1, num_batches), end="")
+            sl = slice(i * batch_size, (i + 1) * batch_size)
+            prediction_all[sl] = self.forward_(data[sl]).cpu()
+        if len(data) > stop:
+            prediction_all[stop:] = self.forward_(data[stop:]).cpu()
+        return prediction_all
+
+    def predict(self, data: torch.Tensor, out_shape: Tuple[int] = None,
+                num_batches: int = 1) -> torch.Tensor:
+        out_shape = data.shape if out_shape is None else (data.shape[0], *out_shape)
+        data = self.preprocess(data)
+        return self.batch_predict(data, out_shape, num_batches)
+
+
+class SegPredictor(BasePredictor):
+    """
+    Prediction with a trained fully convolutional neural network; arguments as in
+    atomai/predictors/predictor.py:124-188 (trained_model, refine, resize, use_gpu, logits,
+    **thresh, **d, **nb_classes, **downsampling).
+
+    Example:
+        >>> nn_output, coords = SegPredictor(trained_model, use_gpu=True).run(expdata)
+    """
+    def __init__(self, trained_model: Type[torch.nn.Module], refine: bool = False,
+                 resize: Union[Tuple, List] = None, use_gpu: bool = False, logits: bool = True,
+                 **kwargs: Union[int, float, bool]) -> None:
+        super(SegPredictor, self).__init__(trained_model, use_gpu)
+        set_train_rng(1)
+        self.nb_classes = kwargs.get('nb_classes', None)
+        if self.nb_classes is None:
+            self.nb_classes = get_nb_classes(trained_model)
+        self.downsampling = kwargs.get('downsampling', None)
+        if self.downsampling is None:
+            self.downsampling = get_downsample_factor(trained_model)
+        self.resize = resize
+        self.logits = logits
+        self.refine = refine
+        self.d = kwargs.get("d", None)
+        self.thresh = kwargs.get("thresh", .5)
+        self.use_gpu = use_gpu
+        self.verbose = kwargs.get("verbose", True)
+
+    def preprocess(self, image_data: np.ndarray, norm: bool = True) -> torch.Tensor:
+        """squeeze channel dim, optional resize, pad to the downsampling factor, global min-max
+        normalisation in float64 -> float32 (predictor.py:190-207)."""
+        if image_data.ndim == 2:
+            image_data = image_data[np.newaxis, ...]
+        elif image_data.ndim == 4:
+            if image_data.shape[-1] == 1:
+                image_data = image_data[..., 0]
+            elif image_data.shape[1] == 1:
+                image_data = image_data[:, 0, ...]
+        if self.resize is not None:
+            image_data = img_resize(image_data, self.resize)
+        image_data = img_pad(image_data, self.downsampling)
+        return torch_format_image(image_data, norm)
+
+    def forward_(self, images: torch.Tensor) -> torch.Tensor:
+        """Per-pixel class 'probabilities', channel-last, on the CPU (predictor.py:209-231)."""
+        images = images.to(self.device)
+        self.model.eval()
+        with torch.no_grad():
+            prob = self.model(images)
+        if self.logits:
+            prob = F.softmax(prob, dim=1) if self.nb_classes > 1 else torch.sigmoid(prob)
+        elif self.nb_classes > 1:
+            prob = torch.exp(prob)
+        return prob.permute(0, 2, 3, 1).cpu()
+
+    def predict(self, image_data: np.ndarray, return_image: bool = False,
+                **kwargs: int) -> Tuple[np.ndarray]:
+        """Make prediction (predictor.py:233-262): one image per batch for >= 256 px frames,
+        otherwise 10 batches, unless num_batches is given."""
+        image_data = self.preprocess(image_data, kwargs.get("norm", True))
+        n, _, w, h = image_data.shape
+        num_batches = kwargs.get("num_batches")
+        if num_batches is None:
+            num_batches = len(image_data) if (w >= 256 or h >= 256) else 10
+        segmented_imgs = self.batch_predict(image_data, (n, w, h, self.nb_classes), num_batches)
+        if return_image:
+            return image_data.permute(0, 2, 3, 1).numpy(), segmented_imgs.numpy()
+        return segmented_imgs.numpy()
+
+    def run(self, image_data: np.ndarray, compute_coords=True,
+            **kwargs: int) -> Tuple[np.ndarray, Dict[int, np.ndarray]]:
+        """Prediction + coordinates (predictor.py:264-298)."""
+        start_time = time.time()
+        if not compute_coords:
+            return self.predict(image_data, **kwargs)
+        images, decoded_imgs = self.predict(image_data, return_image=True, **kwargs)
+        loc = Locator(kwargs.get("thresh", self.thresh), refine=self.refine, d=self.d)
+        coordinates = loc.run(decoded_imgs, images)
+        if self.verbose:
+            n_images_str = " image was " if decoded_imgs.shape[0] == 1 else " images were "
+            print("\n" + str(decoded_imgs.shape[0]) + n_images_str +
+                  "decoded in approximately " +
+                  str(np.around(time.time() - start_time, decimals=4)) + ' seconds')
+        return decoded_imgs, coordinates
+
+
+class Locator:
+    """
+    Transforms pixel data from NN output into coordinate data
+    (atomai/predictors/predictor.py:531-639): threshold -> 4-connected components -> centre of
+    mass (of the thresholded image) -> drop coordinates within `dist_edge` px of the border.
+    Returns {frame: (n_atoms, 3) float64 [x, y, class]}.
+
+    Example:
+        >>> coordinates = Locator(dist_edge=10, refine=False).run(nn_output)
+    """
+    def __init__(self, threshold: float = 0.5, dist_edge: int = 5,
+                 dim_order: str = 'channel_last', **kwargs: Union[bool, float]) -> None:
+        self.dim_order = dim_order
+        self.threshold = threshold
+        self.dist_edge = dist_edge
+        self.refine = kwargs.get("refine")
+        self.d = kwargs.get("d")
+
+    def preprocess(self, nn_output: np.ndarray) -> np.ndarray:
+        if nn_output.shape[-1] == 1:   # add the background class for 1-channel data
+            nn_output = np.concatenate((nn_output, 1 - nn_output), axis=3)
+        if self.dim_order == 'channel_first':
+            nn_output = np.transpose(nn_output, (0, 2, 3, 1))
+        elif self.dim_order != 'channel_last':
+            raise NotImplementedError('For dim_order, use "channel_first"',
+                                      'or "channel_last" (e.g. tensorflow)')
+        return nn_output
+
+    def run(self, nn_output: np.ndarray, *args: np.ndarray) -> Dict[int, np.ndarray]:
+        nn_output = self.preprocess(nn_output)
+        h, w = nn_output.shape[1:3]
+        d_coord = {}
+        for i, decoded_img in enumerate(nn_output):
+            per_class = []
+            for ch in range(decoded_img.shape[2] - 1):   # background is always the last class
+                blobs = cv_thresh(decoded_img[:, :, ch], self.threshold)
+                coord_ch = self.rem_edge_coord(find_com(blobs), h, w)
+                per_class.append(np.concatenate(
+                    (coord_ch, np.zeros((coord_ch.shape[0], 1)) + ch), axis=1))
+            d_coord[i] = np.concatenate(per_class, axis=0) if per_class else np.empty((0, 3))
+        if self.refine:
+            raise NotImplementedError(
+                "2-D Gaussian peak refinement (atomai/utils/coords.py:179-231) is outside the "
+                "accelerated hot path; pass refine=False")
+        return d_coord
+
+    def rem_edge_coord(self, coordinates: np.ndarray, h: int, w: int) -> np.ndarray:
+        """Removes coordinates at the image edges (predictor.py:622-639)."""
+        if coordinates.shape[0] == 0:
+            return coordinates
+        e = self.dist_edge
+        bad = ((coordinates[:, 0] > h - e) | (coordinates[:, 0] < e) |
+               (coordinates[:, 1] > w - e) | (coordinates[:, 1] < e))
+        return coordinates[~bad]

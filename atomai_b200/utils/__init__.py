@@ -1,0 +1,9 @@
+from .coords import find_com, grid2xy, imcoordgrid, transform_coordinates
+from .img import cv_thresh, img_pad, img_resize
+from .nn import (average_weights, get_downsample_factor, get_nb_classes, gpu_usage_map,
+                 mock_forward, reset_bnorm, set_train_rng, weights_init)
+from .preproc import (array2list, check_image_dims, check_signal_dims, get_array_memsize,
+                      init_dataloader, init_dataloaders, init_fcnn_dataloaders,
+                      init_imspec_dataloaders, num_classes_from_labels,
+                      preprocess_training_image_data, preprocess_training_imspec_data,
+                      shard_batches, torch_format_image, torch_format_spectra)

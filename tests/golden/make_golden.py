@@ -34,7 +34,7 @@ def load_seeded(net, seed):
     return net
 
 
-def fcnn_case(tag, model, nb_classes, seed, n, h, w, **kw):
+def fcnn_case(tag, model, nb_classes, seed, n, h, w, logit_stride=1, **kw):
     """eval logits, train logits, loss, grads (sampled), BN running stats after one train fwd."""
     from atomai.nets import init_fcnn_model
     net, meta = init_fcnn_model(model, nb_classes, **kw)
@@ -50,6 +50,7 @@ def fcnn_case(tag, model, nb_classes, seed, n, h, w, **kw):
     net.eval()
     with torch.no_grad():
         out["logits_eval"] = net(x).numpy()
+    out["logit_stride"] = np.int64(logit_stride)
     net.train()
     net.zero_grad()
     logits = net(x)
@@ -78,6 +79,10 @@ def fcnn_case(tag, model, nb_classes, seed, n, h, w, **kw):
     out["adam_losses"] = np.array(losses, np.float64)
     out["adam_px_weight"] = net.px.weight.detach().numpy().copy()
     out["adam_c1_weight"] = net.c1.block[0].weight.detach().numpy().copy()
+    if logit_stride > 1:
+        out["logits_absmax"] = np.float64(np.abs(out["logits_eval"]).max())
+        out["logits_eval"] = gu.sample_flat(out["logits_eval"], logit_stride)
+        out["logits_train"] = gu.sample_flat(out["logits_train"], logit_stride)
     np.savez_compressed(os.path.join(HERE, f"{tag}.npz"), **out)
     print(tag, "loss", loss.item(), "adam", losses, "logits absmax", np.abs(out["logits_eval"]).max())
 
@@ -113,10 +118,14 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "locator":
         locator_case()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "big":
+        fcnn_case("unet_default_3c_128", "Unet", 3, 600, 4, 128, 128, logit_stride=5)
+        sys.exit(0)
     fcnn_case("unet_default_3c", "Unet", 3, 100, 2, 32, 48)
     fcnn_case("unet_nearest_1c", "Unet", 1, 200, 2, 32, 32, upsampling="nearest", nb_filters=8)
     fcnn_case("unet_dilated_3c", "Unet", 3, 300, 2, 64, 64, with_dilation=True)
     fcnn_case("unet_nobn_3c", "Unet", 3, 400, 2, 32, 32, batch_norm=False, layers=[2, 2, 2, 2])
     fcnn_case("dilnet_default_3c", "dilnet", 3, 500, 2, 32, 32)
+    fcnn_case("unet_default_3c_128", "Unet", 3, 600, 4, 128, 128, logit_stride=5)
     bfo_case()
     locator_case()

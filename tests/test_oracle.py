@@ -19,7 +19,15 @@ CASES = {
     "unet_nobn_3c": dict(model="Unet", nb_classes=3, seed=400, n=2, h=32, w=32,
                          cfg=dict(batch_norm=False, layers=[2, 2, 2, 2])),
     "dilnet_default_3c": dict(model="dilnet", nb_classes=3, seed=500, n=2, h=32, w=32, cfg={}),
+    "unet_default_3c_128": dict(model="Unet", nb_classes=3, seed=600, n=4, h=128, w=128, cfg={}),
 }
+
+
+def logits_view(arr, gold):
+    """Full logits, or the strided sample the larger goldens store."""
+    stride = int(gold["logit_stride"]) if "logit_stride" in gold.files else 1
+    arr = np.asarray(arr)
+    return arr if stride == 1 else gu.sample_flat(arr, stride)
 
 
 def build_case(name):
@@ -51,14 +59,15 @@ def test_oracle_matches_reference_goldens(name):
     _, sd, cfg, x, y, gold = build_case(name)
     with torch.no_grad():
         le = oracle_forward(name, sd, cfg, x, False)
-    np.testing.assert_allclose(le.numpy(), gold["logits_eval"], rtol=0, atol=2e-5)
+    np.testing.assert_allclose(logits_view(le.numpy(), gold), gold["logits_eval"], rtol=0, atol=2e-5)
     leaves = {k: v.clone().requires_grad_(True) for k, v in sd.items()
               if v.dtype.is_floating_point and "running_" not in k}
     work = dict(sd)
     work.update(leaves)
     stats = {}
     lt = oracle_forward(name, work, cfg, x, True, stats)
-    np.testing.assert_allclose(lt.detach().numpy(), gold["logits_train"], rtol=0, atol=2e-5)
+    np.testing.assert_allclose(logits_view(lt.detach().numpy(), gold), gold["logits_train"], rtol=0,
+                               atol=2e-5)
     loss = nets_ref.seg_loss(lt, y, cfg["nb_classes"])
     assert abs(float(loss) - float(gold["loss_train"])) < 1e-5
     loss.backward()

@@ -76,31 +76,33 @@ def unet():
     from atomai_b200.losses_metrics import select_loss
     import golden_utils as gu
     out = {}
-    for math in ("fp32", "tf32"):
-        ab.set_math(math)
+    for math in ("fp32", "tf32", "tf32_simtwgrad"):
+        ab.set_math(math.split("_")[0], wgrad_tc=(math != "tf32_simtwgrad"))
         for name in CASES:
             try:
                 net, sd, cfg, x, y, gold = build_case(name)
                 net = net.to(dev); x = x.to(dev); y = y.to(dev)
                 net.eval()
                 with torch.no_grad(): le = net(x)
-                r = {"eval": float(np.abs(le.cpu().numpy() - gold["logits_eval"]).max() / np.abs(gold["logits_eval"]).max())}
+                from test_oracle import logits_view
+                r = {"eval": float(np.abs(logits_view(le.cpu().numpy(), gold) - gold["logits_eval"]).max() / np.abs(gold["logits_eval"]).max())}
                 net.train(); net.zero_grad()
                 lt = net(x)
-                r["train"] = float(np.abs(lt.detach().cpu().numpy() - gold["logits_train"]).max() / np.abs(gold["logits_train"]).max())
+                r["train"] = float(np.abs(logits_view(lt.detach().cpu().numpy(), gold) - gold["logits_train"]).max() / np.abs(gold["logits_train"]).max())
                 loss = select_loss("ce", cfg["nb_classes"])(lt, y)
                 r["loss"] = [loss.item(), float(gold["loss_train"])]
                 loss.backward()
-                worst = ("", 0.0); worstn = ("", 0.0)
+                worst = ("", 0.0); worstn = ("", 0.0); te = tr = 0.0
                 for k, p in net.named_parameters():
                     gg = p.grad.detach().cpu().numpy(); ref = gold["grad/" + k]
                     got = gu.sample_flat(gg, 97) if gg.size > 4096 else gg
+                    te += float(((got.reshape(-1) - ref.reshape(-1)).astype(np.float64) ** 2).sum()); tr += float((ref.reshape(-1).astype(np.float64) ** 2).sum())
                     scale = max(float(gold["gradnorm/" + k]) / np.sqrt(gg.size), 1e-8)
                     e = float(np.abs(got.reshape(-1) - ref.reshape(-1)).max() / scale)
                     if e > worst[1]: worst = (k, e)
                     en = abs(float(np.linalg.norm(gg.astype(np.float64))) - float(gold["gradnorm/" + k])) / (float(gold["gradnorm/" + k]) + 1e-12)
                     if en > worstn[1]: worstn = (k, en)
-                r["grad_worst_elem_over_rms"] = worst; r["gradnorm_worst_rel"] = worstn
+                r["grad_worst_elem_over_rms"] = worst; r["gradnorm_worst_rel"] = worstn; r["grel"] = (te / tr) ** 0.5
                 rb = 0.0
                 for k, b in net.named_buffers():
                     if "running" in k:
