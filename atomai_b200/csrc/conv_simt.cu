@@ -74,7 +74,8 @@ __global__ void __launch_bounds__(F_THREADS) conv_simt_fwd_kernel(const ConvSimt
       s_w[i] = v;
     }
     __syncthreads();
-    for (int c = 0; c < F_CIT; ++c) {
+    const int cmax = min(F_CIT, Cin - ci0);
+    for (int c = 0; c < cmax; ++c) {
       for (int t = 0; t < taps; ++t) {
         const int ty = t / p.tw, tx = t - ty * p.tw;
         const float* ip = s_in + (c * THp + r + ty * p.dil) * TWp + wq + tx * p.dil;
@@ -132,6 +133,116 @@ __global__ void __launch_bounds__(F_THREADS) conv_simt_fwd_kernel(const ConvSimt
       atomicAdd(p.stats + p.Cout + co0 + tid, (double)s_red[F_COT + tid]);
     }
   }
+}
+
+
+// ------------------------------------------------------------------ thin-channel specialisations
+// The first layer (Cin = 1, 3x3) and the pixel-wise head / its data-gradient (1x1 with <= 4 or
+// from <= 4 channels) are pure HBM streams: one thread per pixel, all output channels in
+// registers, weights broadcast from shared memory, float4 stores.
+template <int CO>
+__global__ void __launch_bounds__(256) conv_pix_kernel(const ConvSimtParams p, int vec_in) {
+  extern __shared__ float s_w[];                 // [taps][Cin][CO] (zero padded to CO)
+  __shared__ float s_red[2 * CO];
+  const int taps = p.th * p.tw, Cin = p.S.Ctot;
+  for (int i = threadIdx.x; i < taps * Cin * CO; i += blockDim.x) {
+    const int co = i % CO, r = i / CO;
+    s_w[i] = co < p.Cout ? __ldg(p.w + (size_t)r * p.Cout + co) : 0.f;
+  }
+  if (threadIdx.x < 2 * CO) s_red[threadIdx.x] = 0.f;
+  __syncthreads();
+  float bias[CO];
+#pragma unroll
+  for (int k = 0; k < CO; ++k) bias[k] = (p.bias && k < p.Cout) ? __ldg(p.bias + k) : 0.f;
+  float ssum[CO], ssq[CO];
+#pragma unroll
+  for (int k = 0; k < CO; ++k) { ssum[k] = 0.f; ssq[k] = 0.f; }
+  const int64_t npix = (int64_t)p.N * p.H * p.W;
+  const int ph = p.dil * (p.th >> 1), pw = p.dil * (p.tw >> 1);
+  for (int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pix < npix;
+       pix += (int64_t)gridDim.x * blockDim.x) {
+    const int w = (int)(pix % p.W);
+    const int h = (int)((pix / p.W) % p.H);
+    const int n = (int)(pix / ((int64_t)p.W * p.H));
+    float acc[CO];
+#pragma unroll
+    for (int k = 0; k < CO; ++k) acc[k] = bias[k];
+    for (int t = 0; t < taps; ++t) {
+      const int ty = t / p.tw, tx = t - ty * p.tw;
+      const int hh = h - ph + ty * p.dil, ww = w - pw + tx * p.dil;
+      const float* wt = s_w + (size_t)t * Cin * CO;
+      if (vec_in) {
+        for (int c = 0; c < Cin; c += 4) {
+          const float4 x = load_src4(p.S, n, hh, ww, p.H, p.W, c);
+#pragma unroll
+          for (int k = 0; k < CO; ++k)
+            acc[k] = fmaf(x.x, wt[c * CO + k], fmaf(x.y, wt[(c + 1) * CO + k],
+                     fmaf(x.z, wt[(c + 2) * CO + k], fmaf(x.w, wt[(c + 3) * CO + k], acc[k]))));
+        }
+      } else {
+        for (int c = 0; c < Cin; ++c) {
+          const float x = load_src1(p.S, n, hh, ww, p.H, p.W, c);
+#pragma unroll
+          for (int k = 0; k < CO; ++k) acc[k] = fmaf(x, wt[c * CO + k], acc[k]);
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < CO; ++k) {
+      acc[k] = act_f(acc[k], p.act, p.alpha);
+      ssum[k] += acc[k];
+      ssq[k] = fmaf(acc[k], acc[k], ssq[k]);
+    }
+    if (!p.out_nchw) {
+      float* o = p.out + pix * p.ld_out;
+      if (CO % 4 == 0 && p.Cout == CO && (p.ld_out & 3) == 0) {
+#pragma unroll
+        for (int k = 0; k < CO; k += 4)
+          *reinterpret_cast<float4*>(o + k) = make_float4(acc[k], acc[k + 1], acc[k + 2], acc[k + 3]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < CO; ++k)
+          if (k < p.Cout) o[k] = acc[k];
+      }
+    } else {
+      const size_t hw = (size_t)p.H * p.W;
+#pragma unroll
+      for (int k = 0; k < CO; ++k)
+        if (k < p.Cout) p.out[((size_t)n * p.Cout + k) * hw + (size_t)h * p.W + w] = acc[k];
+    }
+  }
+  if (p.stats) {
+#pragma unroll
+    for (int k = 0; k < CO; ++k) {
+      const float a = warp_sum(ssum[k]), b = warp_sum(ssq[k]);
+      if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&s_red[k], a);
+        atomicAdd(&s_red[CO + k], b);
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < CO && threadIdx.x < p.Cout) {
+      atomicAdd(p.stats + threadIdx.x, (double)s_red[threadIdx.x]);
+      atomicAdd(p.stats + p.Cout + threadIdx.x, (double)s_red[CO + threadIdx.x]);
+    }
+  }
+}
+
+template <int CO>
+int launch_conv_pix(const ConvSimtParams& p, cudaStream_t stream) {
+  const int taps = p.th * p.tw, Cin = p.S.Ctot;
+  const size_t smem = (size_t)taps * Cin * CO * sizeof(float);
+  const int64_t npix = (int64_t)p.N * p.H * p.W;
+  int vec = (Cin % 4 == 0);
+  for (int i = 0; i < p.S.nsrc; ++i)
+    if (p.S.s[i].C % 4 != 0 || p.S.s[i].ld % 4 != 0 || ((uintptr_t)p.S.s[i].ptr & 15)) vec = 0;
+  int64_t blocks = (npix + 256 * 4 - 1) / (256 * 4);
+  const int64_t cap = (int64_t)ab_num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  conv_pix_kernel<CO><<<(unsigned)blocks, 256, smem, stream>>>(p, vec);
+  AB_LAUNCH_CHECK();
+  return 0;
 }
 
 // ------------------------------------------------------------------ weight gradient
@@ -216,6 +327,79 @@ __global__ void __launch_bounds__(G_THREADS) conv_simt_wgrad_kernel(const WgradS
   }
 }
 
+// ------------------------------------------------------------------ weight gradient, tiny shapes
+// First layer (Cin = 1) and the pixel-wise head (Cout = nb_classes): the 64 x 64 register tiling
+// above would waste > 95 % of its FMAs, so here every thread walks pixels and keeps the whole
+// CO x CI x TW slice of dW in registers; one warp-shuffle reduction + atomics per CTA at the end.
+// grid: (pixel ranges, tap rows (ks_h), co-groups * ci-groups).
+template <int CO, int CI, int TW>
+__global__ void __launch_bounds__(256) wgrad_small_kernel(const WgradSimtParams p, int co_groups) {
+  const int ty = blockIdx.y;
+  const int cog = blockIdx.z % co_groups, cig = blockIdx.z / co_groups;
+  const int co0 = cog * CO, ci0 = cig * CI;
+  const int Cin = p.S.Ctot;
+  const int dh = (ty - (p.th >> 1)) * p.dil;
+  float acc[CO][CI][TW];
+#pragma unroll
+  for (int a = 0; a < CO; ++a)
+#pragma unroll
+    for (int b = 0; b < CI; ++b)
+#pragma unroll
+      for (int t = 0; t < TW; ++t) acc[a][b][t] = 0.f;
+  for (int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pix < p.npix;
+       pix += (int64_t)gridDim.x * blockDim.x) {
+    const int w = (int)(pix % p.W);
+    const int h = (int)((pix / p.W) % p.H);
+    const int n = (int)(pix / ((int64_t)p.W * p.H));
+    float d[CO];
+#pragma unroll
+    for (int a = 0; a < CO; ++a)
+      d[a] = (co0 + a < p.Cout) ? __ldg(p.dy + pix * p.ld_dy + co0 + a) : 0.f;
+#pragma unroll
+    for (int t = 0; t < TW; ++t) {
+      const int dw_ = (t - (p.tw >> 1)) * p.dil;
+#pragma unroll
+      for (int b = 0; b < CI; ++b) {
+        const float x = (ci0 + b < Cin) ? load_src1(p.S, n, h + dh, w + dw_, p.H, p.W, ci0 + b) : 0.f;
+#pragma unroll
+        for (int a = 0; a < CO; ++a) acc[a][b][t] = fmaf(d[a], x, acc[a][b][t]);
+      }
+    }
+  }
+  __shared__ float s_acc[CO * CI * TW];
+  for (int i = threadIdx.x; i < CO * CI * TW; i += blockDim.x) s_acc[i] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int a = 0; a < CO; ++a)
+#pragma unroll
+    for (int b = 0; b < CI; ++b)
+#pragma unroll
+      for (int t = 0; t < TW; ++t) {
+        const float v = warp_sum(acc[a][b][t]);
+        if ((threadIdx.x & 31) == 0) atomicAdd(&s_acc[(a * CI + b) * TW + t], v);
+      }
+  __syncthreads();
+  const int taps = p.th * p.tw;
+  for (int i = threadIdx.x; i < CO * CI * TW; i += blockDim.x) {
+    const int t = i % TW, b = (i / TW) % CI, a = i / (TW * CI);
+    if (co0 + a < p.Cout && ci0 + b < Cin)
+      atomicAdd(p.dw + ((size_t)(co0 + a) * Cin + ci0 + b) * taps + ty * p.tw + t, s_acc[i]);
+  }
+}
+
+template <int CO, int CI, int TW>
+int launch_wgrad_small(const WgradSimtParams& p, cudaStream_t stream) {
+  const int co_groups = (p.Cout + CO - 1) / CO, ci_groups = (p.S.Ctot + CI - 1) / CI;
+  int64_t bx = (p.npix + 256 * 16 - 1) / (256 * 16);
+  const int64_t cap = (int64_t)ab_num_sms() * 4;
+  if (bx > cap) bx = cap;
+  if (bx < 1) bx = 1;
+  dim3 grid((unsigned)bx, p.th, co_groups * ci_groups);
+  wgrad_small_kernel<CO, CI, TW><<<grid, 256, 0, stream>>>(p, co_groups);
+  AB_LAUNCH_CHECK();
+  return 0;
+}
+
 // W[co][ci][ty][tx] -> [tap][Cin][Cout] (FWD) ; dgrad: out[tap][co][ci] with flipped taps
 __global__ void pack_weights_simt_kernel(const float* __restrict__ w, int Cout, int Cin, int th,
                                          int tw, int mode, float* __restrict__ out,
@@ -257,6 +441,16 @@ int ab_conv_simt_fwd(const ab_conv_t* d, const float* w, const float* bias, floa
   p.out_nchw = d->out_nchw; p.stats = stats;
   p.tiles_h = (d->H + F_TH - 1) / F_TH;
   p.tiles_w = (d->W + F_TW - 1) / F_TW;
+  // thin-channel specialisations (first layer, pixel-wise head and its data-gradient)
+  {
+    const int Cin = p.S.Ctot, taps = d->ks_h * d->ks_w;
+    if (taps * Cin <= 64 && d->N * (int64_t)d->H * d->W > 0) {
+      if (d->Cout <= 4) return launch_conv_pix<4>(p, stream);
+      if (d->Cout == 8) return launch_conv_pix<8>(p, stream);
+      if (d->Cout == 16) return launch_conv_pix<16>(p, stream);
+      if (d->Cout == 32) return launch_conv_pix<32>(p, stream);
+    }
+  }
   const int ph = d->dil * (d->ks_h >> 1), pw = d->dil * (d->ks_w >> 1);
   const int smem = (F_CIT * (F_TH + 2 * ph) * (F_TW + 2 * pw) + d->ks_h * d->ks_w * F_CIT * F_COT) *
                    (int)sizeof(float);
@@ -287,6 +481,11 @@ int ab_conv_simt_wgrad(const ab_conv_t* d, const float* dy, int ld_dy, float* dw
   if (p.npix == 0) return 0;
   p.co_tiles = (d->Cout + G_CT - 1) / G_CT;
   p.ci_tiles = (p.S.Ctot + G_CT - 1) / G_CT;
+  p.px_per_cta = 0;
+  if (p.S.Ctot <= 2 && d->ks_w == 3) return launch_wgrad_small<16, 1, 3>(p, stream);
+  if (p.S.Ctot <= 2 && d->ks_w == 1) return launch_wgrad_small<16, 2, 1>(p, stream);
+  if (d->Cout <= 4 && d->ks_w == 1) return launch_wgrad_small<4, 16, 1>(p, stream);
+  if (d->Cout <= 4 && d->ks_w == 3) return launch_wgrad_small<4, 4, 3>(p, stream);
   const int taps = d->ks_h * d->ks_w;
   const int64_t per_range_ctas = (int64_t)taps * p.co_tiles * p.ci_tiles;
   int64_t ranges = (4ll * ab_num_sms() + per_range_ctas - 1) / per_range_ctas;  // ~4 waves

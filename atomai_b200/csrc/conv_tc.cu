@@ -4,7 +4,9 @@
 //   warps 0-3   epilogue   TMEM -> regs -> bias + LeakyReLU -> NHWC/NCHW store + BN statistics
 //   warp  4     MMA issue  one elected lane issues tcgen05.mma for every (k-chunk, tap, k-step)
 //   warp  5     weights    TMEM alloc + cp.async.bulk of pre-packed weight blobs (L2 -> smem)
-//   warps 6-13  loaders    HBM/L2 -> regs -> [BN affine, 2x2 max-pool, zero pad, RN->TF32] -> smem
+//   warps 8-15  loaders    HBM/L2 -> regs -> [BN affine, 2x2 max-pool, zero pad, RN->TF32] -> smem
+//                          (two groups of 4 warps working on alternate k-chunks; setmaxnreg moves
+//                          registers from the MMA/epilogue warpgroups to the loaders)
 //
 // GEMM view: M = 128 output pixels (a 16 x 8 tile), N = Cout, K = taps * Cin.
 // The activation halo tile is loaded ONCE per 32-channel chunk and re-used by all nine taps: it
@@ -25,13 +27,16 @@ constexpr int kTileW = 8;
 constexpr int kNumEpiWarps = 4;
 constexpr int kMmaWarp = 4;
 constexpr int kWgtWarp = 5;
-constexpr int kFirstLoadWarp = 6;
+constexpr int kFirstLoadWarp = 8;   // warps 6,7 idle: roles are aligned to 4-warp groups (setmaxnreg)
 constexpr int kNumLoadWarps = 8;
-constexpr int kNumLoadThreads = kNumLoadWarps * 32;
-constexpr int kThreads = (kFirstLoadWarp + kNumLoadWarps) * 32;  // 448
+constexpr int kThreads = (kFirstLoadWarp + kNumLoadWarps) * 32;  // 512 -> 128 regs/thread at launch
+// register re-balancing between the warpgroups (sum * 128 threads = 64K registers)
+constexpr int kRegsEpi = 80, kRegsMma = 48, kRegsLoad = 192;
+static_assert(kRegsEpi + kRegsMma + 2 * kRegsLoad == 512, "register budget");
 constexpr int kMaxAStages = 4;
-constexpr int kMaxBStages = 6;
-constexpr int kMaxLoadsPerThread = 8;  // register-staged 16B loads per thread per chunk
+constexpr int kMaxBStages = 12;
+constexpr int kGroupThreads = 128;  // loader threads per group (2 groups of 4 warps)
+constexpr int kMaxU = 12;           // register-staged 16B elements per loader thread per chunk
 
 struct ConvTcParams {
   SrcSet S;
@@ -52,23 +57,30 @@ struct ConvTcParams {
   int plane_bytes;   // stride between 4-channel planes (== 128/P mod 128 -> conflict-free STS)
   int a_stage_bytes, b_stage_bytes;
   int n_a, n_b;      // pipeline depths
-  int tmem_cols;     // power of two >= 2*Cout
+  int tmem_cols;     // power of two >= 2*sub*Cout
+  int sub;           // 8-pixel-wide sub-tiles per CTA tile (1 or 2): M = 128*sub per weight stage
+  int w_resident;    // 1: all weights live in shared memory for the whole kernel
+  int w_bytes;       // taps * Ctot * Cout * 4
 };
 
 struct __align__(8) SharedCtl {
   uint64_t full_a[kMaxAStages], empty_a[kMaxAStages];
   uint64_t full_b[kMaxBStages], empty_b[kMaxBStages];
   uint64_t tmem_full[2], tmem_empty[2];
+  uint64_t w_full;
   uint32_t tmem_base;
   uint32_t pad;
 };
 
+static_assert(sizeof(SharedCtl) <= 320, "SharedCtl must fit below the MMA offset table");
+
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   SharedCtl* ctl = reinterpret_cast<SharedCtl*>(smem);
-  float* s_stats = reinterpret_cast<float*>(smem + 256);  // [4 warps][2][Cout]
+  uint2* mma_tab = reinterpret_cast<uint2*>(smem + 320);   // [taps * ksteps] <= 36 entries
+  float* s_stats = reinterpret_cast<float*>(smem + 640);  // [4 warps][2][Cout]
   const uint32_t stats_bytes = kNumEpiWarps * 2 * p.Cout * sizeof(float);
-  const uint32_t a_base = smem_u32(smem) + ((256 + stats_bytes + 127) & ~127u);
+  const uint32_t a_base = smem_u32(smem) + ((640 + stats_bytes + 127) & ~127u);
   const uint32_t b_base = a_base + p.n_a * p.a_stage_bytes;
 
   const int warp = threadIdx.x >> 5;
@@ -77,7 +89,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.n_a; ++i) {
-      mbar_init(smem_u32(&ctl->full_a[i]), kNumLoadWarps);
+      mbar_init(smem_u32(&ctl->full_a[i]), kNumLoadWarps / 2);
       mbar_init(smem_u32(&ctl->empty_a[i]), 1);
     }
     for (int i = 0; i < p.n_b; ++i) {
@@ -88,6 +100,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
       mbar_init(smem_u32(&ctl->tmem_full[i]), 1);
       mbar_init(smem_u32(&ctl->tmem_empty[i]), kNumEpiWarps);
     }
+    mbar_init(smem_u32(&ctl->w_full), 1);
     fence_barrier_init();
   }
   if (warp == kWgtWarp) tmem_alloc(smem_u32(&ctl->tmem_base), p.tmem_cols);
@@ -100,123 +113,243 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
   const uint32_t tmem_base = ctl->tmem_base;
 
   if (warp >= kFirstLoadWarp) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsLoad));
     // ===================== activation loaders =====================
-    const int lt = threadIdx.x - kFirstLoadWarp * 32;
+    // Two groups of 4 warps; group g stages the k-chunks with (global chunk counter & 1) == g, so
+    // two chunks are always in flight per SM.  Per thread the (halo row, halo col) of each of its
+    // <= kMaxU 16-byte elements is fixed for the whole kernel (no divisions in the loop); loads
+    // are issued branch-free from clamped addresses and masked afterwards, so the compiler keeps
+    // all of them in flight before the first use.
+    const int grp = (warp - kFirstLoadWarp) >> 2;
+    const int gt = threadIdx.x - (kFirstLoadWarp + grp * 4) * 32;   // 0..127
     const int P = p.KC >> 2;                   // planes per chunk
     const int elems = p.HP * P;                // 16B elements per chunk stage
-    const int j = lt % P;                      // this thread's plane (constant: 256 % P == 0)
+    const int j = gt % P;                      // this thread's plane (constant: 128 % P == 0)
+    const int U = (elems + kGroupThreads - 1) / kGroupThreads;     // <= kMaxU (plan guarantees)
+    uint32_t hw[kMaxU];
+#pragma unroll
+    for (int u = 0; u < kMaxU; ++u) {
+      const int e = gt + u * kGroupThreads;
+      hw[u] = 0xFFFFFFFFu;
+      if (u < U && e < elems) {
+        const int q = e / P;
+        const int hh = q / p.TWp;
+        hw[u] = ((uint32_t)hh << 16) | (uint32_t)(q - hh * p.TWp);
+      }
+    }
+    const int H = p.H, W = p.W;
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const int tw_i = tile % p.tiles_w;
       const int th_i = (tile / p.tiles_w) % p.tiles_h;
       const int n = tile / (p.tiles_w * p.tiles_h);
       const int h_org = th_i * kTileH - p.dil * (p.taps_h >> 1);
-      const int w_org = tw_i * kTileW - p.dil * (p.taps_w >> 1);
+      const int w_org = tw_i * kTileW * p.sub - p.dil * (p.taps_w >> 1);
       for (int ch = 0; ch < p.n_chunks; ++ch, ++it) {
-        const int c = ch * p.KC + j * 4;
-        float4 v[kMaxLoadsPerThread];
+        if ((int)(it & 1) != grp) continue;
+        int c = ch * p.KC + j * 4;
+        const SrcDev* sp = &p.S.s[0];
+        if (p.S.nsrc > 1 && c >= p.S.s[0].C) {
+          sp = &p.S.s[1];
+          c -= p.S.s[0].C;
+        }
+        const int ld = sp->ld;
+        const bool pool = sp->pool != 0;
+        float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (sp->scale) {
+          sc = __ldg(reinterpret_cast<const float4*>(sp->scale + c));
+          sh = __ldg(reinterpret_cast<const float4*>(sp->shift + c));
+        }
+        const float* base = sp->ptr + c;
+        float4 v[kMaxU];
+        uint32_t okmask = 0;
+        if (!pool) {
+          const size_t img = (size_t)n * H;
 #pragma unroll
-        for (int u = 0; u < kMaxLoadsPerThread; ++u) {
-          const int e = lt + u * kNumLoadThreads;
-          if (e < elems) {
-            const int q = e / P;
-            const int hh = q / p.TWp, ww = q - hh * p.TWp;
-            v[u] = load_src4(p.S, n, h_org + hh, w_org + ww, p.H, p.W, c);
+          for (int u = 0; u < kMaxU; ++u) {
+            if (u < U) {
+              const int gh = h_org + (int)(hw[u] >> 16), gw = w_org + (int)(hw[u] & 0xFFFFu);
+              const bool ok = hw[u] != 0xFFFFFFFFu && (unsigned)gh < (unsigned)H &&
+                              (unsigned)gw < (unsigned)W;
+              const int ghc = min(max(gh, 0), H - 1), gwc = min(max(gw, 0), W - 1);
+              v[u] = __ldg(reinterpret_cast<const float4*>(base + ((img + ghc) * W + gwc) * ld));
+              okmask |= (ok ? 1u : 0u) << u;
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < kMaxU; ++u) {
+            if (u < U) {
+              v[u].x = fmaf(v[u].x, sc.x, sh.x);
+              v[u].y = fmaf(v[u].y, sc.y, sh.y);
+              v[u].z = fmaf(v[u].z, sc.z, sh.z);
+              v[u].w = fmaf(v[u].w, sc.w, sh.w);
+            }
+          }
+        } else {
+          const int H2 = 2 * H, W2 = 2 * W;
+          const size_t img = (size_t)n * H2;
+          const size_t rs = (size_t)W2 * ld;
+#pragma unroll
+          for (int u = 0; u < kMaxU; ++u) {
+            if (u < U) {
+              const int gh = h_org + (int)(hw[u] >> 16), gw = w_org + (int)(hw[u] & 0xFFFFu);
+              const bool ok = hw[u] != 0xFFFFFFFFu && (unsigned)gh < (unsigned)H &&
+                              (unsigned)gw < (unsigned)W;
+              const int ghc = min(max(gh, 0), H - 1), gwc = min(max(gw, 0), W - 1);
+              const float* q0 = base + ((img + 2 * ghc) * W2 + 2 * gwc) * ld;
+              const float4 a0 = __ldg(reinterpret_cast<const float4*>(q0));
+              const float4 a1 = __ldg(reinterpret_cast<const float4*>(q0 + ld));
+              const float4 a2 = __ldg(reinterpret_cast<const float4*>(q0 + rs));
+              const float4 a3 = __ldg(reinterpret_cast<const float4*>(q0 + rs + ld));
+              v[u].x = fmaxf(fmaxf(fmaf(a0.x, sc.x, sh.x), fmaf(a1.x, sc.x, sh.x)),
+                             fmaxf(fmaf(a2.x, sc.x, sh.x), fmaf(a3.x, sc.x, sh.x)));
+              v[u].y = fmaxf(fmaxf(fmaf(a0.y, sc.y, sh.y), fmaf(a1.y, sc.y, sh.y)),
+                             fmaxf(fmaf(a2.y, sc.y, sh.y), fmaf(a3.y, sc.y, sh.y)));
+              v[u].z = fmaxf(fmaxf(fmaf(a0.z, sc.z, sh.z), fmaf(a1.z, sc.z, sh.z)),
+                             fmaxf(fmaf(a2.z, sc.z, sh.z), fmaf(a3.z, sc.z, sh.z)));
+              v[u].w = fmaxf(fmaxf(fmaf(a0.w, sc.w, sh.w), fmaf(a1.w, sc.w, sh.w)),
+                             fmaxf(fmaf(a2.w, sc.w, sh.w), fmaf(a3.w, sc.w, sh.w)));
+              okmask |= (ok ? 1u : 0u) << u;
+            }
           }
         }
         const uint32_t st = it % p.n_a;
         mbar_wait(smem_u32(&ctl->empty_a[st]), ((it / p.n_a) & 1) ^ 1);
         const uint32_t dst = a_base + st * p.a_stage_bytes + j * p.plane_bytes;
 #pragma unroll
-        for (int u = 0; u < kMaxLoadsPerThread; ++u) {
-          const int e = lt + u * kNumLoadThreads;
-          if (e < elems) {
-            const int q = e / P;
+        for (int u = 0; u < kMaxU; ++u) {
+          if (u < U && hw[u] != 0xFFFFFFFFu) {
+            const bool ok = (okmask >> u) & 1u;
+            const uint32_t q = (hw[u] >> 16) * p.TWp + (hw[u] & 0xFFFFu);
             asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + q * 16),
-                         "f"(to_tf32(v[u].x)), "f"(to_tf32(v[u].y)), "f"(to_tf32(v[u].z)),
-                         "f"(to_tf32(v[u].w))
+                         "f"(ok ? to_tf32(v[u].x) : 0.f), "f"(ok ? to_tf32(v[u].y) : 0.f),
+                         "f"(ok ? to_tf32(v[u].z) : 0.f), "f"(ok ? to_tf32(v[u].w) : 0.f)
                          : "memory");
           }
-        }
-        // remaining elements (large dilation halos) go through a plain loop
-        for (int e = lt + kMaxLoadsPerThread * kNumLoadThreads; e < elems;
-             e += kNumLoadThreads) {
-          const int q = e / P;
-          const int hh = q / p.TWp, ww = q - hh * p.TWp;
-          const float4 x = load_src4(p.S, n, h_org + hh, w_org + ww, p.H, p.W, c);
-          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + q * 16),
-                       "f"(to_tf32(x.x)), "f"(to_tf32(x.y)), "f"(to_tf32(x.z)), "f"(to_tf32(x.w))
-                       : "memory");
         }
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&ctl->full_a[st]));
       }
     }
-  } else if (warp == kWgtWarp) {
+  } else if (warp >= kNumEpiWarps) {
+   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsMma));
+   if (warp == kWgtWarp) {
     // ===================== weight producer =====================
     if (lane == 0) {
-      uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        for (int ch = 0; ch < p.n_chunks; ++ch) {
-          for (int t = 0; t < taps; ++t, ++it) {
-            const uint32_t st = it % p.n_b;
-            mbar_wait(smem_u32(&ctl->empty_b[st]), ((it / p.n_b) & 1) ^ 1);
-            const uint32_t bar = smem_u32(&ctl->full_b[st]);
-            mbar_arrive_expect_tx(bar, p.b_stage_bytes);
-            const int ksteps = p.KC >> 3;
-            const uint32_t piece = p.Cout * 32;  // bytes of one (k-step, tap) piece
-            for (int ks = 0; ks < ksteps; ++ks)
-              bulk_g2s(b_base + st * p.b_stage_bytes + ks * piece,
-                       p.wblob + ((size_t)(ch * ksteps + ks) * taps + t) * (piece >> 2), piece,
-                       bar);
+      if (p.w_resident) {
+        // the packed blob is already in shared-memory order: copy it once, in 16 KB pieces
+        const uint32_t bar = smem_u32(&ctl->w_full);
+        mbar_arrive_expect_tx(bar, p.w_bytes);
+        for (int off = 0; off < p.w_bytes; off += 16384) {
+          const int n = min(16384, p.w_bytes - off);
+          bulk_g2s(b_base + off, reinterpret_cast<const char*>(p.wblob) + off, n, bar);
+        }
+      } else {
+        uint32_t it = 0;
+        const int ksteps = p.KC >> 3;
+        const uint32_t piece = p.Cout * 32;  // bytes of one (k-step, tap) piece
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+          for (int ch = 0; ch < p.n_chunks; ++ch) {
+            for (int t = 0; t < taps; ++t, ++it) {
+              const uint32_t st = it % p.n_b;
+              mbar_wait(smem_u32(&ctl->empty_b[st]), ((it / p.n_b) & 1) ^ 1);
+              const uint32_t bar = smem_u32(&ctl->full_b[st]);
+              mbar_arrive_expect_tx(bar, p.b_stage_bytes);
+              for (int ks = 0; ks < ksteps; ++ks)
+                bulk_g2s(b_base + st * p.b_stage_bytes + ks * piece,
+                         p.wblob + ((size_t)(ch * ksteps + ks) * taps + t) * (piece >> 2), piece,
+                         bar);
+            }
           }
         }
       }
     }
     __syncwarp();
-  } else if (warp == kMmaWarp) {
+   } else if (warp == kMmaWarp) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // One thread issues every tcgen05.mma, so its instruction count per MMA bounds the kernel for
+    // the thin layers (an M128 x N16 x K8 MMA is 8 tensor-pipe cycles).  All descriptor
+    // arithmetic is hoisted: a table of (A offset, B offset) per (tap, k-step) in shared memory,
+    // constant descriptor high words, and a loop body of two adds + the MMA.
+    {   // the whole warp runs the (uniform) control flow; one elected lane issues MMAs/commits
       const uint32_t idesc = umma_idesc_tf32(128, p.Cout, 0, 0);
-      const uint32_t a_sbo = p.TWp * 16, a_lbo = p.plane_bytes;
-      const uint32_t b_sbo = 128, b_lbo = p.Cout * 16;
+      const uint32_t piece = p.Cout * 32;
       const int ksteps = p.KC >> 3;
+      const int nmma = taps * ksteps;                 // MMAs per chunk (per sub-tile)
+      const uint64_t a_tmpl = umma_desc(0, p.plane_bytes, p.TWp * 16);
+      const uint64_t b_tmpl = umma_desc(0, p.Cout * 16, 128);
+      for (int t = 0; t < taps; ++t) {
+        const int ty = t / p.taps_w, tx = t - ty * p.taps_w;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const uint32_t ao = (ty * p.dil * p.TWp + tx * p.dil) * 16 + ks * 2 * p.plane_bytes;
+          const uint32_t bo = p.w_resident ? (uint32_t)(t + ks * taps) * piece : ks * piece;
+          if (lane == 0) mma_tab[t * ksteps + ks] = make_uint2(ao >> 4, bo >> 4);
+        }
+      }
+      __syncwarp();
       uint32_t ita = 0, itb = 0, acc = 0, acc_phase = 0;
+      const uint32_t sub = p.sub, n_a = p.n_a, n_b = p.n_b, n_chunks = p.n_chunks;
+      const uint32_t a_stage16 = p.a_stage_bytes >> 4, b_stage16 = p.b_stage_bytes >> 4;
+      const uint32_t a_base16 = a_base >> 4, b_base16 = b_base >> 4;
+      const uint32_t chunk_w16 = (uint32_t)(ksteps * taps) * piece >> 4;   // resident weights per chunk
+      const uint32_t cout = p.Cout;
+      const bool resident = p.w_resident != 0;
+      if (resident) {
+        mbar_wait(smem_u32(&ctl->w_full), 0);
+        tc_fence_after();
+      }
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         mbar_wait(smem_u32(&ctl->tmem_empty[acc]), acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * p.Cout;
-        uint32_t first = 1;
-        for (int ch = 0; ch < p.n_chunks; ++ch, ++ita) {
-          const uint32_t sa = ita % p.n_a;
-          mbar_wait(smem_u32(&ctl->full_a[sa]), (ita / p.n_a) & 1);
+        const uint32_t d_tmem = tmem_base + acc * sub * cout;
+        for (uint32_t ch = 0; ch < n_chunks; ++ch, ++ita) {
+          const uint32_t sa = ita % n_a;
+          mbar_wait(smem_u32(&ctl->full_a[sa]), (ita / n_a) & 1);
           tc_fence_after();
-          const uint32_t a_st = a_base + sa * p.a_stage_bytes;
-          for (int t = 0; t < taps; ++t, ++itb) {
-            const uint32_t sb = itb % p.n_b;
-            mbar_wait(smem_u32(&ctl->full_b[sb]), (itb / p.n_b) & 1);
-            tc_fence_after();
-            const int ty = t / p.taps_w, tx = t - ty * p.taps_w;
-            const uint32_t a_tap = a_st + (ty * p.dil * p.TWp + tx * p.dil) * 16;
-            const uint32_t b_st = b_base + sb * p.b_stage_bytes;
-            for (int ks = 0; ks < ksteps; ++ks) {
-              const uint64_t ad = umma_desc(a_tap + ks * 2 * p.plane_bytes, a_lbo, a_sbo);
-              const uint64_t bd = umma_desc(b_st + ks * 2 * b_lbo, b_lbo, b_sbo);
-              umma_tf32(d_tmem, ad, bd, idesc, first ? 0u : 1u);
-              first = 0;
+          const uint64_t a0 = a_tmpl + (a_base16 + sa * a_stage16);
+          if (resident) {
+            const uint64_t b0 = b_tmpl + (b_base16 + ch * chunk_w16);
+            uint32_t accum = ch != 0 ? 1u : 0u;
+            for (int i = 0; i < nmma; ++i) {
+              const uint2 o = mma_tab[i];
+              if (elect_one()) {
+                umma_tf32(d_tmem, a0 + o.x, b0 + o.y, idesc, accum);
+                if (sub > 1)
+                  umma_tf32(d_tmem + cout, a0 + o.x + (kTileW * 16 >> 4), b0 + o.y, idesc, accum);
+              }
+              accum = 1u;
             }
-            umma_commit(smem_u32(&ctl->empty_b[sb]));
+          } else {
+            uint32_t accum = ch != 0 ? 1u : 0u;
+            for (int t = 0; t < taps; ++t, ++itb) {
+              const uint32_t sb = itb % n_b;
+              mbar_wait(smem_u32(&ctl->full_b[sb]), (itb / n_b) & 1);
+              tc_fence_after();
+              const uint64_t b0 = b_tmpl + (b_base16 + sb * b_stage16);
+              for (int ks = 0; ks < ksteps; ++ks) {
+                const uint2 o = mma_tab[t * ksteps + ks];
+                if (elect_one()) {
+                  umma_tf32(d_tmem, a0 + o.x, b0 + o.y, idesc, accum);
+                  if (sub > 1)
+                    umma_tf32(d_tmem + cout, a0 + o.x + (kTileW * 16 >> 4), b0 + o.y, idesc, accum);
+                }
+                accum = 1u;
+              }
+              if (elect_one()) umma_commit(smem_u32(&ctl->empty_b[sb]));
+            }
           }
-          umma_commit(smem_u32(&ctl->empty_a[sa]));
+          if (elect_one()) umma_commit(smem_u32(&ctl->empty_a[sa]));
         }
-        umma_commit(smem_u32(&ctl->tmem_full[acc]));
+        if (elect_one()) umma_commit(smem_u32(&ctl->tmem_full[acc]));
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
     }
     __syncwarp();
+   }
   } else {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsEpi));
     // ===================== epilogue =====================
     uint32_t acc = 0, acc_phase = 0;
     float* my_stats = s_stats + warp * 2 * p.Cout;
@@ -226,11 +359,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
       const int tw_i = tile % p.tiles_w;
       const int th_i = (tile / p.tiles_w) % p.tiles_h;
       const int n = tile / (p.tiles_w * p.tiles_h);
-      const int gh = th_i * kTileH + r_h, gw = tw_i * kTileW + r_w;
-      const bool valid = gh < p.H && gw < p.W;
       mbar_wait(smem_u32(&ctl->tmem_full[acc]), acc_phase);
       tc_fence_after();
-      const uint32_t t_addr = tmem_base + acc * p.Cout + ((uint32_t)(warp * 32) << 16);
+     for (int sb_ = 0; sb_ < p.sub; ++sb_) {
+      const int gh = th_i * kTileH + r_h, gw = (tw_i * p.sub + sb_) * kTileW + r_w;
+      const bool valid = gh < p.H && gw < p.W;
+      const uint32_t t_addr =
+          tmem_base + (acc * p.sub + sb_) * p.Cout + ((uint32_t)(warp * 32) << 16);
       const size_t pix = ((size_t)n * p.H + gh) * p.W + gw;
       for (int c0 = 0; c0 < p.Cout; c0 += 16) {
         float v[16];
@@ -267,6 +402,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
           }
         }
       }
+     }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&ctl->tmem_empty[acc]));
@@ -365,40 +501,58 @@ static int conv_tc_plan(const ab_conv_t* d, ConvTcParams* p, int* smem_bytes) {
   p->alpha = d->lrelu;
   p->act = d->act;
   p->out_nchw = d->out_nchw;
-  p->tiles_h = (d->H + kTileH - 1) / kTileH;
-  p->tiles_w = (d->W + kTileW - 1) / kTileW;
-  p->num_tiles = d->N * p->tiles_h * p->tiles_w;
-  p->THp = kTileH + d->dil * (d->ks_h - 1);
-  p->TWp = kTileW + d->dil * (d->ks_w - 1);
-  p->HP = p->THp * p->TWp;
-  int KC = pick_kc(S.Ctot);
-  const int budget = 200 * 1024;
-  const int stats_bytes = ((kNumEpiWarps * 2 * d->Cout * 4 + 127) & ~127) + 256 + 128;
-  for (;; KC >>= 1) {
-    AB_CHECK(KC >= 8, "conv_tc: halo tile too large for shared memory (dil=%d)", d->dil);
-    if (S.Ctot % KC != 0) continue;
-    const int P = KC / 4;
-    int plane = p->HP * 16;
-    const int want = (128 / P) % 128;  // plane stride mod 128 that spreads the P planes over banks
-    plane += ((want - plane % 128) + 128) % 128;
-    p->KC = KC;
-    p->plane_bytes = plane;
-    p->a_stage_bytes = P * plane;
-    p->b_stage_bytes = KC * d->Cout * 4;
-    p->n_b = 4;
-    int avail = budget - stats_bytes - p->n_b * p->b_stage_bytes;
-    int na = avail / p->a_stage_bytes;
-    if (na >= 2) {
+  const int taps = d->ks_h * d->ks_w;
+  p->w_bytes = taps * S.Ctot * d->Cout * 4;
+  const int budget = 212 * 1024;
+  const int stats_bytes = ((kNumEpiWarps * 2 * d->Cout * 4 + 127) & ~127) + 640 + 128;
+  // Try, in order of preference: (resident weights, 1 sub-tile), (streamed weights, 2 sub-tiles
+  // so that every weight stage feeds M = 256), (streamed, 1 sub-tile).
+  bool ok = false;
+  for (int attempt = 0; attempt < 3 && !ok; ++attempt) {
+    const int resident = attempt == 0;
+    const int sub = attempt == 1 ? 2 : 1;
+    if (sub == 2 && (4 * d->Cout > 512 || d->W <= kTileW)) continue;
+    p->tiles_h = (d->H + kTileH - 1) / kTileH;
+    p->tiles_w = (d->W + kTileW * sub - 1) / (kTileW * sub);
+    p->THp = kTileH + d->dil * (d->ks_h - 1);
+    p->TWp = kTileW * sub + d->dil * (d->ks_w - 1);
+    p->HP = p->THp * p->TWp;
+    for (int KC = pick_kc(S.Ctot); KC >= 8 && !ok; KC >>= 1) {
+      if (S.Ctot % KC != 0) continue;
+      const int P = KC / 4;
+      if (p->HP * P > kMaxU * kGroupThreads) continue;
+      int plane = p->HP * 16;
+      const int want = (128 / P) % 128;  // plane stride mod 128 spreading the P planes over banks
+      plane += ((want - plane % 128) + 128) % 128;
+      const int a_stage = P * plane;
+      int avail = budget - stats_bytes;
+      int n_b = 0, b_stage = KC * d->Cout * 4;
+      if (resident) {
+        avail -= (p->w_bytes + 127) & ~127;
+      } else {
+        // weight stages: cover ~1.5 us of L2 latency, leave room for >= 2 activation stages
+        n_b = (avail - 2 * a_stage) / b_stage;
+        if (n_b > kMaxBStages) n_b = kMaxBStages;
+        if (n_b < 3) continue;
+        avail -= n_b * b_stage;
+      }
+      int na = avail / a_stage;
+      if (na < 2) continue;
+      p->KC = KC; p->plane_bytes = plane; p->a_stage_bytes = a_stage; p->b_stage_bytes = b_stage;
       p->n_a = na > kMaxAStages ? kMaxAStages : na;
-      break;
+      p->n_b = n_b; p->sub = sub; p->w_resident = resident;
+      ok = true;
     }
   }
+  AB_CHECK(ok, "conv_tc: no shared-memory plan (Cin=%d Cout=%d dil=%d)", S.Ctot, d->Cout, d->dil);
+  p->num_tiles = d->N * p->tiles_h * p->tiles_w;
   p->n_chunks = S.Ctot / p->KC;
   AB_CHECK(p->plane_bytes / 16 < (1 << 14) && p->TWp < (1 << 14), "conv_tc: descriptor overflow");
   int cols = 32;
-  while (cols < 2 * d->Cout) cols <<= 1;
+  while (cols < 2 * p->sub * d->Cout) cols <<= 1;
   p->tmem_cols = cols;
-  *smem_bytes = stats_bytes + p->n_a * p->a_stage_bytes + p->n_b * p->b_stage_bytes;
+  *smem_bytes = stats_bytes + p->n_a * p->a_stage_bytes +
+                (p->w_resident ? ((p->w_bytes + 127) & ~127) : p->n_b * p->b_stage_bytes);
   return 0;
 }
 
@@ -422,8 +576,8 @@ int ab_conv_tc_fwd(const ab_conv_t* d, const float* wblob, const float* bias, fl
   static int configured_smem = 0;
   if (smem_bytes > configured_smem) {
     AB_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 220 * 1024));
-    configured_smem = 220 * 1024;
+                                 226 * 1024));
+    configured_smem = 226 * 1024;
   }
   const int sms = ab_num_sms();
   const int grid = p.num_tiles < sms ? p.num_tiles : sms;

@@ -9,6 +9,8 @@
 // F.max_pool2d atomai/nets/fcnn.py:123-127; F.interpolate atomai/nets/blocks.py:130-131;
 // DilatedBlock.forward blocks.py:321-329; nn.CrossEntropyLoss / BCEWithLogits / MSE
 // atomai/losses_metrics/losses.py:154-164; torch.optim.Adam atomai/trainers/trainer.py:539.
+#include <initializer_list>
+
 #include "common.cuh"
 
 namespace {
@@ -448,6 +450,259 @@ __global__ void adam_multi_kernel(const int64_t* __restrict__ table, float lr, f
   }
 }
 
+
+// ================================================================= float4 fast paths
+// Used when C % 4 == 0, every pixel stride % 4 == 0 and all pointers are 16 B aligned (always the
+// case for the UNet path).  Index math is 32-bit with shift/mask when C/4 is a power of two.
+struct VIdx {
+  int C4;
+  int shift;  // log2(C4) or -1
+  __device__ __forceinline__ void split(uint32_t i, uint32_t& pix, int& c4) const {
+    if (shift >= 0) { pix = i >> shift; c4 = (int)(i & (uint32_t)(C4 - 1)); }
+    else { pix = i / (uint32_t)C4; c4 = (int)(i - pix * (uint32_t)C4); }
+  }
+};
+inline VIdx make_vidx(int C) {
+  VIdx v; v.C4 = C / 4; v.shift = -1;
+  for (int s = 0; s < 12; ++s) if ((1 << s) == v.C4) v.shift = s;
+  return v;
+}
+inline bool vec_ok(int C, std::initializer_list<const void*> ptrs, std::initializer_list<int> lds,
+                   int64_t total4) {
+  if (C % 4 != 0 || total4 >= (int64_t)1 << 31) return false;
+  for (auto p : ptrs) if (p && ((uintptr_t)p & 15)) return false;
+  for (auto l : lds) if (l % 4 != 0) return false;
+  return true;
+}
+__device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 f4fma(float4 a, float4 s, float4 t) {
+  return make_float4(fmaf(a.x, s.x, t.x), fmaf(a.y, s.y, t.y), fmaf(a.z, s.z, t.z), fmaf(a.w, s.w, t.w));
+}
+__device__ __forceinline__ float4 f4max(float4 a, float4 b) {
+  return make_float4(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z), fmaxf(a.w, b.w));
+}
+__device__ __forceinline__ float4 f4add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float4 f4scale(float4 a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
+
+__global__ void __launch_bounds__(kT) affine_vec_kernel(const float* __restrict__ a, int ld_a, const float* scale,
+                                  const float* shift, float* __restrict__ y, int ld_y, uint32_t total, VIdx ix) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    uint32_t pix; int c4; ix.split(i, pix, c4);
+    float4 v = ld4(a + (size_t)pix * ld_a + c4 * 4);
+    if (scale) v = f4fma(v, ld4(scale + c4 * 4), ld4(shift + c4 * 4));
+    *reinterpret_cast<float4*>(y + (size_t)pix * ld_y + c4 * 4) = v;
+  }
+}
+
+__global__ void __launch_bounds__(kT) add_slice_vec_kernel(const float* __restrict__ src, int ld_s, float* __restrict__ dst,
+                                     int ld_d, int accumulate, uint32_t total, VIdx ix) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    uint32_t pix; int c4; ix.split(i, pix, c4);
+    float4 v = ld4(src + (size_t)pix * ld_s + c4 * 4);
+    float4* o = reinterpret_cast<float4*>(dst + (size_t)pix * ld_d + c4 * 4);
+    if (accumulate) v = f4add(v, *o);
+    *o = v;
+  }
+}
+
+// per-channel reductions: thread = (c4 lane cx, pixel row py), CW4 = pow2 >= C4, R = 256 / CW4
+__device__ __forceinline__ void block_chan_reduce_vec(float4 v1, float4 v2, int cx, int py, int CW, int R, int C4,
+                                                      double* out1, double* out2) {
+  __shared__ float4 s1[kT], s2[kT];
+  s1[py * CW + cx] = v1;
+  s2[py * CW + cx] = v2;
+  __syncthreads();
+  if (py == 0 && cx < C4) {
+    float4 a = make_float4(0, 0, 0, 0), b = a;
+    for (int r = 0; r < R; ++r) { a = f4add(a, s1[r * CW + cx]); b = f4add(b, s2[r * CW + cx]); }
+    if (out1) { atomicAdd(out1 + cx * 4, (double)a.x); atomicAdd(out1 + cx * 4 + 1, (double)a.y);
+                atomicAdd(out1 + cx * 4 + 2, (double)a.z); atomicAdd(out1 + cx * 4 + 3, (double)a.w); }
+    if (out2) { atomicAdd(out2 + cx * 4, (double)b.x); atomicAdd(out2 + cx * 4 + 1, (double)b.y);
+                atomicAdd(out2 + cx * 4 + 2, (double)b.z); atomicAdd(out2 + cx * 4 + 3, (double)b.w); }
+  }
+}
+
+__global__ void __launch_bounds__(kT) bn_bwd_reduce_vec_kernel(const float* __restrict__ dy, int ld_dy, const float* __restrict__ a,
+                                         int ld_a, const float* mean, const float* invstd, int64_t npix, int C4,
+                                         int CW, int R, double* sums) {
+  const int cx = threadIdx.x % CW, py = threadIdx.x / CW;
+  float4 s1 = make_float4(0, 0, 0, 0), s2 = s1;
+  if (cx < C4) {
+    const float4 m = ld4(mean + cx * 4), is = ld4(invstd + cx * 4);
+    for (int64_t p = (int64_t)blockIdx.x * R + py; p < npix; p += (int64_t)gridDim.x * R) {
+      const float4 g = ld4(dy + p * ld_dy + cx * 4), av = ld4(a + p * ld_a + cx * 4);
+      s1 = f4add(s1, g);
+      s2.x = fmaf(g.x, (av.x - m.x) * is.x, s2.x); s2.y = fmaf(g.y, (av.y - m.y) * is.y, s2.y);
+      s2.z = fmaf(g.z, (av.z - m.z) * is.z, s2.z); s2.w = fmaf(g.w, (av.w - m.w) * is.w, s2.w);
+    }
+  }
+  block_chan_reduce_vec(s1, s2, cx, py, CW, R, C4, sums, sums + C4 * 4);
+}
+
+__device__ __forceinline__ float bwd1(float g, float av, bool bn, float m, float is, float sc, float k1, float k2,
+                                      float ex, bool has_ex, int act, float alpha) {
+  if (bn) g = sc * (g - k1 - (av - m) * is * k2);
+  if (has_ex) g += ex;
+  return g * act_grad_from_out(av, act, alpha) + (has_ex ? ex : 0.f);
+}
+
+__global__ void __launch_bounds__(kT) bn_lrelu_bwd_vec_kernel(const float* __restrict__ dy, int ld_dy, const float* __restrict__ a, int ld_a,
+                                        const float* mean, const float* invstd, const float* scale, const double* sums,
+                                        double count, const float* __restrict__ extra, int ld_extra, int act, float alpha,
+                                        float* __restrict__ dpre, int ld_dpre, double* dbias, int64_t npix, int C4,
+                                        int CW, int R) {
+  const int cx = threadIdx.x % CW, py = threadIdx.x / CW;
+  float4 sb = make_float4(0, 0, 0, 0);
+  if (cx < C4) {
+    const bool bn = scale != nullptr, has_ex = extra != nullptr;
+    float4 m = sb, is = sb, sc = sb, k1 = sb, k2 = sb;
+    if (bn) {
+      const int C = C4 * 4, c = cx * 4;
+      m = ld4(mean + c); is = ld4(invstd + c); sc = ld4(scale + c);
+      k1 = make_float4((float)(sums[c] / count), (float)(sums[c + 1] / count), (float)(sums[c + 2] / count), (float)(sums[c + 3] / count));
+      k2 = make_float4((float)(sums[C + c] / count), (float)(sums[C + c + 1] / count), (float)(sums[C + c + 2] / count), (float)(sums[C + c + 3] / count));
+    }
+    for (int64_t p = (int64_t)blockIdx.x * R + py; p < npix; p += (int64_t)gridDim.x * R) {
+      const float4 av = ld4(a + p * ld_a + cx * 4);
+      const float4 g = dy ? ld4(dy + p * ld_dy + cx * 4) : make_float4(0, 0, 0, 0);
+      const float4 ex = has_ex ? ld4(extra + p * ld_extra + cx * 4) : make_float4(0, 0, 0, 0);
+      float4 d;
+      d.x = bwd1(g.x, av.x, bn, m.x, is.x, sc.x, k1.x, k2.x, ex.x, has_ex, act, alpha);
+      d.y = bwd1(g.y, av.y, bn, m.y, is.y, sc.y, k1.y, k2.y, ex.y, has_ex, act, alpha);
+      d.z = bwd1(g.z, av.z, bn, m.z, is.z, sc.z, k1.z, k2.z, ex.z, has_ex, act, alpha);
+      d.w = bwd1(g.w, av.w, bn, m.w, is.w, sc.w, k1.w, k2.w, ex.w, has_ex, act, alpha);
+      *reinterpret_cast<float4*>(dpre + p * ld_dpre + cx * 4) = d;
+      sb = f4add(sb, d);
+    }
+  }
+  if (dbias) block_chan_reduce_vec(sb, make_float4(0, 0, 0, 0), cx, py, CW, R, C4, dbias, nullptr);
+}
+
+__global__ void __launch_bounds__(kT) pool_fwd_vec_kernel(const float* __restrict__ a, int ld_a, const float* scale, const float* shift,
+                                    float* __restrict__ y, int ld_y, int Ho, int Wo, uint32_t total, VIdx ix) {
+  const int W2 = 2 * Wo;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    uint32_t pix; int c4; ix.split(i, pix, c4);
+    const uint32_t wo = pix % Wo, r = pix / Wo, ho = r % Ho, n = r / Ho;
+    float4 sc = make_float4(1, 1, 1, 1), sh = make_float4(0, 0, 0, 0);
+    if (scale) { sc = ld4(scale + c4 * 4); sh = ld4(shift + c4 * 4); }
+    const float* b = a + (((size_t)n * 2 * Ho + 2 * ho) * W2 + 2 * wo) * ld_a + c4 * 4;
+    const float4 v = f4max(f4max(f4fma(ld4(b), sc, sh), f4fma(ld4(b + ld_a), sc, sh)),
+                           f4max(f4fma(ld4(b + (size_t)W2 * ld_a), sc, sh), f4fma(ld4(b + (size_t)W2 * ld_a + ld_a), sc, sh)));
+    *reinterpret_cast<float4*>(y + (size_t)pix * ld_y + c4 * 4) = v;
+  }
+}
+
+__device__ __forceinline__ void pick4(float v0, float v1, float v2, float v3, float g, float& o0, float& o1, float& o2, float& o3) {
+  int best = 0; float bv = v0;
+  if (v1 > bv) { bv = v1; best = 1; }
+  if (v2 > bv) { bv = v2; best = 2; }
+  if (v3 > bv) { bv = v3; best = 3; }
+  o0 = best == 0 ? g : 0.f; o1 = best == 1 ? g : 0.f; o2 = best == 2 ? g : 0.f; o3 = best == 3 ? g : 0.f;
+}
+
+__global__ void __launch_bounds__(kT) pool_bwd_vec_kernel(const float* __restrict__ dp, int ld_dp, const float* __restrict__ a, int ld_a,
+                                    const float* scale, const float* shift, float* __restrict__ df, int ld_df,
+                                    int accumulate, int Ho, int Wo, uint32_t total, VIdx ix) {
+  const int W2 = 2 * Wo;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    uint32_t pix; int c4; ix.split(i, pix, c4);
+    const uint32_t wo = pix % Wo, r = pix / Wo, ho = r % Ho, n = r / Ho;
+    float4 sc = make_float4(1, 1, 1, 1), sh = make_float4(0, 0, 0, 0);
+    if (scale) { sc = ld4(scale + c4 * 4); sh = ld4(shift + c4 * 4); }
+    const size_t base = ((size_t)n * 2 * Ho + 2 * ho) * W2 + 2 * wo;
+    const size_t off[4] = {0, 1, (size_t)W2, (size_t)W2 + 1};
+    float4 v[4], o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = f4fma(ld4(a + (base + off[k]) * ld_a + c4 * 4), sc, sh);
+    const float4 g = ld4(dp + (size_t)pix * ld_dp + c4 * 4);
+    pick4(v[0].x, v[1].x, v[2].x, v[3].x, g.x, o[0].x, o[1].x, o[2].x, o[3].x);
+    pick4(v[0].y, v[1].y, v[2].y, v[3].y, g.y, o[0].y, o[1].y, o[2].y, o[3].y);
+    pick4(v[0].z, v[1].z, v[2].z, v[3].z, g.z, o[0].z, o[1].z, o[2].z, o[3].z);
+    pick4(v[0].w, v[1].w, v[2].w, v[3].w, g.w, o[0].w, o[1].w, o[2].w, o[3].w);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float4* q = reinterpret_cast<float4*>(df + (base + off[k]) * ld_df + c4 * 4);
+      *q = accumulate ? f4add(*q, o[k]) : o[k];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kT) upsample_fwd_vec_kernel(const float* __restrict__ x, int ld_x, float* __restrict__ y, int ld_y,
+                                        int h, int w, int bilinear, uint32_t total, VIdx ix) {
+  const int H = 2 * h, W = 2 * w;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    uint32_t pix; int c4; ix.split(i, pix, c4);
+    const uint32_t ow = pix % W, r = pix / W, oh = r % H, n = r / H;
+    const float* xb = x + (size_t)n * h * w * ld_x + c4 * 4;
+    float4 v;
+    if (bilinear) {
+      int h0, h1, w0, w1; float lh, lw;
+      up_src((int)oh, h, h0, h1, lh);
+      up_src((int)ow, w, w0, w1, lw);
+      const float4 x00 = ld4(xb + ((size_t)h0 * w + w0) * ld_x), x01 = ld4(xb + ((size_t)h0 * w + w1) * ld_x);
+      const float4 x10 = ld4(xb + ((size_t)h1 * w + w0) * ld_x), x11 = ld4(xb + ((size_t)h1 * w + w1) * ld_x);
+      const float a0 = (1.f - lh) * (1.f - lw), a1 = (1.f - lh) * lw, a2 = lh * (1.f - lw), a3 = lh * lw;
+      v.x = (1.f - lh) * ((1.f - lw) * x00.x + lw * x01.x) + lh * ((1.f - lw) * x10.x + lw * x11.x);
+      v.y = (1.f - lh) * ((1.f - lw) * x00.y + lw * x01.y) + lh * ((1.f - lw) * x10.y + lw * x11.y);
+      v.z = (1.f - lh) * ((1.f - lw) * x00.z + lw * x01.z) + lh * ((1.f - lw) * x10.z + lw * x11.z);
+      v.w = (1.f - lh) * ((1.f - lw) * x00.w + lw * x01.w) + lh * ((1.f - lw) * x10.w + lw * x11.w);
+      (void)a0; (void)a1; (void)a2; (void)a3;
+    } else {
+      v = ld4(xb + ((size_t)(oh >> 1) * w + (ow >> 1)) * ld_x);
+    }
+    *reinterpret_cast<float4*>(y + (size_t)pix * ld_y + c4 * 4) = v;
+  }
+}
+
+__global__ void __launch_bounds__(kT) upsample_bwd_vec_kernel(const float* __restrict__ dy, int ld_dy, float* __restrict__ dx, int ld_dx,
+                                        int h, int w, int bilinear, uint32_t total, VIdx ix) {
+  const int H = 2 * h, W = 2 * w;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    uint32_t pix; int c4; ix.split(i, pix, c4);
+    const uint32_t iw = pix % w, r = pix / w, ih = r % h, n = r / h;
+    const float* db = dy + (size_t)n * H * W * ld_dy + c4 * 4;
+    float4 acc = make_float4(0, 0, 0, 0);
+    if (bilinear) {
+      int oh[4], ow[4]; float wh[4], ww[4];
+      const int nh = up_adj((int)ih, h, oh, wh), nw = up_adj((int)iw, w, ow, ww);
+      for (int a = 0; a < nh; ++a) {
+        float4 row = make_float4(0, 0, 0, 0);
+        for (int b = 0; b < nw; ++b) {
+          const float4 g = ld4(db + ((size_t)oh[a] * W + ow[b]) * ld_dy);
+          row.x = fmaf(ww[b], g.x, row.x); row.y = fmaf(ww[b], g.y, row.y);
+          row.z = fmaf(ww[b], g.z, row.z); row.w = fmaf(ww[b], g.w, row.w);
+        }
+        acc.x = fmaf(wh[a], row.x, acc.x); acc.y = fmaf(wh[a], row.y, acc.y);
+        acc.z = fmaf(wh[a], row.z, acc.z); acc.w = fmaf(wh[a], row.w, acc.w);
+      }
+    } else {
+      const size_t b0 = ((size_t)(2 * ih) * W + 2 * iw) * ld_dy;
+      acc = f4add(f4add(ld4(db + b0), ld4(db + b0 + ld_dy)),
+                  f4add(ld4(db + b0 + (size_t)W * ld_dy), ld4(db + b0 + (size_t)W * ld_dy + ld_dy)));
+    }
+    *reinterpret_cast<float4*>(dx + (size_t)pix * ld_dx + c4 * 4) = acc;
+  }
+}
+
+// batched 2-D transpose: y[n][c][r] = x[n][r][c]  (NHWC <-> NCHW around flatten/Linear)
+__global__ void transpose_kernel(const float* __restrict__ x, float* __restrict__ y, int R, int Cc) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const float* xb = x + (size_t)n * R * Cc;
+  float* yb = y + (size_t)n * R * Cc;
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < R && c < Cc) ? xb[(size_t)r * Cc + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (r < R && c < Cc) yb[(size_t)c * R + r] = tile[threadIdx.x][i];
+  }
+}
+
 }  // namespace
 
 #define STREAM ((cudaStream_t)stream)
@@ -471,6 +726,12 @@ int atomai_b200_bn_finalize(const double* stats, int C, double count, const floa
 int atomai_b200_affine(const float* a, int ld_a, const float* scale, const float* shift, float* y,
                        int ld_y, int64_t npix, int C, int out_nchw_hw, void* stream) {
   if (npix * C == 0) return 0;
+  if (!out_nchw_hw && vec_ok(C, {a, y, scale, shift}, {ld_a, ld_y}, npix * C / 4)) {
+    affine_vec_kernel<<<grid_for(npix * C / 4), kT, 0, STREAM>>>(a, ld_a, scale, shift, y, ld_y,
+                                                               (uint32_t)(npix * C / 4), make_vidx(C));
+    AB_LAUNCH_CHECK();
+    return 0;
+  }
   affine_kernel<<<grid_for(npix * C), kT, 0, STREAM>>>(a, ld_a, scale, shift, y, ld_y, npix, C,
                                                        out_nchw_hw);
   AB_LAUNCH_CHECK();
@@ -482,6 +743,13 @@ int atomai_b200_bn_bwd_reduce(const float* dy, int ld_dy, const float* a, int ld
                               double* sums, void* stream) {
   AB_CHECK(C <= kT, "bn_bwd_reduce: C=%d > %d unsupported", C, kT);
   if (npix == 0) return 0;
+  if (vec_ok(C, {dy, a, mean, invstd}, {ld_dy, ld_a}, npix)) {
+    const ChanLayout l4 = chan_layout(C / 4);
+    bn_bwd_reduce_vec_kernel<<<grid_for(npix, l4.R * 8), kT, 0, STREAM>>>(
+        dy, ld_dy, a, ld_a, mean, invstd, npix, C / 4, l4.CW, l4.R, sums);
+    AB_LAUNCH_CHECK();
+    return 0;
+  }
   const ChanLayout l = chan_layout(C);
   bn_bwd_reduce_kernel<<<grid_for(npix, l.R * 8), kT, 0, STREAM>>>(dy, ld_dy, a, ld_a, mean,
                                                                   invstd, npix, C, l.CW, l.R,
@@ -497,6 +765,14 @@ int atomai_b200_bn_lrelu_bwd(const float* dy, int ld_dy, const float* a, int ld_
                              int64_t npix, int C, void* stream) {
   AB_CHECK(C <= kT, "bn_lrelu_bwd: C=%d > %d unsupported", C, kT);
   if (npix == 0) return 0;
+  if (vec_ok(C, {dy, a, mean, invstd, scale, extra, dpre}, {dy ? ld_dy : 0, ld_a, extra ? ld_extra : 0, ld_dpre}, npix)) {
+    const ChanLayout l4 = chan_layout(C / 4);
+    bn_lrelu_bwd_vec_kernel<<<grid_for(npix, l4.R * 8), kT, 0, STREAM>>>(
+        dy, ld_dy, a, ld_a, mean, invstd, scale, sums, count, extra, ld_extra, act, lrelu, dpre,
+        ld_dpre, dbias, npix, C / 4, l4.CW, l4.R);
+    AB_LAUNCH_CHECK();
+    return 0;
+  }
   const ChanLayout l = chan_layout(C);
   bn_lrelu_bwd_kernel<<<grid_for(npix, l.R * 8), kT, 0, STREAM>>>(
       dy, ld_dy, a, ld_a, mean, invstd, scale, sums, count, extra, ld_extra, act, lrelu, dpre,
@@ -509,6 +785,12 @@ int atomai_b200_pool2x2_fwd(const float* a, int ld_a, const float* scale, const 
                             float* y, int ld_y, int N, int Ho, int Wo, int C, void* stream) {
   const int64_t total = (int64_t)N * Ho * Wo * C;
   if (total == 0) return 0;
+  if (vec_ok(C, {a, y, scale, shift}, {ld_a, ld_y}, total / 4)) {
+    pool_fwd_vec_kernel<<<grid_for(total / 4), kT, 0, STREAM>>>(a, ld_a, scale, shift, y, ld_y, Ho, Wo,
+                                                              (uint32_t)(total / 4), make_vidx(C));
+    AB_LAUNCH_CHECK();
+    return 0;
+  }
   pool_fwd_kernel<<<grid_for(total), kT, 0, STREAM>>>(a, ld_a, scale, shift, y, ld_y, N, Ho, Wo,
                                                       C);
   AB_LAUNCH_CHECK();
@@ -520,6 +802,13 @@ int atomai_b200_pool2x2_bwd(const float* dp, int ld_dp, const float* a, int ld_a
                             int accumulate, int N, int Ho, int Wo, int C, void* stream) {
   const int64_t total = (int64_t)N * Ho * Wo * C;
   if (total == 0) return 0;
+  if (vec_ok(C, {dp, a, dfull, scale, shift}, {ld_dp, ld_a, ld_df}, total / 4)) {
+    pool_bwd_vec_kernel<<<grid_for(total / 4), kT, 0, STREAM>>>(dp, ld_dp, a, ld_a, scale, shift, dfull,
+                                                              ld_df, accumulate, Ho, Wo,
+                                                              (uint32_t)(total / 4), make_vidx(C));
+    AB_LAUNCH_CHECK();
+    return 0;
+  }
   pool_bwd_kernel<<<grid_for(total), kT, 0, STREAM>>>(dp, ld_dp, a, ld_a, scale, shift, dfull,
                                                       ld_df, accumulate, N, Ho, Wo, C);
   AB_LAUNCH_CHECK();
@@ -530,6 +819,12 @@ int atomai_b200_upsample2x_fwd(const float* x, int ld_x, float* y, int ld_y, int
                                int C, int bilinear, void* stream) {
   const int64_t total = (int64_t)N * 4 * h * w * C;
   if (total == 0) return 0;
+  if (vec_ok(C, {x, y}, {ld_x, ld_y}, total / 4)) {
+    upsample_fwd_vec_kernel<<<grid_for(total / 4), kT, 0, STREAM>>>(x, ld_x, y, ld_y, h, w, bilinear,
+                                                                  (uint32_t)(total / 4), make_vidx(C));
+    AB_LAUNCH_CHECK();
+    return 0;
+  }
   upsample_fwd_kernel<<<grid_for(total), kT, 0, STREAM>>>(x, ld_x, y, ld_y, N, h, w, C, bilinear);
   AB_LAUNCH_CHECK();
   return 0;
@@ -539,6 +834,12 @@ int atomai_b200_upsample2x_bwd(const float* dy, int ld_dy, float* dx, int ld_dx,
                                int w, int C, int bilinear, void* stream) {
   const int64_t total = (int64_t)N * h * w * C;
   if (total == 0) return 0;
+  if (vec_ok(C, {dy, dx}, {ld_dy, ld_dx}, total / 4)) {
+    upsample_bwd_vec_kernel<<<grid_for(total / 4), kT, 0, STREAM>>>(dy, ld_dy, dx, ld_dx, h, w, bilinear,
+                                                                  (uint32_t)(total / 4), make_vidx(C));
+    AB_LAUNCH_CHECK();
+    return 0;
+  }
   upsample_bwd_kernel<<<grid_for(total), kT, 0, STREAM>>>(dy, ld_dy, dx, ld_dx, N, h, w, C,
                                                           bilinear);
   AB_LAUNCH_CHECK();
@@ -548,6 +849,12 @@ int atomai_b200_upsample2x_bwd(const float* dy, int ld_dy, float* dx, int ld_dx,
 int atomai_b200_add_slice(const float* src, int ld_s, float* dst, int ld_d, int accumulate,
                           int64_t npix, int C, void* stream) {
   if (npix * C == 0) return 0;
+  if (vec_ok(C, {src, dst}, {ld_s, ld_d}, npix * C / 4)) {
+    add_slice_vec_kernel<<<grid_for(npix * C / 4), kT, 0, STREAM>>>(src, ld_s, dst, ld_d, accumulate,
+                                                                  (uint32_t)(npix * C / 4), make_vidx(C));
+    AB_LAUNCH_CHECK();
+    return 0;
+  }
   add_slice_kernel<<<grid_for(npix * C), kT, 0, STREAM>>>(src, ld_s, dst, ld_d, accumulate, npix,
                                                           C);
   AB_LAUNCH_CHECK();
@@ -597,6 +904,16 @@ int atomai_b200_sqerr_reduce(const float* x, const float* xhat, int64_t n, doubl
                              float* dxhat, float gscale, const float* gscale_dev, void* stream) {
   if (n == 0) return 0;
   sqerr_kernel<<<grid_for(n), kT, 0, STREAM>>>(x, xhat, n, out, dxhat, gscale, gscale_dev);
+  AB_LAUNCH_CHECK();
+  return 0;
+}
+
+int atomai_b200_transpose(const float* x, float* y, int N, int R, int Cc, void* stream) {
+  AB_CHECK(x && y && N >= 0 && R > 0 && Cc > 0, "transpose: bad arguments");
+  if (N == 0) return 0;
+  AB_CHECK(N <= 65535 && (R + 31) / 32 <= 65535, "transpose: grid too large");
+  dim3 grid((Cc + 31) / 32, (R + 31) / 32, N), block(32, 8);
+  transpose_kernel<<<grid, block, 0, STREAM>>>(x, y, R, Cc);
   AB_LAUNCH_CHECK();
   return 0;
 }

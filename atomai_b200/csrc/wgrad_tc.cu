@@ -13,7 +13,8 @@
 //
 // A CTA owns one block of 32 input channels and a contiguous range of pixel tiles; its
 // taps x 32 accumulators live in TMEM for the whole kernel and are flushed once, with atomics,
-// into dW (OIHW).  Warp roles: 0-3 epilogue, 4 MMA issue, 5 TMEM alloc, 6-13 loaders.
+// into dW (OIHW).  Warp roles: 0-3 epilogue, 4 MMA issue, 5 TMEM alloc, 8-15 loaders (two groups
+// of 4 warps on alternate tiles; setmaxnreg moves registers to them).
 //
 // Replaces autograd's cuDNN bwd-filter behind loss.backward(), atomai/trainers/trainer.py:206.
 #include "common.cuh"
@@ -21,9 +22,10 @@
 namespace {
 
 constexpr int kTileH = 16, kTileW = 8;
-constexpr int kNumEpiWarps = 4, kMmaWarp = 4, kAllocWarp = 5, kFirstLoadWarp = 6;
-constexpr int kNumLoadWarps = 8, kNumLoadThreads = 256;
-constexpr int kThreads = (kFirstLoadWarp + kNumLoadWarps) * 32;
+constexpr int kNumEpiWarps = 4, kMmaWarp = 4, kAllocWarp = 5, kFirstLoadWarp = 8;
+constexpr int kNumLoadWarps = 8, kGroupThreads = 128, kB = 8;
+constexpr int kThreads = (kFirstLoadWarp + kNumLoadWarps) * 32;   // 512: 4 warpgroups
+constexpr int kRegsEpi = 80, kRegsMma = 48, kRegsLoad = 192;      // setmaxnreg re-balancing
 constexpr int kStages = 2;
 constexpr int kNB = 32;                       // input channels per CTA (one 128 B swizzle row)
 constexpr int kDChunk = 128 * 128;            // bytes between 32-channel chunks of the dy tile
@@ -78,7 +80,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const WgradTcPara
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kStages; ++i) {
-      mbar_init(smem_u32(&ctl->full[i]), kNumLoadWarps);
+      mbar_init(smem_u32(&ctl->full[i]), kNumLoadWarps / 2);
       mbar_init(smem_u32(&ctl->empty[i]), 1);
     }
     mbar_init(smem_u32(&ctl->done), 1);
@@ -96,11 +98,17 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const WgradTcPara
 
   if (warp >= kFirstLoadWarp) {
     // ===================== loaders: dy tile + x halo tile =====================
-    const int lt = threadIdx.x - kFirstLoadWarp * 32;
+    // Two groups of 4 warps stage alternate pixel tiles, so two tiles are in flight per SM.  Loads
+    // are issued in branch-free batches of kB from clamped addresses and masked afterwards.
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsLoad));
+    const int grp = (warp - kFirstLoadWarp) >> 2;
+    const int gt = threadIdx.x - (kFirstLoadWarp + grp * 4) * 32;   // 0..127
     const int n_d = PD * 128;     // 16 B pieces of the dy tile
     const int n_x = PX * p.HP;    // 16 B pieces of the x halo block
+    const int H = p.H, W = p.W;
     uint32_t it = 0;
     for (int tile = t_begin; tile < t_end; ++tile, ++it) {
+      if ((int)(it & 1) != grp) continue;
       const int tw_i = tile % p.tiles_w;
       const int th_i = (tile / p.tiles_w) % p.tiles_h;
       const int n = tile / (p.tiles_w * p.tiles_h);
@@ -109,51 +117,94 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const WgradTcPara
       const uint32_t st = it % kStages;
       mbar_wait(smem_u32(&ctl->empty[st]), ((it / kStages) & 1) ^ 1);
       const uint32_t d0 = base + st * p.stage_bytes, x0 = d0 + kDBytes;
-      for (int e = lt; e < n_d; e += kNumLoadThreads) {
-        const int j = e % PD, q = e / PD;
-        const int gh = h0 + (q >> 3), gw = w0 + (q & 7);
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (gh < p.H && gw < p.W)
-          v = __ldg(reinterpret_cast<const float4*>(
-              p.dy + (((size_t)n * p.H + gh) * p.W + gw) * p.ld_dy + co0 + j * 4));
-        sts128(swz128_32(d0 + (j >> 3) * kDChunk + q * 128 + (j & 7) * 16),
-               make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w)));
+      const size_t img = (size_t)n * H;
+      // ---- dy tile: piece e -> (pixel q = e / PD, channel piece j = e % PD)
+      for (int e0 = gt; e0 < n_d; e0 += kB * kGroupThreads) {
+        float4 v[kB];
+        uint32_t ok = 0;
+#pragma unroll
+        for (int k = 0; k < kB; ++k) {
+          const int e = min(e0 + k * kGroupThreads, n_d - 1);
+          const int q = e / PD, j = e - q * PD;
+          const int gh = h0 + (q >> 3), gw = w0 + (q & 7);
+          const int ghc = min(gh, H - 1), gwc = min(gw, W - 1);
+          v[k] = __ldg(reinterpret_cast<const float4*>(
+              p.dy + ((img + ghc) * W + gwc) * p.ld_dy + co0 + j * 4));
+          ok |= (gh < H && gw < W ? 1u : 0u) << k;
+        }
+#pragma unroll
+        for (int k = 0; k < kB; ++k) {
+          const int e = e0 + k * kGroupThreads;
+          if (e < n_d) {
+            const int q = e / PD, j = e - q * PD;
+            const bool m = (ok >> k) & 1u;
+            sts128(swz128_32(d0 + (j >> 3) * kDChunk + q * 128 + (j & 7) * 16),
+                   make_float4(m ? to_tf32(v[k].x) : 0.f, m ? to_tf32(v[k].y) : 0.f,
+                               m ? to_tf32(v[k].z) : 0.f, m ? to_tf32(v[k].w) : 0.f));
+          }
+        }
       }
-      for (int e = lt; e < n_x; e += kNumLoadThreads) {
-        const int j = e % PX, q = e / PX;
-        const int hh = q / p.TWp, ww = q - hh * p.TWp;
-        const float4 v = load_src4(p.S, n, h_org + hh, w_org + ww, p.H, p.W, cc * kNB + j * 4);
-        sts128(swz128_32(x0 + q * 128 + j * 16),
-               make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w)));
+      // ---- x halo block through the normalise-on-load source loader
+      for (int e0 = gt; e0 < n_x; e0 += kB * kGroupThreads) {
+        float4 v[kB];
+#pragma unroll
+        for (int k = 0; k < kB; ++k) {
+          const int e = min(e0 + k * kGroupThreads, n_x - 1);
+          const int q = e / PX, j = e - q * PX;
+          const int hh = q / p.TWp, ww = q - hh * p.TWp;
+          v[k] = load_src4(p.S, n, h_org + hh, w_org + ww, H, W, cc * kNB + j * 4);
+        }
+#pragma unroll
+        for (int k = 0; k < kB; ++k) {
+          const int e = e0 + k * kGroupThreads;
+          if (e < n_x) {
+            const int q = e / PX, j = e - q * PX;
+            sts128(swz128_32(x0 + q * 128 + j * 16),
+                   make_float4(to_tf32(v[k].x), to_tf32(v[k].y), to_tf32(v[k].z), to_tf32(v[k].w)));
+          }
+        }
       }
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&ctl->full[st]));
     }
-  } else if (warp == kMmaWarp) {
-    if (lane == 0) {
+  } else if (warp >= kNumEpiWarps) {
+   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsMma));
+   if (warp == kMmaWarp) {
+    {   // warp-converged control flow; one elected lane issues the MMAs / commits
       const uint32_t idesc = umma_idesc_tf32(128, kNB, 1, 1);
+      const uint64_t a_tmpl = umma_desc_ex(0, kDChunk, 512, 1, 0);
+      const uint64_t b_tmpl = umma_desc_ex(0, 1024, 512, 1, 0);
+      const uint32_t b_row16 = (uint32_t)p.TWp * 8;          // one halo row = TWp * 128 B
       uint32_t it = 0;
       for (int tile = t_begin; tile < t_end; ++tile, ++it) {
         const uint32_t st = it % kStages;
         mbar_wait(smem_u32(&ctl->full[st]), (it / kStages) & 1);
         tc_fence_after();
         const uint32_t d0 = base + st * p.stage_bytes, x0 = d0 + kDBytes;
+        const uint64_t a0 = a_tmpl + (d0 >> 4), b0 = b_tmpl + (x0 >> 4);
         for (int t = 0; t < taps; ++t) {
           const int ty = t / p.taps_w, tx = t - ty * p.taps_w;
+          uint64_t ad = a0;
+          uint64_t bd = b0 + (uint32_t)((ty * p.dil * p.TWp + tx * p.dil) * 8);
+          const uint32_t dcol = tmem_base + t * kNB;
+          uint32_t accum = it > 0 ? 1u : 0u;
+#pragma unroll 4
           for (int h = 0; h < kTileH; ++h) {
-            const uint64_t ad = umma_desc_ex(d0 + h * 1024, kDChunk, 512, 1, 0);
-            const uint64_t bd = umma_desc_ex(
-                x0 + ((h + ty * p.dil) * p.TWp + tx * p.dil) * 128, 1024, 512, 1, 0);
-            umma_tf32(tmem_base + t * kNB, ad, bd, idesc, (it > 0 || h > 0) ? 1u : 0u);
+            if (elect_one()) umma_tf32(dcol, ad, bd, idesc, accum);
+            accum = 1u;
+            ad += 64;              // next 8 pixels of the dy tile (8 x 128 B)
+            bd += b_row16;         // next halo row
           }
         }
-        umma_commit(smem_u32(&ctl->empty[st]));
+        if (elect_one()) umma_commit(smem_u32(&ctl->empty[st]));
       }
-      umma_commit(smem_u32(&ctl->done));
+      if (elect_one()) umma_commit(smem_u32(&ctl->done));
     }
     __syncwarp();
-  } else if (warp < kNumEpiWarps) {
+   }
+  } else {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsEpi));
     // ===================== epilogue: TMEM -> atomics into dW (OIHW) =====================
     if (t_end > t_begin) {
       mbar_wait(smem_u32(&ctl->done), 0);

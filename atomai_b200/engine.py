@@ -90,6 +90,15 @@ class _ConvRec:
                  "invstd", "scale", "count", "needs_in_grad")
 
 
+class _PointwiseAdapter:
+    """Presents an nn.Linear as the 1x1 convolution it is when applied per pixel."""
+    __slots__ = ("weight", "bias", "dilation", "stride", "padding", "_w4")
+
+    def __init__(self, lin):
+        self.weight, self.bias = lin.weight, lin.bias
+        self.dilation, self.stride, self.padding = (1, 1), (1, 1), (0, 0)
+
+
 class Tape:
     def __init__(self, training: bool, record: bool, comm=None):
         self.training = training      # BatchNorm uses batch statistics
@@ -132,16 +141,18 @@ class Tape:
         if wt.dim() == 4:
             ks = (wt.shape[2], wt.shape[3])
             dil = conv_mod.dilation[0]
-        else:                          # Conv1d: signals are (N, 1, L, C)
+        elif wt.dim() == 3:            # Conv1d: signals are (N, 1, L, C)
             ks = (1, wt.shape[2])
             dil = conv_mod.dilation[0]
+        else:                          # nn.Linear applied per pixel == 1x1 convolution
+            ks, dil = (1, 1), 1
         _check_conv(conv_mod, ks, dil)
         ctot = sum(s.C for s in srcs)
         assert ctot == wt.shape[1], f"conv expects {wt.shape[1]} input channels, got {ctot}"
         math = self._math_for(srcs, cout)
         d = ops.conv_desc([s.source() for s in srcs], n, h, w, cout, ks, dil, slope, math,
                           out_nchw, act)
-        wp = ops.prep_weights(wt, ops.WMODE_FWD, math)
+        wp = ops.prep_weights(_w4(wt), ops.WMODE_FWD, math)
         dev = wt.device
         if out_nchw:
             out_t = torch.empty((n, cout, h, w), device=dev, dtype=torch.float32)
@@ -231,7 +242,7 @@ class Tape:
             dsrc = [Source(dpre)]
             dmath = MATH_TF32 if (_MATH["mode"] == MATH_TF32 and ops.tc_supported(dsrc, ctot)) \
                 else MATH_FP32
-            wpd = ops.prep_weights(wt, ops.WMODE_DGRAD, dmath)
+            wpd = ops.prep_weights(_w4(wt), ops.WMODE_DGRAD, dmath)
             dd = ops.conv_desc(dsrc, n, h, w, ctot, r.ks, r.dil, 1.0, dmath)
             dx = torch.empty((n, h, w, ctot), device=dev, dtype=torch.float32)
             ops.conv_fwd(dd, wpd, None, dx, None)
@@ -352,9 +363,172 @@ class Tape:
             if l.scale is not None:    # BN output also enters the sum
                 _acc_grad(l, g, False)
 
+
+    # ------------------------------------------------------------------ dense layers
+    def pointwise(self, x: Act, lin_mod, slope: float = 1.0, act: int = ACT_LRELU) -> Act:
+        """nn.Linear applied to every pixel's channel vector (rDecoderNet's fc_decoder / out,
+        atomai/nets/ed.py:620-624,639) = 1x1 convolution on the tensor cores."""
+        return self.conv(x, _PointwiseAdapter(lin_mod), None, slope, act)
+
+    def linear(self, x: Act, lin_mod, act: Optional[int] = None) -> Act:
+        """nn.Linear on a (B, K) activation stored as (B,1,1,K) — the skinny heads of the VAE /
+        ImSpec nets (atomai/nets/ed.py:64,273-274,503-505) and the DKL MLP (nets/gp.py:23-26).
+        act: None (identity), ACT_TANH, or 'relu'."""
+        if x.pending():
+            x = self.materialize(x)
+        b, k = x.t.shape[0], x.t.shape[3]
+        assert x.t.shape[1] == 1 and x.t.shape[2] == 1 and x.t.is_contiguous()
+        w, bias = lin_mod.weight.detach(), _d(lin_mod.bias)
+        o = w.shape[0]
+        y = torch.empty((b, 1, 1, o), device=w.device, dtype=torch.float32)
+        if act is None:
+            ops.linear_fwd(x.t.view(b, k), w, bias, y.view(b, o))
+        else:
+            a_id, slope = (ACT_TANH, 1.0) if act == ACT_TANH else (ACT_LRELU, 0.0)
+            ops.gemm(x.t, k, 1, w, 1, k, y, o, b, o, k, bias, a_id, slope)
+        out = Act(y, needs_grad=True)
+        if self.record:
+            self.ops.append(("lin", (x, out, lin_mod, act)))
+        return out
+
+    def _lin_bwd(self, rec) -> None:
+        x, out, lin_mod, act = rec
+        if out.grad is None:
+            return
+        dy = _dense(out.grad)
+        out.grad = None
+        b, k, o = x.t.shape[0], x.t.shape[3], out.t.shape[3]
+        if act is not None:
+            a_id, slope = (ACT_TANH, 1.0) if act == ACT_TANH else (ACT_LRELU, 0.0)
+            dpre = torch.empty_like(out.t)
+            ops.bn_act_bwd(dy, out.t, None, None, None, None, 1.0, None, a_id, slope, dpre, None)
+            dy = dpre
+        w = lin_mod.weight.detach()
+        dx = torch.empty_like(x.t) if x.needs_grad else None
+        dw = torch.empty_like(w)
+        db = torch.empty(o, device=w.device, dtype=torch.float32) if lin_mod.bias is not None else None
+        ops.linear_bwd(x.t.view(b, k), w, dy.view(b, o), None if dx is None else dx.view(b, k), dw, db)
+        self._add_pgrad(lin_mod.weight, dw)
+        if db is not None:
+            self._add_pgrad(lin_mod.bias, db)
+        if dx is not None:
+            _acc_grad(x, dx, True)
+
+    def flatten(self, x: Act) -> Act:
+        """(N,H,W,C) -> (N,1,1,C*H*W) in the reference's NCHW order (`x.reshape(-1, C*H*W)`)."""
+        x = self.materialize(x)
+        n, h, w, c = x.t.shape
+        y = torch.empty((n, 1, 1, c * h * w), device=x.t.device, dtype=torch.float32)
+        if c == 1 or h * w == 1:
+            y.copy_(x.t.reshape(n, 1, 1, -1))
+        else:
+            ops.transpose(x.t, y, n, h * w, c)
+        out = Act(y, needs_grad=x.needs_grad)
+        if self.record:
+            self.ops.append(("flat", (x, out, True)))
+        return out
+
+    def unflatten(self, x: Act, c: int, h: int, w: int) -> Act:
+        """(N,1,1,C*H*W) in NCHW order -> (N,H,W,C)."""
+        x = self.materialize(x)
+        n = x.t.shape[0]
+        y = torch.empty((n, h, w, c), device=x.t.device, dtype=torch.float32)
+        if c == 1 or h * w == 1:
+            y.copy_(x.t.reshape(n, h, w, c))
+        else:
+            ops.transpose(x.t.contiguous(), y, n, c, h * w)
+        out = Act(y, needs_grad=x.needs_grad)
+        if self.record:
+            self.ops.append(("flat", (x, out, False)))
+        return out
+
+    def _flat_bwd(self, rec) -> None:
+        x, out, fwd_is_flatten = rec
+        if out.grad is None or not x.needs_grad:
+            return
+        g = _dense(out.grad)
+        out.grad = None
+        gx = torch.empty_like(x.t)
+        if fwd_is_flatten:
+            n, h, w, c = x.t.shape
+            if c == 1 or h * w == 1:
+                gx.copy_(g.reshape(x.t.shape))
+            else:
+                ops.transpose(g, gx, n, c, h * w)
+        else:
+            n, h, w, c = out.t.shape
+            if c == 1 or h * w == 1:
+                gx.copy_(g.reshape(x.t.shape))
+            else:
+                ops.transpose(g, gx, n, h * w, c)
+        _acc_grad(x, gx, True)
+
+    def coord_latent(self, mod, hw, z: Act, phi: Optional[Act], dx: Optional[Act],
+                     tanh_act: bool) -> Act:
+        """coord_latent + transform_coordinates fused (atomai/nets/ed.py:672-687,
+        atomai/utils/coords.py:57-83): h0[b, p, :] = act(Wc (R(phi_b) g_p + dx_b) + bc + Wz z_b)."""
+        h, w = hw
+        b = z.t.shape[0]
+        zt = z.t.reshape(b, -1).contiguous()
+        wc, bc = mod.fc_coord.weight.detach(), _d(mod.fc_coord.bias)
+        wz = mod.fc_latent.weight.detach()
+        hid = wc.shape[0]
+        ph = None if phi is None else phi.t.reshape(b).contiguous()
+        dxt = None if dx is None else dx.t.reshape(b, 2).contiguous()
+        d = ops.coord_latent_desc(b, h, w, zt, ph, dxt, wc, bc, wz, tanh_act)
+        h0 = torch.empty((b, h, w, hid), device=wc.device, dtype=torch.float32)
+        ops.coord_latent_fwd(d, h0)
+        out = Act(h0)
+        if self.record:
+            self.ops.append(("cl", (mod, (h, w), z, phi, dx, tanh_act, zt, ph, dxt, out)))
+        return out
+
+    def _cl_bwd(self, rec) -> None:
+        mod, (h, w), z, phi, dx, tanh_act, zt, ph, dxt, out = rec
+        if out.grad is None:
+            return
+        g = _dense(out.grad)
+        out.grad = None
+        b, hid = zt.shape[0], out.t.shape[3]
+        dev = g.device
+        if tanh_act:
+            dpre = torch.empty_like(out.t)
+            ops.bn_act_bwd(g, out.t, None, None, None, None, 1.0, None, ACT_TANH, 1.0, dpre, None)
+            g = dpre
+        wc, bc = mod.fc_coord.weight.detach(), _d(mod.fc_coord.bias)
+        wz = mod.fc_latent.weight.detach()
+        dwc = torch.zeros_like(wc)
+        dbc = torch.zeros(hid, device=dev, dtype=torch.float32)
+        sb = torch.zeros((b, hid), device=dev, dtype=torch.float32)
+        dphi = torch.zeros(b, device=dev, dtype=torch.float32) if phi is not None else None
+        ddx = torch.zeros((b, 2), device=dev, dtype=torch.float32) if dx is not None else None
+        d = ops.coord_latent_desc(b, h, w, zt, ph, dxt, wc, bc, wz, tanh_act)
+        ops.coord_latent_bwd(d, g, dwc, dbc, sb, dphi, ddx)
+        self._add_pgrad(mod.fc_coord.weight, dwc)
+        if mod.fc_coord.bias is not None:
+            self._add_pgrad(mod.fc_coord.bias, dbc)
+        zd = zt.shape[1]
+        dwz = torch.empty_like(wz)                       # dWz[h][k] = sum_b sb[b][h] z[b][k]
+        ops.gemm(sb, 1, hid, zt, zd, 1, dwz, zd, hid, zd, b)
+        self._add_pgrad(mod.fc_latent.weight, dwz)
+        if z.needs_grad:
+            dz = torch.empty((b, 1, 1, zd), device=dev, dtype=torch.float32)
+            ops.gemm(sb, hid, 1, wz, zd, 1, dz, zd, b, zd, hid)   # dz = sb @ Wz
+            _acc_grad(z, dz, True)
+        if phi is not None and phi.needs_grad:
+            _acc_grad(phi, dphi.reshape(phi.t.shape), True)
+        if dx is not None and dx.needs_grad:
+            _acc_grad(dx, ddx.reshape(dx.t.shape), True)
+
     # ------------------------------------------------------------------ backward driver
+    def backward_no_seed(self) -> None:
+        self._replay()
+
     def backward(self, out: Act, grad_out_nhwc: torch.Tensor) -> None:
         out.grad, out.grad_owned = grad_out_nhwc, False
+        self._replay()
+
+    def _replay(self) -> None:
         for kind, rec in reversed(self.ops):
             if kind == "conv":
                 self._conv_bwd(rec)
@@ -364,6 +538,12 @@ class Tape:
                 self._mat_bwd(rec)
             elif kind == "dsum":
                 self._dsum_bwd(rec)
+            elif kind == "lin":
+                self._lin_bwd(rec)
+            elif kind == "flat":
+                self._flat_bwd(rec)
+            elif kind == "cl":
+                self._cl_bwd(rec)
             elif kind == "custom":
                 rec.backward(self)
             else:
@@ -373,6 +553,16 @@ class Tape:
 
 def _d(p):
     return None if p is None else p.detach()
+
+
+def _w4(w: torch.Tensor) -> torch.Tensor:
+    """Weight as OIHW: Conv2d as is, Conv1d (O,I,k) -> (O,I,1,k), Linear (O,I) -> (O,I,1,1)."""
+    w = w.detach()
+    if w.dim() == 3:
+        return w.unsqueeze(2)
+    if w.dim() == 2:
+        return w.reshape(w.shape[0], w.shape[1], 1, 1)
+    return w
 
 
 def _check_conv(m, ks, dil) -> None:
@@ -425,6 +615,52 @@ class _NetFn(torch.autograd.Function):
             gx = ctx.a_in.grad.permute(0, 3, 1, 2)
         tape.param_grads = {}
         return (None, None, None, gx) + grads
+
+
+class _MultiFn(torch.autograd.Function):
+    """General boundary: emit(tape, *acts) -> Act or tuple of Acts.  Inputs/outputs are NHWC-shaped
+    tensors already ((B,1,1,K) for vectors); the caller reshapes at the API surface."""
+
+    @staticmethod
+    def forward(ctx, module, emit, comm, grad_on, n_in, *tensors):
+        ins, params = tensors[:n_in], tensors[n_in:]
+        in_needs = [grad_on and t.requires_grad for t in ins]
+        record = grad_on and (any(p.requires_grad for p in params) or any(in_needs))
+        tape = Tape(module.training, record, comm)
+        acts = [tape.input(t.detach().contiguous(), needs_grad=nd) for t, nd in zip(ins, in_needs)]
+        outs = emit(tape, *acts)
+        single = isinstance(outs, Act)
+        outs = [outs] if single else list(outs)
+        outs = [tape.materialize(o) for o in outs]
+        ctx.tape, ctx.outs, ctx.acts, ctx.params, ctx.in_needs = tape, outs, acts, params, in_needs
+        res = tuple(o.t for o in outs)
+        return res[0] if single else res
+
+    @staticmethod
+    def backward(ctx, *gs):
+        tape = ctx.tape
+        first = True
+        for o, g in zip(ctx.outs, gs):
+            if g is not None:
+                o.grad, o.grad_owned = g.contiguous(), False
+        # replay (Tape.backward expects one seeded output; seed all, then run the op loop)
+        out0 = ctx.outs[0]
+        seed = out0.grad
+        tape.backward(out0, seed) if seed is not None else tape.backward_no_seed()
+        grads_in = tuple(a.grad if nd else None for a, nd in zip(ctx.acts, ctx.in_needs))
+        grads_in = tuple(None if g is None else _dense(g) for g in grads_in)
+        grads_p = tuple(tape.param_grads.get(p) for p in ctx.params)
+        tape.param_grads = {}
+        return (None, None, None, None, None) + grads_in + grads_p
+
+
+def run_multi(module, emit, inputs, comm=None):
+    """Execute `emit(tape, *acts)` natively; `inputs` are NHWC-shaped CUDA tensors."""
+    params = [p for p in module.parameters()]
+    for t in inputs:
+        if not t.is_cuda:
+            raise RuntimeError("atomai_b200 networks run on CUDA (sm_100a) only; there is no CPU path")
+    return _MultiFn.apply(module, emit, comm, torch.is_grad_enabled(), len(inputs), *inputs, *params)
 
 
 def _to_nhwc(x: torch.Tensor) -> torch.Tensor:

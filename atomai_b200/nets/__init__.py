@@ -1,4 +1,10 @@
 from .blocks import ConvBlock, DilatedBlock, UpsampleBlock
+from .ed import (SignalDecoder, SignalED, SignalEncoder, convDecoderNet, convEncoderNet,
+                 coord_latent, fcDecoderNet, fcEncoderNet, init_imspec_model, init_VAE_nets,
+                 rDecoderNet)
 from .fcnn import Unet, dilnet, init_fcnn_model
 
-__all__ = ["ConvBlock", "UpsampleBlock", "DilatedBlock", "Unet", "dilnet", "init_fcnn_model"]
+__all__ = ["ConvBlock", "UpsampleBlock", "DilatedBlock", "Unet", "dilnet", "init_fcnn_model",
+           "SignalEncoder", "SignalDecoder", "SignalED", "convEncoderNet", "convDecoderNet",
+           "fcEncoderNet", "fcDecoderNet", "rDecoderNet", "coord_latent", "init_imspec_model",
+           "init_VAE_nets"]

@@ -163,6 +163,12 @@ def upsample_bwd(dy, dx, bilinear=True) -> None:
                                            1 if bilinear else 0, stream_ptr()))
 
 
+def transpose(x, y, N, R, Cc) -> None:
+    """y[n][c][r] = x[n][r][c] (both contiguous)."""
+    assert x.is_contiguous() and y.is_contiguous() and x.numel() == y.numel() == N * R * Cc
+    check(lib().atomai_b200_transpose(ptr(x), ptr(y), N, R, Cc, stream_ptr()))
+
+
 def add_slice(src, dst, accumulate) -> None:
     N, H, W, Cc = src.shape
     check(lib().atomai_b200_add_slice(ptr(src), _ld(src), ptr(dst), _ld(dst),
@@ -223,6 +229,23 @@ def linear_bwd(x, w, dy, dx, dw, db) -> None:
     O = w.shape[0]
     check(lib().atomai_b200_linear_bwd(ptr(x), ptr(w), ptr(dy), ptr(dx), ptr(dw), ptr(db), Bn, K,
                                        O, stream_ptr()))
+
+
+def coord_latent_desc(B, H, W, z, phi, dx, wc, bc, wz, tanh_act) -> _C.CoordLat:
+    d = _C.CoordLat()
+    d.B, d.H, d.W, d.zdim, d.hid, d.tanh_act = B, H, W, (z.shape[1] if z is not None else 0), \
+        wc.shape[0], 1 if tanh_act else 0
+    d.z, d.phi, d.dx, d.wc, d.bc, d.wz = ptr(z), ptr(phi), ptr(dx), ptr(wc), ptr(bc), ptr(wz)
+    return d
+
+
+def coord_latent_fwd(d: _C.CoordLat, h0) -> None:
+    check(lib().atomai_b200_coord_latent_fwd(C.byref(d), ptr(h0), stream_ptr()))
+
+
+def coord_latent_bwd(d: _C.CoordLat, dpre0, dwc, dbc, sb, dphi, ddx) -> None:
+    check(lib().atomai_b200_coord_latent_bwd(C.byref(d), ptr(dpre0), ptr(dwc), ptr(dbc), ptr(sb),
+                                             ptr(dphi), ptr(ddx), stream_ptr()))
 
 
 def gram(x1, x2, inv_ls, outputscale, kind, out) -> None:

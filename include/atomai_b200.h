@@ -136,6 +136,9 @@ int atomai_b200_upsample2x_fwd(const float* x, int ld_x, float* y, int ld_y, int
                                int C, int bilinear, void* stream);
 int atomai_b200_upsample2x_bwd(const float* dy, int ld_dy, float* dx, int ld_dx, int N, int h,
                                int w, int C, int bilinear, void* stream);
+/* y[n][c][r] = x[n][r][c]: NHWC <-> NCHW around `x.reshape(-1, C*H*W)` -> nn.Linear
+ * (atomai/nets/ed.py:77-79, 284-287, 516-517). */
+int atomai_b200_transpose(const float* x, float* y, int N, int R, int Cc, void* stream);
 /* dst[p][0:C] (+)= src[p][0:C] — gradient routing between channel slices */
 int atomai_b200_add_slice(const float* src, int ld_s, float* dst, int ld_d, int accumulate,
                           int64_t npix, int C, void* stream);

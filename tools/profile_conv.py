@@ -1,0 +1,21 @@
+"""Launch the fused conv kernel on selected UNet layer shapes (for `ncu --set full`)."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+from atomai_b200 import ops
+from atomai_b200.ops import Source
+shapes = {"c6": (32, 512, 32, 16), "bn3": (32, 64, 128, 128), "c5": (32, 256, 64, 32)}
+which = sys.argv[1:] or ["c6", "bn3"]
+for tag in which:
+    N, hh, cin, cout = shapes[tag]
+    dev = "cuda"
+    x = torch.rand(N, hh, hh, cin, device=dev); sc = torch.rand(cin, device=dev) + 0.5; sh = torch.rand(cin, device=dev)
+    w = torch.randn(cout, cin, 3, 3, device=dev) * 0.05; b = torch.randn(cout, device=dev) * 0.1
+    out = torch.empty(N, hh, hh, cout, device=dev); st = torch.zeros(2 * cout, device=dev, dtype=torch.float64)
+    d = ops.conv_desc([Source(x, sc, sh)], N, hh, hh, cout, (3, 3), 1, 0.01, ops.MATH_TF32)
+    wp = ops.prep_weights(w, ops.WMODE_FWD, ops.MATH_TF32)
+    for _ in range(3):
+        ops.conv_fwd(d, wp, b, out, st)
+    torch.cuda.synchronize()
+print("done")
