@@ -31,8 +31,8 @@ constexpr int kFirstLoadWarp = 8;   // warps 6,7 idle: roles are aligned to 4-wa
 constexpr int kNumLoadWarps = 8;
 constexpr int kThreads = (kFirstLoadWarp + kNumLoadWarps) * 32;  // 512 -> 128 regs/thread at launch
 // register re-balancing between the warpgroups (sum * 128 threads = 64K registers)
-constexpr int kRegsEpi = 80, kRegsMma = 48, kRegsLoad = 192;
-static_assert(kRegsEpi + kRegsMma + 2 * kRegsLoad == 512, "register budget");
+constexpr int kRegsEpi = 80, kRegsMma = 72, kRegsLoad = 176;
+static_assert(kRegsEpi + kRegsMma + 2 * kRegsLoad <= 512, "register budget");
 constexpr int kMaxAStages = 4;
 constexpr int kMaxBStages = 12;
 constexpr int kGroupThreads = 128;  // loader threads per group (2 groups of 4 warps)
@@ -77,9 +77,9 @@ static_assert(sizeof(SharedCtl) <= 320, "SharedCtl must fit below the MMA offset
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   SharedCtl* ctl = reinterpret_cast<SharedCtl*>(smem);
-  uint2* mma_tab = reinterpret_cast<uint2*>(smem + 320);   // [taps * ksteps] <= 36 entries
   float* s_stats = reinterpret_cast<float*>(smem + 640);  // [4 warps][2][Cout]
-  const uint32_t stats_bytes = kNumEpiWarps * 2 * p.Cout * sizeof(float);
+  const uint32_t stats_bytes = (kNumEpiWarps * 2 + 1) * p.Cout * sizeof(float);   // + bias copy
+  float* s_bias = s_stats + kNumEpiWarps * 2 * p.Cout;
   const uint32_t a_base = smem_u32(smem) + ((640 + stats_bytes + 127) & ~127u);
   const uint32_t b_base = a_base + p.n_a * p.a_stage_bytes;
 
@@ -106,6 +106,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
   if (warp == kWgtWarp) tmem_alloc(smem_u32(&ctl->tmem_base), p.tmem_cols);
   if (warp < kNumEpiWarps) {
     for (int i = lane; i < 2 * p.Cout; i += 32) s_stats[warp * 2 * p.Cout + i] = 0.f;
+    if (warp == 0)
+      for (int i = lane; i < p.Cout; i += 32) s_bias[i] = p.bias ? __ldg(p.bias + i) : 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -138,6 +140,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
       }
     }
     const int H = p.H, W = p.W;
+    const uint32_t bar_full_a = smem_u32(&ctl->full_a[0]), bar_empty_a = smem_u32(&ctl->empty_a[0]);
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const int tw_i = tile % p.tiles_w;
@@ -214,7 +217,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
           }
         }
         const uint32_t st = it % p.n_a;
-        mbar_wait(smem_u32(&ctl->empty_a[st]), ((it / p.n_a) & 1) ^ 1);
+        mbar_wait(bar_empty_a + st * 8, ((it / p.n_a) & 1) ^ 1);
         const uint32_t dst = a_base + st * p.a_stage_bytes + j * p.plane_bytes;
 #pragma unroll
         for (int u = 0; u < kMaxU; ++u) {
@@ -229,14 +232,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
         }
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&ctl->full_a[st]));
+        if (lane == 0) mbar_arrive(bar_full_a + st * 8);
       }
     }
   } else if (warp >= kNumEpiWarps) {
    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsMma));
    if (warp == kWgtWarp) {
     // ===================== weight producer =====================
-    if (lane == 0) {
+    if (elect_one()) {
       if (p.w_resident) {
         // the packed blob is already in shared-memory order: copy it once, in 16 KB pieces
         const uint32_t bar = smem_u32(&ctl->w_full);
@@ -246,20 +249,22 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
           bulk_g2s(b_base + off, reinterpret_cast<const char*>(p.wblob) + off, n, bar);
         }
       } else {
-        uint32_t it = 0;
+        uint32_t st = 0, ph = 1;
         const int ksteps = p.KC >> 3;
         const uint32_t piece = p.Cout * 32;  // bytes of one (k-step, tap) piece
+        const uint32_t n_b = p.n_b, b_stage = p.b_stage_bytes;
+        const uint32_t bar_full_b = smem_u32(&ctl->full_b[0]), bar_empty_b = smem_u32(&ctl->empty_b[0]);
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
           for (int ch = 0; ch < p.n_chunks; ++ch) {
-            for (int t = 0; t < taps; ++t, ++it) {
-              const uint32_t st = it % p.n_b;
-              mbar_wait(smem_u32(&ctl->empty_b[st]), ((it / p.n_b) & 1) ^ 1);
-              const uint32_t bar = smem_u32(&ctl->full_b[st]);
-              mbar_arrive_expect_tx(bar, p.b_stage_bytes);
+            for (int t = 0; t < taps; ++t) {
+              mbar_wait(bar_empty_b + st * 8, ph);
+              const uint32_t bar = bar_full_b + st * 8;
+              mbar_arrive_expect_tx(bar, b_stage);
+              const float* src = p.wblob + ((size_t)ch * ksteps * taps + t) * (piece >> 2);
               for (int ks = 0; ks < ksteps; ++ks)
-                bulk_g2s(b_base + st * p.b_stage_bytes + ks * piece,
-                         p.wblob + ((size_t)(ch * ksteps + ks) * taps + t) * (piece >> 2), piece,
-                         bar);
+                bulk_g2s(b_base + st * b_stage + ks * piece, src + (size_t)ks * taps * (piece >> 2),
+                         piece, bar);
+              if (++st == n_b) { st = 0; ph ^= 1; }
             }
           }
         }
@@ -268,80 +273,70 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
     __syncwarp();
    } else if (warp == kMmaWarp) {
     // ===================== MMA issuer =====================
-    // One thread issues every tcgen05.mma, so its instruction count per MMA bounds the kernel for
-    // the thin layers (an M128 x N16 x K8 MMA is 8 tensor-pipe cycles).  All descriptor
-    // arithmetic is hoisted: a table of (A offset, B offset) per (tap, k-step) in shared memory,
-    // constant descriptor high words, and a loop body of two adds + the MMA.
-    {   // the whole warp runs the (uniform) control flow; one elected lane issues MMAs/commits
+    // One elected thread issues every tcgen05.mma, so its instruction count per MMA bounds the
+    // kernel for the thin layers (an M128 x N16 x K8 MMA is 8 tensor-pipe cycles).  The loop nest
+    // (ty, tx, k-step) advances both descriptors by constant increments only.
+    if (elect_one()) {
       const uint32_t idesc = umma_idesc_tf32(128, p.Cout, 0, 0);
-      const uint32_t piece = p.Cout * 32;
+      const uint32_t piece16 = (uint32_t)p.Cout * 32 >> 4;
       const int ksteps = p.KC >> 3;
-      const int nmma = taps * ksteps;                 // MMAs per chunk (per sub-tile)
       const uint64_t a_tmpl = umma_desc(0, p.plane_bytes, p.TWp * 16);
       const uint64_t b_tmpl = umma_desc(0, p.Cout * 16, 128);
-      for (int t = 0; t < taps; ++t) {
-        const int ty = t / p.taps_w, tx = t - ty * p.taps_w;
-        for (int ks = 0; ks < ksteps; ++ks) {
-          const uint32_t ao = (ty * p.dil * p.TWp + tx * p.dil) * 16 + ks * 2 * p.plane_bytes;
-          const uint32_t bo = p.w_resident ? (uint32_t)(t + ks * taps) * piece : ks * piece;
-          if (lane == 0) mma_tab[t * ksteps + ks] = make_uint2(ao >> 4, bo >> 4);
-        }
-      }
-      __syncwarp();
-      uint32_t ita = 0, itb = 0, acc = 0, acc_phase = 0;
       const uint32_t sub = p.sub, n_a = p.n_a, n_b = p.n_b, n_chunks = p.n_chunks;
       const uint32_t a_stage16 = p.a_stage_bytes >> 4, b_stage16 = p.b_stage_bytes >> 4;
       const uint32_t a_base16 = a_base >> 4, b_base16 = b_base >> 4;
-      const uint32_t chunk_w16 = (uint32_t)(ksteps * taps) * piece >> 4;   // resident weights per chunk
-      const uint32_t cout = p.Cout;
+      const uint32_t plane2_16 = (uint32_t)p.plane_bytes * 2 >> 4;   // next k-step of A
+      const uint32_t dx16 = p.dil, dy16 = (uint32_t)p.dil * p.TWp;   // tap steps of A (16 B units)
+      const int th = p.taps_h, tw = p.taps_w;
       const bool resident = p.w_resident != 0;
+      // resident weights: piece index = (chunk*ksteps + ks)*taps + t  -> B step per ks / per tap
+      const uint32_t b_ks16 = resident ? (uint32_t)taps * piece16 : piece16;
+      const uint32_t chunk_w16 = (uint32_t)(ksteps * taps) * piece16;
+      const uint32_t cout = p.Cout;
+      uint32_t sa = 0, pa = 0, sb = 0, pb = 0, acc = 0, acc_phase = 0;   // stage / phase counters
+      const uint32_t bar_full_a = smem_u32(&ctl->full_a[0]), bar_empty_a = smem_u32(&ctl->empty_a[0]);
+      const uint32_t bar_full_b = smem_u32(&ctl->full_b[0]), bar_empty_b = smem_u32(&ctl->empty_b[0]);
+      const uint32_t bar_tfull = smem_u32(&ctl->tmem_full[0]), bar_tempty = smem_u32(&ctl->tmem_empty[0]);
       if (resident) {
         mbar_wait(smem_u32(&ctl->w_full), 0);
         tc_fence_after();
       }
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        mbar_wait(smem_u32(&ctl->tmem_empty[acc]), acc_phase ^ 1);
+        mbar_wait(bar_tempty + acc * 8, acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * sub * cout;
-        for (uint32_t ch = 0; ch < n_chunks; ++ch, ++ita) {
-          const uint32_t sa = ita % n_a;
-          mbar_wait(smem_u32(&ctl->full_a[sa]), (ita / n_a) & 1);
+        uint32_t accum = 0u;
+        uint32_t w_off16 = 0;                                            // resident: chunk offset
+        for (uint32_t ch = 0; ch < n_chunks; ++ch, w_off16 += chunk_w16) {
+          mbar_wait(bar_full_a + sa * 8, pa);
           tc_fence_after();
-          const uint64_t a0 = a_tmpl + (a_base16 + sa * a_stage16);
-          if (resident) {
-            const uint64_t b0 = b_tmpl + (b_base16 + ch * chunk_w16);
-            uint32_t accum = ch != 0 ? 1u : 0u;
-            for (int i = 0; i < nmma; ++i) {
-              const uint2 o = mma_tab[i];
-              if (elect_one()) {
-                umma_tf32(d_tmem, a0 + o.x, b0 + o.y, idesc, accum);
-                if (sub > 1)
-                  umma_tf32(d_tmem + cout, a0 + o.x + (kTileW * 16 >> 4), b0 + o.y, idesc, accum);
+          uint64_t a_row = a_tmpl + (a_base16 + sa * a_stage16);
+          uint64_t b_tap = b_tmpl + (b_base16 + w_off16);                // resident only
+          for (int ty = 0; ty < th; ++ty, a_row += dy16) {
+            uint64_t a_tap = a_row;
+            for (int tx = 0; tx < tw; ++tx, a_tap += dx16, b_tap += piece16) {
+              uint64_t bd = b_tap;
+              if (!resident) {
+                mbar_wait(bar_full_b + sb * 8, pb);
+                tc_fence_after();
+                bd = b_tmpl + (b_base16 + sb * b_stage16);
               }
-              accum = 1u;
-            }
-          } else {
-            uint32_t accum = ch != 0 ? 1u : 0u;
-            for (int t = 0; t < taps; ++t, ++itb) {
-              const uint32_t sb = itb % n_b;
-              mbar_wait(smem_u32(&ctl->full_b[sb]), (itb / n_b) & 1);
-              tc_fence_after();
-              const uint64_t b0 = b_tmpl + (b_base16 + sb * b_stage16);
-              for (int ks = 0; ks < ksteps; ++ks) {
-                const uint2 o = mma_tab[t * ksteps + ks];
-                if (elect_one()) {
-                  umma_tf32(d_tmem, a0 + o.x, b0 + o.y, idesc, accum);
-                  if (sub > 1)
-                    umma_tf32(d_tmem + cout, a0 + o.x + (kTileW * 16 >> 4), b0 + o.y, idesc, accum);
-                }
+              uint64_t ad = a_tap;
+              for (int ks = 0; ks < ksteps; ++ks, ad += plane2_16, bd += b_ks16) {
+                umma_tf32(d_tmem, ad, bd, idesc, accum);
+                if (sub > 1) umma_tf32(d_tmem + cout, ad + (kTileW * 16 >> 4), bd, idesc, accum);
                 accum = 1u;
               }
-              if (elect_one()) umma_commit(smem_u32(&ctl->empty_b[sb]));
+              if (!resident) {
+                umma_commit(bar_empty_b + sb * 8);
+                if (++sb == n_b) { sb = 0; pb ^= 1; }
+              }
             }
           }
-          if (elect_one()) umma_commit(smem_u32(&ctl->empty_a[sa]));
+          umma_commit(bar_empty_a + sa * 8);
+          if (++sa == n_a) { sa = 0; pa ^= 1; }
         }
-        if (elect_one()) umma_commit(smem_u32(&ctl->tmem_full[acc]));
+        umma_commit(bar_tfull + acc * 8);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -372,8 +367,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
         tmem_ld16(t_addr + c0, v);
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          float x = v[i] + (p.bias ? __ldg(p.bias + c0 + i) : 0.f);
-          x = act_f(x, p.act, p.alpha);
+          const float x = act_f(v[i] + s_bias[c0 + i], p.act, p.alpha);
           v[i] = valid ? x : 0.f;
         }
         if (valid) {
@@ -391,15 +385,25 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
           }
         }
         if (p.stats) {
+          // 32 per-thread values (16 sums, 16 sums of squares) -> transposing butterfly: 31
+          // shuffles leave in lane l the warp total of value l (instead of 32 x 5 shuffles).
+          float w[32];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const float s1 = warp_sum(v[i]);
-            const float s2 = warp_sum(v[i] * v[i]);
-            if (lane == i) {
-              my_stats[c0 + i] += s1;
-              my_stats[p.Cout + c0 + i] += s2;
+            w[i] = v[i];
+            w[16 + i] = v[i] * v[i];
+          }
+#pragma unroll
+          for (int sft = 16; sft >= 1; sft >>= 1) {
+            const bool up = (lane & sft) != 0;
+#pragma unroll
+            for (int k = 0; k < sft; ++k) {
+              const float send = up ? w[k] : w[k + sft];
+              const float keep = up ? w[k + sft] : w[k];
+              w[k] = keep + __shfl_xor_sync(0xffffffffu, send, sft);
             }
           }
+          my_stats[(lane < 16 ? 0 : p.Cout) + c0 + (lane & 15)] += w[0];
         }
       }
      }
@@ -504,7 +508,7 @@ static int conv_tc_plan(const ab_conv_t* d, ConvTcParams* p, int* smem_bytes) {
   const int taps = d->ks_h * d->ks_w;
   p->w_bytes = taps * S.Ctot * d->Cout * 4;
   const int budget = 212 * 1024;
-  const int stats_bytes = ((kNumEpiWarps * 2 * d->Cout * 4 + 127) & ~127) + 640 + 128;
+  const int stats_bytes = (((kNumEpiWarps * 2 + 1) * d->Cout * 4 + 127) & ~127) + 640 + 128;
   // Try, in order of preference: (resident weights, 1 sub-tile), (streamed weights, 2 sub-tiles
   // so that every weight stage feeds M = 256), (streamed, 1 sub-tile).
   bool ok = false;

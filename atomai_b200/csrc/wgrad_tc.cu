@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const WgradTcPara
   } else if (warp >= kNumEpiWarps) {
    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsMma));
    if (warp == kMmaWarp) {
-    {   // warp-converged control flow; one elected lane issues the MMAs / commits
+    if (elect_one()) {   // one elected thread issues every MMA / commit
       const uint32_t idesc = umma_idesc_tf32(128, kNB, 1, 1);
       const uint64_t a_tmpl = umma_desc_ex(0, kDChunk, 512, 1, 0);
       const uint64_t b_tmpl = umma_desc_ex(0, 1024, 512, 1, 0);
@@ -191,15 +191,15 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const WgradTcPara
           uint32_t accum = it > 0 ? 1u : 0u;
 #pragma unroll 4
           for (int h = 0; h < kTileH; ++h) {
-            if (elect_one()) umma_tf32(dcol, ad, bd, idesc, accum);
+            umma_tf32(dcol, ad, bd, idesc, accum);
             accum = 1u;
             ad += 64;              // next 8 pixels of the dy tile (8 x 128 B)
             bd += b_row16;         // next halo row
           }
         }
-        if (elect_one()) umma_commit(smem_u32(&ctl->empty[st]));
+        umma_commit(smem_u32(&ctl->empty[st]));
       }
-      if (elect_one()) umma_commit(smem_u32(&ctl->done));
+      umma_commit(smem_u32(&ctl->done));
     }
     __syncwarp();
    }

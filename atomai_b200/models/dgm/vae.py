@@ -147,21 +147,21 @@ class VAE(BaseVAE):
         return vae_loss(self.loss, self.in_dim, x, x_reconstr, *args, **kwargs)
 
     def forward_compute_elbo(self, x: torch.Tensor, y: Optional[torch.Tensor] = None,
-                             mode: str = "train") -> torch.Tensor:
-        """VAE forward pass with ELBO (vae.py:661-687)."""
+                             mode: str = "train", eps: Optional[torch.Tensor] = None
+                             ) -> torch.Tensor:
+        """VAE forward pass with ELBO (vae.py:661-687).  `eps` (optional) fixes the
+        reparameterisation noise (tests)."""
         if y is not None:
             raise NotImplementedError("class-conditioned VAE is outside the native hot path")
-        if mode == "eval":
-            with torch.no_grad():
-                z_mean, z_logsd = self.encoder_net(x)
-                z = self.reparameterize(z_mean, torch.exp(z_logsd))
-                x_reconstr = self.decoder_net(z)
-                return self.elbo_fn(x, x_reconstr, z_mean, z_logsd, **self.kdict_)
-        z_mean, z_logsd = self.encoder_net(x)
-        self.kdict_["num_iter"] += 1
-        z = self.reparameterize(z_mean, torch.exp(z_logsd))
-        x_reconstr = self.decoder_net(z)
-        return self.elbo_fn(x, x_reconstr, z_mean, z_logsd, **self.kdict_)
+        grad = mode != "eval"
+        with torch.set_grad_enabled(grad):
+            z_mean, z_logsd = self.encoder_net(x)
+            if grad:
+                self.kdict_["num_iter"] += 1
+            z_sd = torch.exp(z_logsd)
+            z = z_mean + z_sd * eps if eps is not None else self.reparameterize(z_mean, z_sd)
+            x_reconstr = self.decoder_net(z)
+            return self.elbo_fn(x, x_reconstr, z_mean, z_logsd, **self.kdict_)
 
     def fit(self, X_train, y_train=None, X_test=None, y_test=None, loss: str = "mse", **kwargs):
         """Trains VAE model (vae.py:689-743): kwargs capacity, training_cycles, batch_size,

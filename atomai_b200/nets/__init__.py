@@ -3,8 +3,9 @@ from .ed import (SignalDecoder, SignalED, SignalEncoder, convDecoderNet, convEnc
                  coord_latent, fcDecoderNet, fcEncoderNet, init_imspec_model, init_VAE_nets,
                  rDecoderNet)
 from .fcnn import Unet, dilnet, init_fcnn_model
+from .gp import DeepKernel, GPRegressionModel, dense_gram, fcFeatureExtractor
 
 __all__ = ["ConvBlock", "UpsampleBlock", "DilatedBlock", "Unet", "dilnet", "init_fcnn_model",
            "SignalEncoder", "SignalDecoder", "SignalED", "convEncoderNet", "convDecoderNet",
            "fcEncoderNet", "fcDecoderNet", "rDecoderNet", "coord_latent", "init_imspec_model",
-           "init_VAE_nets"]
+           "init_VAE_nets", "fcFeatureExtractor", "DeepKernel", "dense_gram", "GPRegressionModel"]
