@@ -741,15 +741,15 @@ int atomai_b200_affine(const float* a, int ld_a, const float* scale, const float
 int atomai_b200_bn_bwd_reduce(const float* dy, int ld_dy, const float* a, int ld_a,
                               const float* mean, const float* invstd, int64_t npix, int C,
                               double* sums, void* stream) {
-  AB_CHECK(C <= kT, "bn_bwd_reduce: C=%d > %d unsupported", C, kT);
   if (npix == 0) return 0;
-  if (vec_ok(C, {dy, a, mean, invstd}, {ld_dy, ld_a}, npix)) {
+  if (C <= 4 * kT && vec_ok(C, {dy, a, mean, invstd}, {ld_dy, ld_a}, npix)) {
     const ChanLayout l4 = chan_layout(C / 4);
     bn_bwd_reduce_vec_kernel<<<grid_for(npix, l4.R * 8), kT, 0, STREAM>>>(
         dy, ld_dy, a, ld_a, mean, invstd, npix, C / 4, l4.CW, l4.R, sums);
     AB_LAUNCH_CHECK();
     return 0;
   }
+  AB_CHECK(C <= kT, "bn_bwd_reduce: C=%d unsupported (max %d, or %d when C %% 4 == 0)", C, kT, 4 * kT);
   const ChanLayout l = chan_layout(C);
   bn_bwd_reduce_kernel<<<grid_for(npix, l.R * 8), kT, 0, STREAM>>>(dy, ld_dy, a, ld_a, mean,
                                                                   invstd, npix, C, l.CW, l.R,
@@ -763,9 +763,8 @@ int atomai_b200_bn_lrelu_bwd(const float* dy, int ld_dy, const float* a, int ld_
                              const double* sums, double count, const float* extra, int ld_extra,
                              int act, float lrelu, float* dpre, int ld_dpre, double* dbias,
                              int64_t npix, int C, void* stream) {
-  AB_CHECK(C <= kT, "bn_lrelu_bwd: C=%d > %d unsupported", C, kT);
   if (npix == 0) return 0;
-  if (vec_ok(C, {dy, a, mean, invstd, scale, extra, dpre}, {dy ? ld_dy : 0, ld_a, extra ? ld_extra : 0, ld_dpre}, npix)) {
+  if (C <= 4 * kT && vec_ok(C, {dy, a, mean, invstd, scale, extra, dpre}, {dy ? ld_dy : 0, ld_a, extra ? ld_extra : 0, ld_dpre}, npix)) {
     const ChanLayout l4 = chan_layout(C / 4);
     bn_lrelu_bwd_vec_kernel<<<grid_for(npix, l4.R * 8), kT, 0, STREAM>>>(
         dy, ld_dy, a, ld_a, mean, invstd, scale, sums, count, extra, ld_extra, act, lrelu, dpre,
@@ -773,6 +772,7 @@ int atomai_b200_bn_lrelu_bwd(const float* dy, int ld_dy, const float* a, int ld_
     AB_LAUNCH_CHECK();
     return 0;
   }
+  AB_CHECK(C <= kT, "bn_lrelu_bwd: C=%d unsupported (max %d, or %d when C %% 4 == 0)", C, kT, 4 * kT);
   const ChanLayout l = chan_layout(C);
   bn_lrelu_bwd_kernel<<<grid_for(npix, l.R * 8), kT, 0, STREAM>>>(
       dy, ld_dy, a, ld_a, mean, invstd, scale, sums, count, extra, ld_extra, act, lrelu, dpre,

@@ -176,22 +176,23 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const WgradTcPara
       const uint64_t a_tmpl = umma_desc_ex(0, kDChunk, 512, 1, 0);
       const uint64_t b_tmpl = umma_desc_ex(0, 1024, 512, 1, 0);
       const uint32_t b_row16 = (uint32_t)p.TWp * 8;          // one halo row = TWp * 128 B
+      const uint32_t a_hi = (uint32_t)(a_tmpl >> 32), b_hi = (uint32_t)(b_tmpl >> 32);
       uint32_t it = 0;
       for (int tile = t_begin; tile < t_end; ++tile, ++it) {
         const uint32_t st = it % kStages;
         mbar_wait(smem_u32(&ctl->full[st]), (it / kStages) & 1);
         tc_fence_after();
         const uint32_t d0 = base + st * p.stage_bytes, x0 = d0 + kDBytes;
-        const uint64_t a0 = a_tmpl + (d0 >> 4), b0 = b_tmpl + (x0 >> 4);
+        const uint32_t a0 = (uint32_t)a_tmpl + (d0 >> 4), b0 = (uint32_t)b_tmpl + (x0 >> 4);
         for (int t = 0; t < taps; ++t) {
           const int ty = t / p.taps_w, tx = t - ty * p.taps_w;
-          uint64_t ad = a0;
-          uint64_t bd = b0 + (uint32_t)((ty * p.dil * p.TWp + tx * p.dil) * 8);
+          uint32_t ad = a0;
+          uint32_t bd = b0 + (uint32_t)((ty * p.dil * p.TWp + tx * p.dil) * 8);
           const uint32_t dcol = tmem_base + t * kNB;
           uint32_t accum = it > 0 ? 1u : 0u;
-#pragma unroll 4
+#pragma unroll
           for (int h = 0; h < kTileH; ++h) {
-            umma_tf32(dcol, ad, bd, idesc, accum);
+            umma_tf32_lh(dcol, ad, a_hi, bd, b_hi, idesc, accum);
             accum = 1u;
             ad += 64;              // next 8 pixels of the dy tile (8 x 128 B)
             bd += b_row16;         // next halo row

@@ -162,7 +162,8 @@ def run_group(name):
                 y = F.conv2d(x, w, None, padding=dil, dilation=dil)
                 dy = rnd(N, co, H, W)
                 y.backward(dy)
-                d = ops.conv_desc([Source(nhwc(dy))], N, H, W, ci, (3, 3), dil, 1.0, math)
+                dyn = nhwc(dy)   # keep alive: the descriptor only stores its pointer
+                d = ops.conv_desc([Source(dyn)], N, H, W, ci, (3, 3), dil, 1.0, math)
                 wp = ops.prep_weights(w, ops.WMODE_DGRAD, math)
                 out = torch.empty(N, H, W, ci, device=dev)
                 ops.conv_fwd(d, wp, None, out, None)
