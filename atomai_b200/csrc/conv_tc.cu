@@ -31,7 +31,7 @@ constexpr int kFirstLoadWarp = 8;   // warps 6,7 idle: roles are aligned to 4-wa
 constexpr int kNumLoadWarps = 8;
 constexpr int kThreads = (kFirstLoadWarp + kNumLoadWarps) * 32;  // 512 -> 128 regs/thread at launch
 // register re-balancing between the warpgroups (sum * 128 threads = 64K registers)
-constexpr int kRegsEpi = 80, kRegsMma = 72, kRegsLoad = 176;
+constexpr int kRegsEpi = 112, kRegsMma = 72, kRegsLoad = 160;
 static_assert(kRegsEpi + kRegsMma + 2 * kRegsLoad <= 512, "register budget");
 constexpr int kMaxAStages = 4;
 constexpr int kMaxBStages = 12;
@@ -144,6 +144,290 @@ __device__ __forceinline__ void mma_issue_loop(const ConvTcParams& p, SharedCtl*
   }
 }
 
+// RN-to-TF32 of an fp32 bit pattern for a tcgen05 operand: the tensor core reads only the upper
+// 19 bits, so adding half an ulp of the 10-bit mantissa (round-half-away, like cvt.rna) is enough
+// and costs one integer add instead of cvt.rna.tf32's four-instruction emulation.
+__device__ __forceinline__ uint32_t tf32_bits(float x) { return __float_as_uint(x) + 0x1000u; }
+
+// Activation loader of one group (4 warps), specialised on U = 16-byte elements per thread per
+// chunk.  Element u of a thread is halo pixel q0 + u*QS of plane j for every chunk, so its pixel
+// offset relative to the tile origin and its smem slot are loop constants; only element U-1 can be
+// absent (HP is not a multiple of QS), every other load/store is unconditional.
+template <int U>
+__device__ __forceinline__ void loader_loop(const ConvTcParams& p, SharedCtl* ctl,
+                                            uint32_t a_base, int grp) {
+  const int lane = threadIdx.x & 31;
+  const int gt = threadIdx.x - (kFirstLoadWarp + grp * 4) * 32;   // 0..127
+  const int P = p.KC >> 2;                   // planes per chunk (2, 4 or 8)
+  const int j = gt & (P - 1);                // this thread's plane (constant: 128 % P == 0)
+  const int QS = kGroupThreads / P;          // halo pixels advanced per u
+  const int q0 = gt / P;
+  const int H = p.H, W = p.W;
+  uint32_t pix[U], hw[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int q = q0 + u * QS;
+    const bool v = q < p.HP;
+    const int hh = v ? q / p.TWp : 0;
+    const int ww = v ? q - hh * p.TWp : 0;
+    pix[u] = (uint32_t)(hh * W + ww);
+    hw[u] = ((uint32_t)hh << 16) | (uint32_t)ww;
+  }
+  const uint32_t last_valid = (q0 + (U - 1) * QS) < p.HP ? 1u : 0u;
+  const uint32_t dst0 = a_base + j * p.plane_bytes + q0 * 16;
+  const uint32_t qs16 = QS * 16;
+  const uint32_t bar_full_a = smem_u32(&ctl->full_a[0]), bar_empty_a = smem_u32(&ctl->empty_a[0]);
+  const int tpi = p.tiles_w * p.tiles_h;
+  const float inv_tpi = 1.f / (float)tpi, inv_tw = 1.f / (float)p.tiles_w;
+  const int n_chunks = p.n_chunks;
+  const uint32_t n_a = p.n_a;
+  // this group's chunks: the CTA's running chunk counter it = grp, grp+2, ...
+  int tile = blockIdx.x, ch = grp;
+  uint32_t st = grp % n_a, ph = ((grp / n_a) & 1) ^ 1;   // stage / empty-phase of chunk `it`
+  const uint32_t st_step = 2 % n_a, st_wrap2 = 2 / n_a;  // n_a in {2,3,4}
+  for (;;) {
+    while (ch >= n_chunks) { ch -= n_chunks; tile += gridDim.x; }
+    if (tile >= p.num_tiles) break;
+    // tile -> (n, th_i, tw_i) without integer division
+    int n = __float2int_rz((float)tile * inv_tpi);
+    n += ((n + 1) * tpi <= tile) - (n * tpi > tile);
+    const int rem = tile - n * tpi;
+    int th_i = __float2int_rz((float)rem * inv_tw);
+    th_i += ((th_i + 1) * p.tiles_w <= rem) - (th_i * p.tiles_w > rem);
+    const int tw_i = rem - th_i * p.tiles_w;
+    const int h_org = th_i * kTileH - p.dil * (p.taps_h >> 1);
+    const int w_org = tw_i * kTileW * p.sub - p.dil * (p.taps_w >> 1);
+    int c = ch * p.KC + j * 4;
+    const SrcDev* sp = &p.S.s[0];
+    if (p.S.nsrc > 1 && c >= p.S.s[0].C) {
+      sp = &p.S.s[1];
+      c -= p.S.s[0].C;
+    }
+    const uint32_t ld = sp->ld;
+    const bool pool = sp->pool != 0;
+    const bool has_aff = sp->scale != nullptr;
+    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (has_aff) {
+      sc = __ldg(reinterpret_cast<const float4*>(sp->scale + c));
+      sh = __ldg(reinterpret_cast<const float4*>(sp->shift + c));
+    }
+    const float* base = sp->ptr + c;
+    float4 v[U];
+    const bool interior = h_org >= 0 && w_org >= 0 && h_org + p.THp <= H && w_org + p.TWp <= W;
+    if (!pool && interior) {
+      // fast path (~90 % of the tiles of a 512^2 image): one IMAD.WIDE + LDG.128 per element
+      const float* tb = base + ((size_t)(n * H + h_org) * W + w_org) * ld;
+#pragma unroll
+      for (int u = 0; u < U; ++u) v[u] = __ldg(reinterpret_cast<const float4*>(tb + pix[u] * ld));
+      if (has_aff) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          v[u].x = fmaf(v[u].x, sc.x, sh.x);
+          v[u].y = fmaf(v[u].y, sc.y, sh.y);
+          v[u].z = fmaf(v[u].z, sc.z, sh.z);
+          v[u].w = fmaf(v[u].w, sc.w, sh.w);
+        }
+      }
+    } else if (!pool) {
+      const size_t img = (size_t)n * H;
+      uint32_t okmask = 0;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int gh = h_org + (int)(hw[u] >> 16), gw = w_org + (int)(hw[u] & 0xFFFFu);
+        const bool ok = (unsigned)gh < (unsigned)H && (unsigned)gw < (unsigned)W;
+        const int ghc = min(max(gh, 0), H - 1), gwc = min(max(gw, 0), W - 1);
+        v[u] = __ldg(reinterpret_cast<const float4*>(base + ((img + ghc) * W + gwc) * ld));
+        okmask |= (ok ? 1u : 0u) << u;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const bool ok = (okmask >> u) & 1u;
+        v[u].x = ok ? fmaf(v[u].x, sc.x, sh.x) : 0.f;
+        v[u].y = ok ? fmaf(v[u].y, sc.y, sh.y) : 0.f;
+        v[u].z = ok ? fmaf(v[u].z, sc.z, sh.z) : 0.f;
+        v[u].w = ok ? fmaf(v[u].w, sc.w, sh.w) : 0.f;
+      }
+    } else {
+      const int H2 = 2 * H, W2 = 2 * W;
+      const size_t img = (size_t)n * H2;
+      const size_t rs = (size_t)W2 * ld;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int gh = h_org + (int)(hw[u] >> 16), gw = w_org + (int)(hw[u] & 0xFFFFu);
+        const bool ok = (unsigned)gh < (unsigned)H && (unsigned)gw < (unsigned)W;
+        const int ghc = min(max(gh, 0), H - 1), gwc = min(max(gw, 0), W - 1);
+        const float* q0p = base + ((img + 2 * ghc) * W2 + 2 * gwc) * ld;
+        const float4 a0 = __ldg(reinterpret_cast<const float4*>(q0p));
+        const float4 a1 = __ldg(reinterpret_cast<const float4*>(q0p + ld));
+        const float4 a2 = __ldg(reinterpret_cast<const float4*>(q0p + rs));
+        const float4 a3 = __ldg(reinterpret_cast<const float4*>(q0p + rs + ld));
+        const float mx = fmaxf(fmaxf(fmaf(a0.x, sc.x, sh.x), fmaf(a1.x, sc.x, sh.x)),
+                               fmaxf(fmaf(a2.x, sc.x, sh.x), fmaf(a3.x, sc.x, sh.x)));
+        const float my = fmaxf(fmaxf(fmaf(a0.y, sc.y, sh.y), fmaf(a1.y, sc.y, sh.y)),
+                               fmaxf(fmaf(a2.y, sc.y, sh.y), fmaf(a3.y, sc.y, sh.y)));
+        const float mz = fmaxf(fmaxf(fmaf(a0.z, sc.z, sh.z), fmaf(a1.z, sc.z, sh.z)),
+                               fmaxf(fmaf(a2.z, sc.z, sh.z), fmaf(a3.z, sc.z, sh.z)));
+        const float mw = fmaxf(fmaxf(fmaf(a0.w, sc.w, sh.w), fmaf(a1.w, sc.w, sh.w)),
+                               fmaxf(fmaf(a2.w, sc.w, sh.w), fmaf(a3.w, sc.w, sh.w)));
+        v[u] = make_float4(ok ? mx : 0.f, ok ? my : 0.f, ok ? mz : 0.f, ok ? mw : 0.f);
+      }
+    }
+    mbar_wait(bar_empty_a + st * 8, ph);
+    const uint32_t dst = dst0 + st * p.a_stage_bytes;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %5, 0;\n\t"
+          "@p st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n\t}" ::"r"(dst + u * qs16),
+          "r"(tf32_bits(v[u].x)), "r"(tf32_bits(v[u].y)), "r"(tf32_bits(v[u].z)),
+          "r"(tf32_bits(v[u].w)), "r"(u == U - 1 ? last_valid : 1u)
+          : "memory");
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_full_a + st * 8);
+    // advance to this group's next chunk (it += 2)
+    ch += 2;
+    st += st_step;
+    ph ^= st_wrap2;
+    if (st >= n_a) { st -= n_a; ph ^= 1; }
+  }
+}
+
+// Transposing butterfly: 32 per-thread values -> lane l holds the warp total of value l
+// (31 shuffles instead of 32 x 5).
+__device__ __forceinline__ float warp_transpose_sum32(float (&w)[32], int lane) {
+#pragma unroll
+  for (int sft = 16; sft >= 1; sft >>= 1) {
+    const bool up = (lane & sft) != 0;
+#pragma unroll
+    for (int k = 0; k < sft; ++k) {
+      const float send = up ? w[k] : w[k + sft];
+      const float keep = up ? w[k + sft] : w[k];
+      w[k] = keep + __shfl_xor_sync(0xffffffffu, send, sft);
+    }
+  }
+  return w[0];
+}
+
+// Epilogue warps 0-3: TMEM -> registers -> bias + activation -> global store + BN statistics.
+// NG > 0 (Cout = 16*NG <= 32, the HBM-bound thin layers): per-thread running sums live in
+// registers for the whole kernel (2 instructions per value) and are reduced once at the end;
+// NG == 0: per-tile transposing butterfly into per-warp shared-memory partials.
+// FAST: LeakyReLU with 0 <= slope <= 1 as max(x, slope*x).
+template <int NG, bool FAST>
+__device__ __forceinline__ void epilogue_loop(const ConvTcParams& p, SharedCtl* ctl,
+                                              uint32_t tmem_base, float* s_stats,
+                                              const float* s_bias) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t acc = 0, acc_phase = 0;
+  float* my_stats = s_stats + warp * 2 * p.Cout;
+  const int row = warp * 32 + lane;
+  const int r_h = row >> 3, r_w = row & 7;
+  const int tpi = p.tiles_w * p.tiles_h;
+  const float inv_tpi = 1.f / (float)tpi, inv_tw = 1.f / (float)p.tiles_w;
+  const float alpha = p.alpha;
+  constexpr int NA = NG > 0 ? NG * 16 : 16;
+  float rs[NA], rq[NA];
+#pragma unroll
+  for (int i = 0; i < NA; ++i) rs[i] = rq[i] = 0.f;
+  const bool do_stats = p.stats != nullptr;
+  for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    int n = __float2int_rz((float)tile * inv_tpi);
+    n += ((n + 1) * tpi <= tile) - (n * tpi > tile);
+    const int rem = tile - n * tpi;
+    int th_i = __float2int_rz((float)rem * inv_tw);
+    th_i += ((th_i + 1) * p.tiles_w <= rem) - (th_i * p.tiles_w > rem);
+    const int tw_i = rem - th_i * p.tiles_w;
+    mbar_wait(smem_u32(&ctl->tmem_full[acc]), acc_phase);
+    tc_fence_after();
+    for (int sb_ = 0; sb_ < p.sub; ++sb_) {
+      const int gh = th_i * kTileH + r_h, gw = (tw_i * p.sub + sb_) * kTileW + r_w;
+      const bool valid = gh < p.H && gw < p.W;
+      const uint32_t t_addr =
+          tmem_base + (acc * p.sub + sb_) * p.Cout + ((uint32_t)(warp * 32) << 16);
+      const size_t pix = ((size_t)n * p.H + gh) * p.W + gw;
+      auto group = [&](const int g, const int gi) {
+        const int c0 = g * 16;
+        float v[16];
+        tmem_ld16(t_addr + c0, v);
+        const float4* b4 = reinterpret_cast<const float4*>(s_bias + c0);
+#pragma unroll
+        for (int i4 = 0; i4 < 4; ++i4) {
+          const float4 bb = b4[i4];
+          const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float x = v[i4 * 4 + k] + bv[k];
+            const float y = FAST ? fmaxf(x, x * alpha) : act_f(x, p.act, alpha);
+            v[i4 * 4 + k] = valid ? y : 0.f;
+          }
+        }
+        if (valid) {
+          if (!p.out_nchw) {
+            float4* o = reinterpret_cast<float4*>(p.out + pix * p.ld_out + c0);
+            o[0] = make_float4(v[0], v[1], v[2], v[3]);
+            o[1] = make_float4(v[4], v[5], v[6], v[7]);
+            o[2] = make_float4(v[8], v[9], v[10], v[11]);
+            o[3] = make_float4(v[12], v[13], v[14], v[15]);
+          } else {
+            const size_t hw = (size_t)p.H * p.W;
+            float* o = p.out + ((size_t)n * p.Cout + c0) * hw + (size_t)gh * p.W + gw;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i * hw] = v[i];
+          }
+        }
+        if (NG > 0) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            rs[gi * 16 + i] += v[i];
+            rq[gi * 16 + i] = fmaf(v[i], v[i], rq[gi * 16 + i]);
+          }
+        } else if (do_stats) {
+          float w[32];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            w[i] = v[i];
+            w[16 + i] = v[i] * v[i];
+          }
+          const float tot = warp_transpose_sum32(w, lane);
+          my_stats[(lane < 16 ? 0 : p.Cout) + c0 + (lane & 15)] += tot;
+        }
+      };
+      if (NG > 0) {
+#pragma unroll
+        for (int g = 0; g < (NG > 0 ? NG : 1); ++g) group(g, g);
+      } else {
+        const int n_groups = p.Cout >> 4;
+#pragma unroll 1
+        for (int g = 0; g < n_groups; ++g) group(g, 0);
+      }
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(smem_u32(&ctl->tmem_empty[acc]));
+    acc ^= 1;
+    if (acc == 0) acc_phase ^= 1;
+  }
+  if (do_stats) {
+    if (NG > 0) {
+#pragma unroll
+      for (int g = 0; g < NG; ++g) {
+        float w[32];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          w[i] = rs[g * 16 + i];
+          w[16 + i] = rq[g * 16 + i];
+        }
+        const float tot = warp_transpose_sum32(w, lane);
+        my_stats[(lane < 16 ? 0 : p.Cout) + g * 16 + (lane & 15)] += tot;
+      }
+    }
+    __syncwarp();
+    for (int i = lane; i < 2 * p.Cout; i += 32) atomicAdd(p.stats + i, (double)my_stats[i]);
+  }
+}
+
 static_assert(sizeof(SharedCtl) <= 320, "SharedCtl must fit below the MMA offset table");
 
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams p) {
@@ -195,144 +479,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
     // are issued branch-free from clamped addresses and masked afterwards, so the compiler keeps
     // all of them in flight before the first use.
     const int grp = (warp - kFirstLoadWarp) >> 2;
-    const int gt = threadIdx.x - (kFirstLoadWarp + grp * 4) * 32;   // 0..127
-    const int P = p.KC >> 2;                   // planes per chunk
-    const int elems = p.HP * P;                // 16B elements per chunk stage
-    const int j = gt % P;                      // this thread's plane (constant: 128 % P == 0)
-    const int U = (elems + kGroupThreads - 1) / kGroupThreads;     // <= kMaxU (plan guarantees)
-    uint32_t hw[kMaxU];
-#pragma unroll
-    for (int u = 0; u < kMaxU; ++u) {
-      const int e = gt + u * kGroupThreads;
-      hw[u] = 0xFFFFFFFFu;
-      if (u < U && e < elems) {
-        const int q = e / P;
-        const int hh = q / p.TWp;
-        hw[u] = ((uint32_t)hh << 16) | (uint32_t)(q - hh * p.TWp);
-      }
-    }
-    const int H = p.H, W = p.W;
-    const uint32_t my_plane = j * p.plane_bytes;
-    const int last_valid = (gt + (U - 1) * kGroupThreads) < elems;   // is the final element real?
-    const uint32_t bar_full_a = smem_u32(&ctl->full_a[0]), bar_empty_a = smem_u32(&ctl->empty_a[0]);
-    uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const int tw_i = tile % p.tiles_w;
-      const int th_i = (tile / p.tiles_w) % p.tiles_h;
-      const int n = tile / (p.tiles_w * p.tiles_h);
-      const int h_org = th_i * kTileH - p.dil * (p.taps_h >> 1);
-      const int w_org = tw_i * kTileW * p.sub - p.dil * (p.taps_w >> 1);
-      for (int ch = 0; ch < p.n_chunks; ++ch, ++it) {
-        if ((int)(it & 1) != grp) continue;
-        int c = ch * p.KC + j * 4;
-        const SrcDev* sp = &p.S.s[0];
-        if (p.S.nsrc > 1 && c >= p.S.s[0].C) {
-          sp = &p.S.s[1];
-          c -= p.S.s[0].C;
-        }
-        const int ld = sp->ld;
-        const bool pool = sp->pool != 0;
-        float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (sp->scale) {
-          sc = __ldg(reinterpret_cast<const float4*>(sp->scale + c));
-          sh = __ldg(reinterpret_cast<const float4*>(sp->shift + c));
-        }
-        const float* base = sp->ptr + c;
-        float4 v[kMaxU];
-        uint32_t okmask = 0;
-        const bool interior = h_org >= 0 && w_org >= 0 && h_org + p.THp <= H && w_org + p.TWp <= W;
-        if (!pool && interior) {
-          // fast path (~90 % of the tiles of a 512^2 image): no clamps, no masks, 32-bit offsets
-          const float* tb = base + ((size_t)(n * H + h_org) * W + w_org) * ld;
-          const uint32_t row = (uint32_t)W * ld;
-#pragma unroll
-          for (int u = 0; u < kMaxU; ++u) {
-            if (u < U) {
-              const uint32_t hwu = (u == U - 1 && !last_valid) ? 0u : hw[u];
-              v[u] = __ldg(reinterpret_cast<const float4*>(
-                  tb + (hwu >> 16) * row + (hwu & 0xFFFFu) * (uint32_t)ld));
-            }
-          }
-          okmask = 0xFFFFFFFFu;
-          if (sp->scale) {
-#pragma unroll
-            for (int u = 0; u < kMaxU; ++u) {
-              if (u < U) {
-                v[u].x = fmaf(v[u].x, sc.x, sh.x);
-                v[u].y = fmaf(v[u].y, sc.y, sh.y);
-                v[u].z = fmaf(v[u].z, sc.z, sh.z);
-                v[u].w = fmaf(v[u].w, sc.w, sh.w);
-              }
-            }
-          }
-        } else if (!pool) {
-          const size_t img = (size_t)n * H;
-#pragma unroll
-          for (int u = 0; u < kMaxU; ++u) {
-            if (u < U) {
-              const int gh = h_org + (int)(hw[u] >> 16), gw = w_org + (int)(hw[u] & 0xFFFFu);
-              const bool ok = hw[u] != 0xFFFFFFFFu && (unsigned)gh < (unsigned)H &&
-                              (unsigned)gw < (unsigned)W;
-              const int ghc = min(max(gh, 0), H - 1), gwc = min(max(gw, 0), W - 1);
-              v[u] = __ldg(reinterpret_cast<const float4*>(base + ((img + ghc) * W + gwc) * ld));
-              okmask |= (ok ? 1u : 0u) << u;
-            }
-          }
-#pragma unroll
-          for (int u = 0; u < kMaxU; ++u) {
-            if (u < U) {
-              v[u].x = fmaf(v[u].x, sc.x, sh.x);
-              v[u].y = fmaf(v[u].y, sc.y, sh.y);
-              v[u].z = fmaf(v[u].z, sc.z, sh.z);
-              v[u].w = fmaf(v[u].w, sc.w, sh.w);
-            }
-          }
-        } else {
-          const int H2 = 2 * H, W2 = 2 * W;
-          const size_t img = (size_t)n * H2;
-          const size_t rs = (size_t)W2 * ld;
-#pragma unroll
-          for (int u = 0; u < kMaxU; ++u) {
-            if (u < U) {
-              const int gh = h_org + (int)(hw[u] >> 16), gw = w_org + (int)(hw[u] & 0xFFFFu);
-              const bool ok = hw[u] != 0xFFFFFFFFu && (unsigned)gh < (unsigned)H &&
-                              (unsigned)gw < (unsigned)W;
-              const int ghc = min(max(gh, 0), H - 1), gwc = min(max(gw, 0), W - 1);
-              const float* q0 = base + ((img + 2 * ghc) * W2 + 2 * gwc) * ld;
-              const float4 a0 = __ldg(reinterpret_cast<const float4*>(q0));
-              const float4 a1 = __ldg(reinterpret_cast<const float4*>(q0 + ld));
-              const float4 a2 = __ldg(reinterpret_cast<const float4*>(q0 + rs));
-              const float4 a3 = __ldg(reinterpret_cast<const float4*>(q0 + rs + ld));
-              v[u].x = fmaxf(fmaxf(fmaf(a0.x, sc.x, sh.x), fmaf(a1.x, sc.x, sh.x)),
-                             fmaxf(fmaf(a2.x, sc.x, sh.x), fmaf(a3.x, sc.x, sh.x)));
-              v[u].y = fmaxf(fmaxf(fmaf(a0.y, sc.y, sh.y), fmaf(a1.y, sc.y, sh.y)),
-                             fmaxf(fmaf(a2.y, sc.y, sh.y), fmaf(a3.y, sc.y, sh.y)));
-              v[u].z = fmaxf(fmaxf(fmaf(a0.z, sc.z, sh.z), fmaf(a1.z, sc.z, sh.z)),
-                             fmaxf(fmaf(a2.z, sc.z, sh.z), fmaf(a3.z, sc.z, sh.z)));
-              v[u].w = fmaxf(fmaxf(fmaf(a0.w, sc.w, sh.w), fmaf(a1.w, sc.w, sh.w)),
-                             fmaxf(fmaf(a2.w, sc.w, sh.w), fmaf(a3.w, sc.w, sh.w)));
-              okmask |= (ok ? 1u : 0u) << u;
-            }
-          }
-        }
-        const uint32_t st = it % p.n_a;
-        mbar_wait(bar_empty_a + st * 8, ((it / p.n_a) & 1) ^ 1);
-        const uint32_t dst = a_base + st * p.a_stage_bytes + my_plane;
-#pragma unroll
-        for (int u = 0; u < kMaxU; ++u) {
-          if (u < U && hw[u] != 0xFFFFFFFFu) {
-            const bool ok = (okmask >> u) & 1u;
-            const uint32_t q = (hw[u] >> 16) * p.TWp + (hw[u] & 0xFFFFu);
-            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + q * 16),
-                         "f"(ok ? to_tf32(v[u].x) : 0.f), "f"(ok ? to_tf32(v[u].y) : 0.f),
-                         "f"(ok ? to_tf32(v[u].z) : 0.f), "f"(ok ? to_tf32(v[u].w) : 0.f)
-                         : "memory");
-          }
-        }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_full_a + st * 8);
-      }
+    const int U = (p.HP * (p.KC >> 2) + kGroupThreads - 1) / kGroupThreads;   // <= kMaxU (plan)
+    switch (U) {
+#define AB_LOAD_CASE(K) case K: loader_loop<K>(p, ctl, a_base, grp); break;
+      AB_LOAD_CASE(1) AB_LOAD_CASE(2) AB_LOAD_CASE(3) AB_LOAD_CASE(4) AB_LOAD_CASE(5) AB_LOAD_CASE(6)
+      AB_LOAD_CASE(7) AB_LOAD_CASE(8) AB_LOAD_CASE(9) AB_LOAD_CASE(10) AB_LOAD_CASE(11)
+      AB_LOAD_CASE(12)
+#undef AB_LOAD_CASE
+      default: __trap();
     }
   } else if (warp >= kNumEpiWarps) {
    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsMma));
@@ -393,76 +547,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
   } else {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsEpi));
     // ===================== epilogue =====================
-    uint32_t acc = 0, acc_phase = 0;
-    float* my_stats = s_stats + warp * 2 * p.Cout;
-    const int row = warp * 32 + lane;
-    const int r_h = row >> 3, r_w = row & 7;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const int tw_i = tile % p.tiles_w;
-      const int th_i = (tile / p.tiles_w) % p.tiles_h;
-      const int n = tile / (p.tiles_w * p.tiles_h);
-      mbar_wait(smem_u32(&ctl->tmem_full[acc]), acc_phase);
-      tc_fence_after();
-     for (int sb_ = 0; sb_ < p.sub; ++sb_) {
-      const int gh = th_i * kTileH + r_h, gw = (tw_i * p.sub + sb_) * kTileW + r_w;
-      const bool valid = gh < p.H && gw < p.W;
-      const uint32_t t_addr =
-          tmem_base + (acc * p.sub + sb_) * p.Cout + ((uint32_t)(warp * 32) << 16);
-      const size_t pix = ((size_t)n * p.H + gh) * p.W + gw;
-      for (int c0 = 0; c0 < p.Cout; c0 += 16) {
-        float v[16];
-        tmem_ld16(t_addr + c0, v);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float x = act_f(v[i] + s_bias[c0 + i], p.act, p.alpha);
-          v[i] = valid ? x : 0.f;
-        }
-        if (valid) {
-          if (!p.out_nchw) {
-            float4* o = reinterpret_cast<float4*>(p.out + pix * p.ld_out + c0);
-            o[0] = make_float4(v[0], v[1], v[2], v[3]);
-            o[1] = make_float4(v[4], v[5], v[6], v[7]);
-            o[2] = make_float4(v[8], v[9], v[10], v[11]);
-            o[3] = make_float4(v[12], v[13], v[14], v[15]);
-          } else {
-            const size_t hw = (size_t)p.H * p.W;
-            float* o = p.out + ((size_t)n * p.Cout + c0) * hw + (size_t)gh * p.W + gw;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) o[i * hw] = v[i];
-          }
-        }
-        if (p.stats) {
-          // 32 per-thread values (16 sums, 16 sums of squares) -> transposing butterfly: 31
-          // shuffles leave in lane l the warp total of value l (instead of 32 x 5 shuffles).
-          float w[32];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            w[i] = v[i];
-            w[16 + i] = v[i] * v[i];
-          }
-#pragma unroll
-          for (int sft = 16; sft >= 1; sft >>= 1) {
-            const bool up = (lane & sft) != 0;
-#pragma unroll
-            for (int k = 0; k < sft; ++k) {
-              const float send = up ? w[k] : w[k + sft];
-              const float keep = up ? w[k + sft] : w[k];
-              w[k] = keep + __shfl_xor_sync(0xffffffffu, send, sft);
-            }
-          }
-          my_stats[(lane < 16 ? 0 : p.Cout) + c0 + (lane & 15)] += w[0];
-        }
-      }
-     }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&ctl->tmem_empty[acc]));
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
-    }
-    if (p.stats) {
-      __syncwarp();
-      for (int i = lane; i < 2 * p.Cout; i += 32) atomicAdd(p.stats + i, (double)my_stats[i]);
+    const bool fast = p.act == AB_ACT_LRELU && p.alpha >= 0.f && p.alpha <= 1.f;
+    const int ng = p.stats ? p.Cout >> 4 : 0;
+    if (fast) {
+      if (ng == 1) epilogue_loop<1, true>(p, ctl, tmem_base, s_stats, s_bias);
+      else if (ng == 2) epilogue_loop<2, true>(p, ctl, tmem_base, s_stats, s_bias);
+      else epilogue_loop<0, true>(p, ctl, tmem_base, s_stats, s_bias);
+    } else {
+      epilogue_loop<0, false>(p, ctl, tmem_base, s_stats, s_bias);
     }
   }
 
