@@ -27,6 +27,7 @@ constexpr int kTileW = 8;
 constexpr int kNumEpiWarps = 4;
 constexpr int kMmaWarp = 4;
 constexpr int kWgtWarp = 5;
+constexpr int kMmaWarp2 = 6;          // second issuing thread (resident-weight layers only)
 constexpr int kFirstLoadWarp = 8;   // warps 6,7 idle: roles are aligned to 4-warp groups (setmaxnreg)
 constexpr int kNumLoadWarps = 8;
 constexpr int kThreads = (kFirstLoadWarp + kNumLoadWarps) * 32;  // 512 -> 128 regs/thread at launch
@@ -78,7 +79,7 @@ struct __align__(8) SharedCtl {
 template <int KSTEPS, int SUB, bool RESIDENT>
 __device__ __forceinline__ void mma_issue_loop(const ConvTcParams& p, SharedCtl* ctl,
                                                uint32_t tmem_base, uint32_t a_base,
-                                               uint32_t b_base) {
+                                               uint32_t b_base, int issuer) {
   const uint32_t idesc = umma_idesc_tf32(128, p.Cout, 0, 0);
   const uint32_t piece16 = (uint32_t)p.Cout * 32 >> 4;
   const uint64_t a_tmpl = umma_desc(0, p.plane_bytes, p.TWp * 16);
@@ -93,7 +94,7 @@ __device__ __forceinline__ void mma_issue_loop(const ConvTcParams& p, SharedCtl*
   // resident weights: piece index = (chunk*KSTEPS + ks)*taps + t
   const uint32_t b_ks16 = RESIDENT ? (uint32_t)taps * piece16 : piece16;
   const uint32_t chunk_w16 = (uint32_t)(KSTEPS * taps) * piece16;
-  uint32_t sa = 0, pa = 0, sb = 0, pb = 0, acc = 0, acc_phase = 0;
+  uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
   const uint32_t bar_full_a = smem_u32(&ctl->full_a[0]), bar_empty_a = smem_u32(&ctl->empty_a[0]);
   const uint32_t bar_full_b = smem_u32(&ctl->full_b[0]), bar_empty_b = smem_u32(&ctl->empty_b[0]);
   const uint32_t bar_tfull = smem_u32(&ctl->tmem_full[0]), bar_tempty = smem_u32(&ctl->tmem_empty[0]);
@@ -101,17 +102,28 @@ __device__ __forceinline__ void mma_issue_loop(const ConvTcParams& p, SharedCtl*
     mbar_wait(smem_u32(&ctl->w_full), 0);
     tc_fence_after();
   }
+  // Resident-weight (thin, issue-bound) layers run two independent pipelines: loader group i ->
+  // issuing thread i -> TMEM accumulator i, on the CTA's tiles with local index = i (mod 2), each
+  // with its own half of the activation-stage ring (a stage barrier must have ONE consumer, or a
+  // fast consumer aliases the parity of a phase the other one has not seen yet).
+  const uint32_t n_iss = RESIDENT ? 2u : 1u;
+  const uint32_t acc = RESIDENT ? (uint32_t)issuer : 0u;
+  uint32_t acc_phase = 0, acc_s = 0;
+  const uint32_t ring_n = RESIDENT ? n_a / 2 : n_a;
+  const uint32_t ring0 = RESIDENT ? issuer * ring_n : 0u;
   const int num_tiles = p.num_tiles;
-  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-    mbar_wait(bar_tempty + acc * 8, acc_phase ^ 1);
+  const int tile_step = gridDim.x * n_iss;
+  for (int tile = blockIdx.x + issuer * gridDim.x; tile < num_tiles; tile += tile_step) {
+    const uint32_t a_ = RESIDENT ? acc : acc_s;
+    mbar_wait(bar_tempty + a_ * 8, acc_phase ^ 1);
     tc_fence_after();
-    const uint32_t d_tmem = tmem_base + acc * SUB * cout;
+    const uint32_t d_tmem = tmem_base + a_ * SUB * cout;
     uint32_t accum = 0u;
     uint32_t b_tap = b_lo0;                                        // resident: running piece
     for (uint32_t ch = 0; ch < n_chunks; ++ch) {
-      mbar_wait(bar_full_a + sa * 8, pa);
+      mbar_wait(bar_full_a + (ring0 + sa) * 8, pa);
       tc_fence_after();
-      uint32_t a_row = a_lo0 + sa * a_stage16;
+      uint32_t a_row = a_lo0 + (ring0 + sa) * a_stage16;
       if (RESIDENT) b_tap = b_lo0 + ch * chunk_w16;
       for (int ty = 0; ty < th; ++ty, a_row += dy16) {
         uint32_t a_tap = a_row;
@@ -135,12 +147,16 @@ __device__ __forceinline__ void mma_issue_loop(const ConvTcParams& p, SharedCtl*
           }
         }
       }
-      umma_commit(bar_empty_a + sa * 8);
-      if (++sa == n_a) { sa = 0; pa ^= 1; }
+      umma_commit(bar_empty_a + (ring0 + sa) * 8);
+      if (++sa == ring_n) { sa = 0; pa ^= 1; }
     }
-    umma_commit(bar_tfull + acc * 8);
-    acc ^= 1;
-    if (acc == 0) acc_phase ^= 1;
+    umma_commit(bar_tfull + a_ * 8);
+    if (RESIDENT) {
+      acc_phase ^= 1;
+    } else {
+      acc_s ^= 1;
+      if (acc_s == 0) acc_phase ^= 1;
+    }
   }
 }
 
@@ -181,12 +197,20 @@ __device__ __forceinline__ void loader_loop(const ConvTcParams& p, SharedCtl* ct
   const float inv_tpi = 1.f / (float)tpi, inv_tw = 1.f / (float)p.tiles_w;
   const int n_chunks = p.n_chunks;
   const uint32_t n_a = p.n_a;
-  // this group's chunks: the CTA's running chunk counter it = grp, grp+2, ...
-  int tile = blockIdx.x, ch = grp;
-  uint32_t st = grp % n_a, ph = ((grp / n_a) & 1) ^ 1;   // stage / empty-phase of chunk `it`
-  const uint32_t st_step = 2 % n_a, st_wrap2 = 2 / n_a;  // n_a in {2,3,4}
+  // Streamed weights: one pipeline, group g stages the chunks with (running counter & 1) == g.
+  // Resident weights (dual pipelines): group g stages every chunk of the tiles with local index
+  // = g (mod 2) into its own half of the stage ring.
+  const bool dual = p.w_resident != 0;
+  const int ch_step = dual ? 1 : 2;
+  const int tile_step = dual ? 2 * gridDim.x : gridDim.x;
+  const uint32_t ring_n = dual ? n_a / 2 : n_a;
+  const uint32_t ring0 = dual ? grp * ring_n : 0u;
+  int tile = dual ? blockIdx.x + grp * gridDim.x : blockIdx.x;
+  int ch = dual ? 0 : grp;
+  uint32_t st = dual ? 0u : grp % n_a;
+  uint32_t ph = dual ? 1u : ((grp / n_a) & 1) ^ 1;   // stage / empty-phase of the current chunk
   for (;;) {
-    while (ch >= n_chunks) { ch -= n_chunks; tile += gridDim.x; }
+    while (ch >= n_chunks) { ch -= n_chunks; tile += tile_step; }
     if (tile >= p.num_tiles) break;
     // tile -> (n, th_i, tw_i) without integer division
     int n = __float2int_rz((float)tile * inv_tpi);
@@ -272,8 +296,8 @@ __device__ __forceinline__ void loader_loop(const ConvTcParams& p, SharedCtl* ct
         v[u] = make_float4(ok ? mx : 0.f, ok ? my : 0.f, ok ? mz : 0.f, ok ? mw : 0.f);
       }
     }
-    mbar_wait(bar_empty_a + st * 8, ph);
-    const uint32_t dst = dst0 + st * p.a_stage_bytes;
+    mbar_wait(bar_empty_a + (ring0 + st) * 8, ph);
+    const uint32_t dst = dst0 + (ring0 + st) * p.a_stage_bytes;
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       asm volatile(
@@ -285,12 +309,11 @@ __device__ __forceinline__ void loader_loop(const ConvTcParams& p, SharedCtl* ct
     }
     fence_proxy_async_smem();
     __syncwarp();
-    if (lane == 0) mbar_arrive(bar_full_a + st * 8);
-    // advance to this group's next chunk (it += 2)
-    ch += 2;
-    st += st_step;
-    ph ^= st_wrap2;
-    if (st >= n_a) { st -= n_a; ph ^= 1; }
+    if (lane == 0) mbar_arrive(bar_full_a + (ring0 + st) * 8);
+    // advance to this group's next chunk
+    ch += ch_step;
+    st += ch_step;
+    while (st >= ring_n) { st -= ring_n; ph ^= 1; }
   }
 }
 
@@ -524,7 +547,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
       }
     }
     __syncwarp();
-   } else if (warp == kMmaWarp) {
+   } else if (warp == kMmaWarp || (warp == kMmaWarp2 && p.w_resident)) {
+    const int issuer = warp == kMmaWarp ? 0 : 1;
     // ===================== MMA issuer =====================
     // One elected thread issues every tcgen05.mma, so its instruction count per MMA bounds the
     // kernel for the thin layers (an M128 x N16 x K8 MMA is 8 tensor-pipe cycles).  The loop nest
@@ -532,7 +556,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
     if (elect_one()) {
       const int ksteps = p.KC >> 3;
       const bool res = p.w_resident != 0;
-#define AB_MMA_CASE(K, S, R) mma_issue_loop<K, S, R>(p, ctl, tmem_base, a_base, b_base)
+#define AB_MMA_CASE(K, S, R) mma_issue_loop<K, S, R>(p, ctl, tmem_base, a_base, b_base, issuer)
       if (p.sub == 1) {
         if (res) { if (ksteps == 4) AB_MMA_CASE(4, 1, true); else if (ksteps == 2) AB_MMA_CASE(2, 1, true); else AB_MMA_CASE(1, 1, true); }
         else     { if (ksteps == 4) AB_MMA_CASE(4, 1, false); else if (ksteps == 2) AB_MMA_CASE(2, 1, false); else AB_MMA_CASE(1, 1, false); }
@@ -683,6 +707,7 @@ static int conv_tc_plan(const ab_conv_t* d, ConvTcParams* p, int* smem_bytes) {
       if (na < 2) continue;
       p->KC = KC; p->plane_bytes = plane; p->a_stage_bytes = a_stage; p->b_stage_bytes = b_stage;
       p->n_a = na > kMaxAStages ? kMaxAStages : na;
+      if (resident) p->n_a &= ~1;   // two rings of n_a/2 stages
       p->n_b = n_b; p->sub = sub; p->w_resident = resident;
       ok = true;
     }
