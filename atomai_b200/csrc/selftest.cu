@@ -25,18 +25,31 @@ __global__ void __launch_bounds__(128, 1)
   const int tid = threadIdx.x, warp = tid >> 5;
   if (variant >= 8) {
     // ---------------- MN-major, SWIZZLE_128B_BASE32B ----------------
-    const bool swap8 = variant & 1;
-    const uint32_t shift = (variant >> 1) & 3, use_bo = (variant >> 4) & 1;
+    const bool swap8 = variant < 32 && (variant & 1);
+    const uint32_t shift = variant < 32 ? (variant >> 1) & 3 : 0u;
+    const uint32_t use_bo = variant < 32 ? (variant >> 4) & 1 : 0u;
     const uint32_t base0 = (smem_u32(smem) + 1023) & ~1023u;
     const uint32_t chunk = ((uint32_t)K + 8) * 128;               // stride between 32-wide m/n chunks
     const uint32_t lboA = (chunk + 1023) & ~1023u;
     const uint32_t a0 = base0 + shift * 128;
     const uint32_t b0 = base0 + 4 * lboA + 1024 + shift * 128;
     uint8_t* gen0 = smem - smem_u32(smem);                         // generic pointer of smem offset 0
-    for (int i = tid; i < 128 * K; i += 128) {                     // A^T[k][m]
-      const int k = i / 128, m = i % 128;
-      const uint32_t la = a0 + (m / 32) * lboA + k * 128 + (m % 32) * 4;
-      *reinterpret_cast<float*>(gen0 + swz128_32(la)) = to_tf32(A[i]);
+    // variant >= 32: "stacked taps" — A is ONE 32-channel tile X[K+16][32] (given in A) and the
+    // four 32-row chunks of the M = 128 operand are row-shifted views of it: LBO = stack * 128 B,
+    // i.e. A[m = c*32 + i][k] = X[k + c*stack][i] (what wgrad_tc uses to put the tx taps on M).
+    const uint32_t stack = variant >= 32 ? (uint32_t)(variant - 32) : 0u;
+    if (stack) {
+      for (int i = tid; i < (K + 16) * 32; i += 128) {
+        const int k = i / 32, m = i % 32;
+        const uint32_t la = a0 + k * 128 + m * 4;
+        *reinterpret_cast<float*>(gen0 + swz128_32(la)) = to_tf32(A[i]);
+      }
+    } else {
+      for (int i = tid; i < 128 * K; i += 128) {                   // A^T[k][m]
+        const int k = i / 128, m = i % 128;
+        const uint32_t la = a0 + (m / 32) * lboA + k * 128 + (m % 32) * 4;
+        *reinterpret_cast<float*>(gen0 + swz128_32(la)) = to_tf32(A[i]);
+      }
     }
     for (int i = tid; i < N * K; i += 128) {                       // B^T[k][n]
       const int k = i / N, n = i % N;
@@ -56,7 +69,7 @@ __global__ void __launch_bounds__(128, 1)
         uint32_t lbo = lboA, sbo = 512;
         if (swap8) { lbo = 512; sbo = lboA; }
         const uint32_t sa = a0 + ks * 1024, sb = b0 + ks * 1024;
-        const uint64_t ad = umma_desc_ex(sa, lbo, sbo, 1, use_bo ? (sa >> 7) & 7 : 0);
+        const uint64_t ad = umma_desc_ex(sa, stack ? stack * 128 : lbo, sbo, 1, use_bo ? (sa >> 7) & 7 : 0);
         const uint64_t bd = umma_desc_ex(sb, lbo, sbo, 1, use_bo ? (sb >> 7) & 7 : 0);
         umma_tf32(tmem_base, ad, bd, idesc, ks > 0 ? 1u : 0u);
       }

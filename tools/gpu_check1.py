@@ -124,6 +124,18 @@ def run_group(name):
                 except Exception as e:  # noqa
                     res[f"v{variant}_N{N}_K{K}"] = {"error": str(e)[:200]}
                     raise
+        for stack in (1, 2, 3):          # stacked-tap A operand (wgrad_tc): A[c*32+i][k] = X[k+c*stack][i]
+            for (N, K) in [(32, 8), (64, 32), (128, 64)]:
+                X = rnd(K + 16, 32)
+                Bt = rnd(K, N)
+                At = torch.cat([X[c * stack:c * stack + K] for c in range(4)], dim=1)   # [K][128]
+                ref = At.t() @ Bt
+                D = torch.zeros(128, N, device=dev)
+                Xin = torch.zeros(128 * K, device=dev)
+                Xin[:X.numel()] = X.reshape(-1)
+                ops.selftest_umma(Xin, Bt.contiguous(), D, N, K, 32 + stack)
+                torch.cuda.synchronize()
+                res[f"stack{stack}_N{N}_K{K}"] = {"rel": rel(D, ref)}
     elif name == "simt":
         M = ops.MATH_FP32
         conv_case("c1_1to16", M, 2, 40, 48, [1], 16)
@@ -216,6 +228,8 @@ def run_group(name):
         wgrad_case("cat_affine_pool", M, 2, 32, 32, [16, 16], 32, affine=True, pool=True)
         wgrad_case("ragged", M, 3, 37, 29, [32], 48)
         wgrad_case("dil2", M, 2, 32, 32, [64], 128, dil=2)
+        wgrad_case("1x1_40to24", M, 2, 32, 32, [40], 24, ks=1)
+        wgrad_case("cat_48_16_affine", M, 2, 40, 24, [48, 16], 20, affine=True)
     elif name == "elementwise":
         N, H, W, Cc = 3, 20, 24, 32
         a = rnd(N, Cc, H, W)
