@@ -74,6 +74,7 @@ SIGNATURES = {
     "atomai_b200_prep_weights_elems": (_i64, [_i, _i, _i, _i, _i, _i]),
     "atomai_b200_prep_weights": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "atomai_b200_conv_fwd": (_i, [C.POINTER(Conv), _vp, _vp, _vp, _i, _vp, _vp]),
+    "atomai_b200_conv_supported": (_i, [C.POINTER(Conv), _i]),
     "atomai_b200_conv_info": (_i, [C.POINTER(Conv), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
     "atomai_b200_conv_wgrad": (_i, [C.POINTER(Conv), _vp, _i, _vp, _vp]),
     "atomai_b200_bn_finalize": (_i, [_vp, _i, _d, _vp, _vp, _vp, _vp, _f, _f, _i, _vp, _vp, _vp,

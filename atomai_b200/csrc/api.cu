@@ -114,6 +114,11 @@ int atomai_b200_conv_fwd(const ab_conv_t* d, const float* w_prepped, const float
   return ab_conv_simt_fwd(d, w_prepped, bias, y, ld_y, stats, (cudaStream_t)stream);
 }
 
+int atomai_b200_conv_supported(const ab_conv_t* d, int which) {
+  if (!d) return 0;
+  return which == 0 ? ab_conv_tc_supported(d) : ab_wgrad_tc_supported(d);
+}
+
 int atomai_b200_conv_info(const ab_conv_t* d, int* grid, int* block, int* smem_bytes) {
   AB_CHECK(d && grid && block && smem_bytes, "conv_info: null pointer");
   AB_CHECK(d->math == AB_MATH_TF32 && ab_conv_tc_supported(d), "conv_info: tcgen05 path only");

@@ -50,7 +50,7 @@ struct WgradTcParams {
   int ranges;            // pixel-tile ranges per (cc, co_block)
   int TWp, THp, HP;
   int x_chunk;           // taps_w == 1: bytes between 32-channel chunks of the x tile
-  int d_bytes, stage_bytes;
+  int x_bytes, stage_bytes;
   int tmem_cols;
 };
 
@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const WgradTcPara
     // a thread's channel piece is the same for every element when P divides the group size:
     // hoist the source selection and the BN affine of the x operand
     const bool x_const = (kGroupThreads % PX) == 0;
-    const uint32_t d0 = base + grp * p.stage_bytes, x0 = d0 + p.d_bytes;
+    const uint32_t x0 = base + grp * p.stage_bytes, d0 = x0 + p.x_bytes;
     uint32_t use = 0;
     for (int tile = t_begin + grp; tile < t_end; tile += 2, ++use) {
       const int n = (int)fdiv(tile, tpi, mulTpi);
@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const WgradTcPara
         const uint32_t st = it & 1;
         mbar_wait(smem_u32(&ctl->full[st]), (it >> 1) & 1);
         tc_fence_after();
-        const uint32_t d0 = base + st * p.stage_bytes, x0 = d0 + p.d_bytes;
+        const uint32_t x0 = base + st * p.stage_bytes, d0 = x0 + p.x_bytes;
         uint32_t a_ty = (uint32_t)a_tmpl + (x0 >> 4);
         const uint32_t b0 = (uint32_t)b_tmpl + (d0 >> 4);
         uint32_t dcol = tmem_base;
@@ -329,21 +329,25 @@ int wgrad_plan(const ab_conv_t* d, WgradTcParams* p, int* smem_bytes) {
   p->TWp = kTileW + d->dil * (d->ks_w - 1);
   p->HP = p->THp * p->TWp;
   const bool stacked = d->ks_w > 1;
-  p->cib = stacked ? 32 : 128;
   p->co_blocks = (d->Cout + 127) / 128;
   const int co_max = d->Cout < 128 ? d->Cout : 128;
   const int npad = (co_max + 31) & ~31;
-  p->d_bytes = (npad / 32) * kChunk;
-  int x_bytes;
+  const int d_bytes = (npad / 32) * kChunk;
+  // A stage is [x tile][dy tile]: the don't-care rows of the M = 128 operand (chunk 3 of a 3-wide
+  // kernel, chunks >= cib/32 of a 1x1 kernel) then alias the dy tile — finite and in bounds.
   if (stacked) {
-    // + the don't-care rows chunk 3 / the last taps can touch behind the halo tile
+    p->cib = 32;
     p->x_chunk = 0;
-    x_bytes = ((p->HP + 3 * d->dil + 8) * 128 + 1023) & ~1023;
+    p->x_bytes = (p->HP * 128 + 1023) & ~1023;
+    AB_CHECK(3 * d->dil * 128 + 1024 <= d_bytes, "wgrad_tc: dilation %d too large", d->dil);
   } else {
     p->x_chunk = (p->HP * 128 + 1023) & ~1023;
-    x_bytes = 4 * p->x_chunk;
+    p->cib = 128;
+    if (kStages * (4 * p->x_chunk + d_bytes) + 2048 > 225 * 1024) p->cib = 64;
+    p->x_bytes = (p->cib / 32) * p->x_chunk;
+    AB_CHECK(p->cib == 128 || 2 * p->x_chunk <= d_bytes, "wgrad_tc: no shared-memory plan");
   }
-  p->stage_bytes = p->d_bytes + x_bytes;
+  p->stage_bytes = p->x_bytes + d_bytes;
   *smem_bytes = kStages * p->stage_bytes + 128 + 1024;
   AB_CHECK(*smem_bytes <= 225 * 1024, "wgrad_tc: halo tile too large for shared memory (dil=%d)",
            d->dil);

@@ -227,13 +227,11 @@ class Tape:
         # weight gradient
         wt = r.conv.weight
         srcs_s = [s.source() for s in r.srcs]
-        wmath = r.math
-        if wmath == MATH_TF32 and not (_MATH["wgrad_tc"] and
-                                       ops.wgrad_tc_supported(srcs_s, cout, r.ks, r.dil)):
-            wmath = MATH_FP32
         dw = torch.zeros((wt.shape[0], wt.shape[1], r.ks[0], r.ks[1]), device=dev,
                          dtype=torch.float32)
-        dsc = ops.conv_desc(srcs_s, n, h, w, cout, r.ks, r.dil, 1.0, wmath)
+        dsc = ops.conv_desc(srcs_s, n, h, w, cout, r.ks, r.dil, 1.0, r.math)
+        if r.math == MATH_TF32 and not (_MATH["wgrad_tc"] and ops.conv_supported(dsc, 1)):
+            dsc.math = MATH_FP32
         ops.conv_wgrad(dsc, dpre, dw)
         self._add_pgrad(wt, dw)
         # data gradient

@@ -79,10 +79,10 @@ def tc_supported(srcs: Sequence[Source], Cout: int) -> bool:
             and ctot % 8 == 0 and Cout % 16 == 0 and 16 <= Cout <= 256)
 
 
-def wgrad_tc_supported(srcs: Sequence[Source], Cout: int, ks, dil) -> bool:
-    ctot = sum(s.C for s in srcs)
-    return (all(s.C % 4 == 0 and _ld(s.t) % 4 == 0 and s.t.data_ptr() % 16 == 0 for s in srcs)
-            and ctot % 4 == 0 and Cout % 4 == 0 and (dil <= 2 or max(ks) == 1))
+def conv_supported(d: _C.Conv, which: int = 0) -> bool:
+    """Does the tcgen05 kernel take this descriptor?  which: 0 forward/dgrad, 1 weight gradient
+    (atomai_b200_conv_supported — the single source of truth, no Python mirror)."""
+    return bool(lib().atomai_b200_conv_supported(C.byref(d), which))
 
 
 def prep_weights(w_oihw: torch.Tensor, mode: int, math: int) -> torch.Tensor:

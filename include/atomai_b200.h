@@ -86,6 +86,10 @@ int atomai_b200_prep_weights(const float* w_oihw, int Cout, int Cin, int ks_h, i
  * :130-132 (UpsampleBlock 1x1), atomai/nets/fcnn.py:115 (px head). */
 int atomai_b200_conv_fwd(const ab_conv_t* d, const float* w_prepped, const float* bias,
                          float* y, int ld_y, double* stats, void* stream);
+/* 1 if the tcgen05 (AB_MATH_TF32) kernel takes this descriptor: which = 0 forward / dgrad
+ * (atomai_b200_conv_fwd), 1 weight gradient (atomai_b200_conv_wgrad).  Callers fall back to
+ * AB_MATH_FP32 (exact SIMT kernels) for the rest — thin channel counts, odd strides. */
+int atomai_b200_conv_supported(const ab_conv_t* d, int which);
 /* scratch/occupancy query so the caller can report launch geometry */
 int atomai_b200_conv_info(const ab_conv_t* d, int* grid, int* block, int* smem_bytes);
 

@@ -155,6 +155,11 @@ def run_group(name):
         conv_case("128to256", M, 1, 16, 16, [128], 256)
         conv_case("1x1_128to64", M, 2, 32, 32, [128], 64, ks=1, lrelu=1.0)
         conv_case("ragged_37x29", M, 3, 37, 29, [32], 32)
+        conv_case("big_32to16", M, 8, 256, 256, [32], 16, affine=True)
+        conv_case("big_16to32", M, 8, 256, 256, [16], 32, affine=True)
+        conv_case("big_64to64", M, 8, 128, 128, [64], 64, affine=True)
+        conv_case("big_128to128", M, 8, 64, 64, [128], 128, affine=True)
+        conv_case("big_cat", M, 8, 128, 128, [64, 64], 64, affine=True)
     elif name == "tc_fused":
         M = ops.MATH_TF32
         conv_case("affine", M, 2, 32, 32, [32], 32, affine=True)

@@ -18,9 +18,14 @@ for MODE in ("fp32", "tf32"):
     ab.set_math(MODE)
     net, sd, cfg, x, y, gold = build_case(name)
     net = net.cuda().train(); x = x.cuda()
-    with torch.no_grad():
+    if len(sys.argv) > 2 and sys.argv[2] == "grad":
         out = net(x)
+    else:
+        with torch.no_grad():
+            out = net(x)
     torch.cuda.synchronize()
+    rec.setdefault(MODE + "_out", out.detach().clone())
+print("final rel", float((rec["fp32_out"] - rec["tf32_out"]).abs().max() / rec["fp32_out"].abs().max()))
 for i, (a, b) in enumerate(zip(rec["fp32"], rec["tf32"])):
     ra = float((a[0] - b[0]).abs().max() / a[0].abs().max())
     rs = float((a[1] - b[1]).abs().max() / a[1].abs().max()) if a[1] is not None else -1
