@@ -6,7 +6,8 @@ import torch
 from atomai_b200 import ops
 from atomai_b200.ops import Source
 shapes = {"c6": (32, 512, 32, 16), "bn3": (32, 64, 128, 128), "c5": (32, 256, 64, 32)}
-which = sys.argv[1:] or ["c6", "bn3"]
+which = [a for a in sys.argv[1:] if a != "wgrad"] or ["c6", "bn3"]
+do_wgrad = "wgrad" in sys.argv[1:]
 for tag in which:
     N, hh, cin, cout = shapes[tag]
     dev = "cuda"
@@ -17,5 +18,10 @@ for tag in which:
     wp = ops.prep_weights(w, ops.WMODE_FWD, ops.MATH_TF32)
     for _ in range(3):
         ops.conv_fwd(d, wp, b, out, st)
+    if do_wgrad:
+        dy = torch.randn(N, hh, hh, cout, device=dev)
+        dw = torch.zeros(cout, cin, 3, 3, device=dev)
+        for _ in range(3):
+            ops.conv_wgrad(d, dy, dw)
     torch.cuda.synchronize()
 print("done")
