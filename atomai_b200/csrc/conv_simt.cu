@@ -159,11 +159,14 @@ __global__ void __launch_bounds__(256) conv_pix_kernel(const ConvSimtParams p, i
   for (int k = 0; k < CO; ++k) { ssum[k] = 0.f; ssq[k] = 0.f; }
   const int64_t npix = (int64_t)p.N * p.H * p.W;
   const int ph = p.dil * (p.th >> 1), pw = p.dil * (p.tw >> 1);
+  const uint32_t uW = p.W, uHW = (uint32_t)p.H * p.W;      // npix < 2^32 (checked by the launcher)
   for (int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pix < npix;
        pix += (int64_t)gridDim.x * blockDim.x) {
-    const int w = (int)(pix % p.W);
-    const int h = (int)((pix / p.W) % p.H);
-    const int n = (int)(pix / ((int64_t)p.W * p.H));
+    const uint32_t up = (uint32_t)pix;                     // 32-bit divisions: ~20 instrs, not ~150
+    const int n = (int)(up / uHW);
+    const uint32_t rem = up - (uint32_t)n * uHW;
+    const int h = (int)(rem / uW);
+    const int w = (int)(rem - (uint32_t)h * uW);
     float acc[CO];
 #pragma unroll
     for (int k = 0; k < CO; ++k) acc[k] = bias[k];
@@ -233,6 +236,7 @@ int launch_conv_pix(const ConvSimtParams& p, cudaStream_t stream) {
   const int taps = p.th * p.tw, Cin = p.S.Ctot;
   const size_t smem = (size_t)taps * Cin * CO * sizeof(float);
   const int64_t npix = (int64_t)p.N * p.H * p.W;
+  AB_CHECK(npix < (1ll << 32), "conv_pix: too many pixels");
   int vec = (Cin % 4 == 0);
   for (int i = 0; i < p.S.nsrc; ++i)
     if (p.S.s[i].C % 4 != 0 || p.S.s[i].ld % 4 != 0 || ((uintptr_t)p.S.s[i].ptr & 15)) vec = 0;
@@ -332,70 +336,101 @@ __global__ void __launch_bounds__(G_THREADS) conv_simt_wgrad_kernel(const WgradS
 // above would waste > 95 % of its FMAs, so here every thread walks pixels and keeps the whole
 // CO x CI x TW slice of dW in registers; one warp-shuffle reduction + atomics per CTA at the end.
 // grid: (pixel ranges, tap rows (ks_h), co-groups * ci-groups).
-template <int CO, int CI, int TW>
+template <int CO, int CI, int TH, int TW>
 __global__ void __launch_bounds__(256) wgrad_small_kernel(const WgradSimtParams p, int co_groups) {
-  const int ty = blockIdx.y;
   const int cog = blockIdx.z % co_groups, cig = blockIdx.z / co_groups;
   const int co0 = cog * CO, ci0 = cig * CI;
   const int Cin = p.S.Ctot;
-  const int dh = (ty - (p.th >> 1)) * p.dil;
-  float acc[CO][CI][TW];
+  float acc[CO][CI][TH * TW];
 #pragma unroll
   for (int a = 0; a < CO; ++a)
 #pragma unroll
     for (int b = 0; b < CI; ++b)
 #pragma unroll
-      for (int t = 0; t < TW; ++t) acc[a][b][t] = 0.f;
+      for (int t = 0; t < TH * TW; ++t) acc[a][b][t] = 0.f;
+  const uint32_t uW = p.W, uHW = (uint32_t)p.H * p.W;      // npix < 2^32 (checked by the launcher)
+  // float4 loads when the channel group is whole, aligned and inside one source
+  const bool dy_vec = CO % 4 == 0 && co0 + CO <= p.Cout && (p.ld_dy & 3) == 0 &&
+                      ((uintptr_t)(p.dy + co0) & 15) == 0;
+  const bool x_vec = CI % 4 == 0 && ci0 + CI <= Cin && p.S.nsrc == 1 && (p.S.s[0].ld & 3) == 0 &&
+                     ((uintptr_t)p.S.s[0].ptr & 15) == 0 && (p.S.s[0].C & 3) == 0;
   for (int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pix < p.npix;
        pix += (int64_t)gridDim.x * blockDim.x) {
-    const int w = (int)(pix % p.W);
-    const int h = (int)((pix / p.W) % p.H);
-    const int n = (int)(pix / ((int64_t)p.W * p.H));
+    const uint32_t up = (uint32_t)pix;
+    const int n = (int)(up / uHW);
+    const uint32_t rem = up - (uint32_t)n * uHW;
+    const int h = (int)(rem / uW);
+    const int w = (int)(rem - (uint32_t)h * uW);
     float d[CO];
+    if (dy_vec) {
 #pragma unroll
-    for (int a = 0; a < CO; ++a)
-      d[a] = (co0 + a < p.Cout) ? __ldg(p.dy + pix * p.ld_dy + co0 + a) : 0.f;
+      for (int a = 0; a < CO; a += 4) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(p.dy + pix * p.ld_dy + co0 + a));
+        d[a] = v.x; d[a + 1] = v.y; d[a + 2] = v.z; d[a + 3] = v.w;
+      }
+    } else {
 #pragma unroll
-    for (int t = 0; t < TW; ++t) {
-      const int dw_ = (t - (p.tw >> 1)) * p.dil;
+      for (int a = 0; a < CO; ++a)
+        d[a] = (co0 + a < p.Cout) ? __ldg(p.dy + pix * p.ld_dy + co0 + a) : 0.f;
+    }
 #pragma unroll
-      for (int b = 0; b < CI; ++b) {
-        const float x = (ci0 + b < Cin) ? load_src1(p.S, n, h + dh, w + dw_, p.H, p.W, ci0 + b) : 0.f;
+    for (int ty = 0; ty < TH; ++ty) {
+      const int hh = h + (ty - (TH >> 1)) * p.dil;
 #pragma unroll
-        for (int a = 0; a < CO; ++a) acc[a][b][t] = fmaf(d[a], x, acc[a][b][t]);
+      for (int tx = 0; tx < TW; ++tx) {
+        const int ww = w + (tx - (TW >> 1)) * p.dil;
+        float x[CI];
+        if (x_vec) {
+#pragma unroll
+          for (int b = 0; b < CI; b += 4) {
+            const float4 v = load_src4(p.S, n, hh, ww, p.H, p.W, ci0 + b);
+            x[b] = v.x; x[b + 1] = v.y; x[b + 2] = v.z; x[b + 3] = v.w;
+          }
+        } else {
+#pragma unroll
+          for (int b = 0; b < CI; ++b)
+            x[b] = (ci0 + b < Cin) ? load_src1(p.S, n, hh, ww, p.H, p.W, ci0 + b) : 0.f;
+        }
+#pragma unroll
+        for (int b = 0; b < CI; ++b)
+#pragma unroll
+          for (int a = 0; a < CO; ++a)
+            acc[a][b][ty * TW + tx] = fmaf(d[a], x[b], acc[a][b][ty * TW + tx]);
       }
     }
   }
-  __shared__ float s_acc[CO * CI * TW];
-  for (int i = threadIdx.x; i < CO * CI * TW; i += blockDim.x) s_acc[i] = 0.f;
+  constexpr int NA = CO * CI * TH * TW;
+  __shared__ float s_acc[NA];
+  for (int i = threadIdx.x; i < NA; i += blockDim.x) s_acc[i] = 0.f;
   __syncthreads();
 #pragma unroll
   for (int a = 0; a < CO; ++a)
 #pragma unroll
     for (int b = 0; b < CI; ++b)
 #pragma unroll
-      for (int t = 0; t < TW; ++t) {
+      for (int t = 0; t < TH * TW; ++t) {
         const float v = warp_sum(acc[a][b][t]);
-        if ((threadIdx.x & 31) == 0) atomicAdd(&s_acc[(a * CI + b) * TW + t], v);
+        if ((threadIdx.x & 31) == 0) atomicAdd(&s_acc[(a * CI + b) * (TH * TW) + t], v);
       }
   __syncthreads();
-  const int taps = p.th * p.tw;
-  for (int i = threadIdx.x; i < CO * CI * TW; i += blockDim.x) {
-    const int t = i % TW, b = (i / TW) % CI, a = i / (TW * CI);
+  for (int i = threadIdx.x; i < NA; i += blockDim.x) {
+    const int t = i % (TH * TW), b = (i / (TH * TW)) % CI, a = i / (TH * TW * CI);
     if (co0 + a < p.Cout && ci0 + b < Cin)
-      atomicAdd(p.dw + ((size_t)(co0 + a) * Cin + ci0 + b) * taps + ty * p.tw + t, s_acc[i]);
+      atomicAdd(p.dw + ((size_t)(co0 + a) * Cin + ci0 + b) * (TH * TW) + t, s_acc[i]);
   }
 }
 
-template <int CO, int CI, int TW>
+template <int CO, int CI, int TH, int TW>
 int launch_wgrad_small(const WgradSimtParams& p, cudaStream_t stream) {
+  AB_CHECK(p.npix < (1ll << 32), "wgrad_small: too many pixels");
+  AB_CHECK(p.th == TH && p.tw == TW, "wgrad_small: kernel %dx%d != %dx%d", p.th, p.tw, TH, TW);
   const int co_groups = (p.Cout + CO - 1) / CO, ci_groups = (p.S.Ctot + CI - 1) / CI;
   int64_t bx = (p.npix + 256 * 16 - 1) / (256 * 16);
   const int64_t cap = (int64_t)ab_num_sms() * 4;
   if (bx > cap) bx = cap;
   if (bx < 1) bx = 1;
-  dim3 grid((unsigned)bx, p.th, co_groups * ci_groups);
-  wgrad_small_kernel<CO, CI, TW><<<grid, 256, 0, stream>>>(p, co_groups);
+  dim3 grid((unsigned)bx, 1, co_groups * ci_groups);
+  wgrad_small_kernel<CO, CI, TH, TW><<<grid, 256, 0, stream>>>(p, co_groups);
   AB_LAUNCH_CHECK();
   return 0;
 }
@@ -482,10 +517,12 @@ int ab_conv_simt_wgrad(const ab_conv_t* d, const float* dy, int ld_dy, float* dw
   p.co_tiles = (d->Cout + G_CT - 1) / G_CT;
   p.ci_tiles = (p.S.Ctot + G_CT - 1) / G_CT;
   p.px_per_cta = 0;
-  if (p.S.Ctot <= 2 && d->ks_w == 3) return launch_wgrad_small<16, 1, 3>(p, stream);
-  if (p.S.Ctot <= 2 && d->ks_w == 1) return launch_wgrad_small<16, 2, 1>(p, stream);
-  if (d->Cout <= 4 && d->ks_w == 1) return launch_wgrad_small<4, 16, 1>(p, stream);
-  if (d->Cout <= 4 && d->ks_w == 3) return launch_wgrad_small<4, 4, 3>(p, stream);
+  if (p.S.Ctot <= 2 && d->ks_w == 3 && d->ks_h == 3) return launch_wgrad_small<8, 1, 3, 3>(p, stream);
+  if (p.S.Ctot <= 2 && d->ks_w == 3 && d->ks_h == 1) return launch_wgrad_small<16, 1, 1, 3>(p, stream);
+  if (p.S.Ctot <= 2 && d->ks_w == 1 && d->ks_h == 1) return launch_wgrad_small<16, 2, 1, 1>(p, stream);
+  if (d->Cout <= 4 && d->ks_w == 1 && d->ks_h == 1) return launch_wgrad_small<4, 16, 1, 1>(p, stream);
+  if (d->Cout <= 4 && d->ks_w == 3 && d->ks_h == 3) return launch_wgrad_small<4, 4, 3, 3>(p, stream);
+  if (d->Cout <= 4 && d->ks_w == 3 && d->ks_h == 1) return launch_wgrad_small<4, 4, 1, 3>(p, stream);
   const int taps = d->ks_h * d->ks_w;
   const int64_t per_range_ctas = (int64_t)taps * p.co_tiles * p.ci_tiles;
   int64_t ranges = (4ll * ab_num_sms() + per_range_ctas - 1) / per_range_ctas;  // ~4 waves

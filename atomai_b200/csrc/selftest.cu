@@ -177,6 +177,67 @@ __global__ void __launch_bounds__(128, 1)
   }
 }
 
+
+// Issue-rate probe: `issuers` elected threads (one per warp) each issue `iters` back-to-back
+// tcgen05.mma (M = 128, N, K = 8, TF32) on resident shared-memory operands and commit; reports
+// the elapsed SM clocks.  layout 0 = K-major no-swizzle (conv_tc), 1 = MN-major SW128_32B
+// (wgrad_tc).  Used to place the thin-layer floor (shared-memory operand reads) in DESIGN.md.
+__global__ void __launch_bounds__(128, 1)
+    umma_rate_kernel(int N, int layout, int issuers, int iters, int unroll_b, long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar[4];
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t base0 = (smem_u32(smem) + 1023) & ~1023u;
+  for (int i = tid; i < 96 * 1024 / 16; i += 128)
+    asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(base0 + i * 16), "r"(0) : "memory");
+  if (tid == 0) {
+    for (int i = 0; i < 4; ++i) mbar_init(smem_u32(&bar[i]), 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(smem_u32(&tmem_base_s), 512);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  long long t0 = 0, t1 = 0;
+  if (warp < issuers) {
+    if (elect_one()) {
+      const uint32_t idesc = umma_idesc_tf32(128, N, layout, layout);
+      uint64_t a_t, b_t;
+      if (layout == 0) {
+        a_t = umma_desc(base0, 180 * 16 + 16, 18 * 16);          // halo-tile style planes
+        b_t = umma_desc(base0 + 48 * 1024, N * 16, 128);
+      } else {
+        a_t = umma_desc_ex(base0, 128, 512, 1, 0);
+        b_t = umma_desc_ex(base0 + 48 * 1024, 2048, 512, 1, 0);   // overlapping chunks: timing only
+      }
+      const uint32_t a_hi = (uint32_t)(a_t >> 32), b_hi = (uint32_t)(b_t >> 32);
+      uint32_t a_lo = (uint32_t)a_t, b_lo = (uint32_t)b_t;
+      const uint32_t d = tmem_base + warp * 128;
+      t0 = clock64();
+      for (int i = 0; i < iters; i += 4) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          // step the start addresses like the kernels do (16 B: next pixel / 128 B: next row)
+          const uint32_t stp = layout == 0 ? k : 8 * k;
+          umma_tf32_lh(d, a_lo + stp, a_hi, b_lo + (unroll_b ? stp : 0), b_hi, idesc, 1u);
+        }
+      }
+      umma_commit(smem_u32(&bar[warp]));
+      t1 = clock64();
+      out[warp * 2] = t1 - t0;                                    // issue time
+    }
+    __syncwarp();
+    mbar_wait(smem_u32(&bar[warp]), 0);
+    if ((tid & 31) == 0) out[warp * 2 + 1] = clock64() - t0;      // until the last MMA retired
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
 }  // namespace
 
 extern "C" int atomai_b200_selftest_umma(const float* A, const float* B, float* D, int N, int K,
@@ -188,6 +249,17 @@ extern "C" int atomai_b200_selftest_umma(const float* A, const float* B, float* 
   AB_CUDA(cudaFuncSetAttribute(selftest_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                smem));
   selftest_umma_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(A, B, D, N, K, variant);
+  AB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int atomai_b200_umma_rate(int N, int layout, int issuers, int iters, long long* out,
+                                     void* stream) {
+  AB_CHECK(N % 16 == 0 && N >= 16 && N <= 128 && issuers >= 1 && issuers <= 4 && iters % 4 == 0,
+           "umma_rate: bad arguments");
+  const int smem = 100 * 1024;
+  AB_CUDA(cudaFuncSetAttribute(umma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  umma_rate_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(N, layout, issuers, iters, 1, out);
   AB_LAUNCH_CHECK();
   return 0;
 }

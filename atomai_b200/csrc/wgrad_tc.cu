@@ -20,8 +20,9 @@
 //        taps_w == 1: chunk c = input channels 32c..32c+31 (LBO = chunk stride), CTA owns 128 ci.
 // A CTA owns one input-channel block, one block of <= 128 output channels and a contiguous range
 // of pixel tiles; its taps_h x N accumulators stay in TMEM for the whole kernel and are flushed
-// once, with atomics, into dW (OIHW).  Warp roles: 0-3 epilogue, 4 MMA issue, 5 TMEM alloc, 8-15
-// loaders (two groups of 4 warps, group g owns stage g; setmaxnreg moves registers to them).
+// once, with atomics, into dW (OIHW).  Warp roles: 4 MMA issue, 5 TMEM alloc, 8-11 / 12-15 / 0-3
+// three loader groups feeding a ring of shared-memory stages (setmaxnreg moves registers to
+// them); warps 0-3 also flush the accumulators at the end.
 //
 // Replaces autograd's cuDNN bwd-filter behind loss.backward(), atomai/trainers/trainer.py:206.
 #include "common.cuh"
@@ -30,10 +31,10 @@ namespace {
 
 constexpr int kTileH = 16, kTileW = 8;
 constexpr int kNumEpiWarps = 4, kMmaWarp = 4, kAllocWarp = 5, kFirstLoadWarp = 8;
-constexpr int kNumLoadWarps = 8, kGroupThreads = 128, kB = 8;
-constexpr int kThreads = (kFirstLoadWarp + kNumLoadWarps) * 32;   // 512: 4 warpgroups
-constexpr int kRegsEpi = 80, kRegsMma = 48, kRegsLoad = 192;      // setmaxnreg re-balancing
-constexpr int kStages = 2;
+constexpr int kGroupThreads = 128;
+constexpr int kThreads = 512;                                     // 4 warpgroups
+constexpr int kRegsMma = 48, kRegsLoad = 152;                    // setmaxnreg re-balancing (3 x 152 + 48)
+constexpr int kMaxStages = 6;
 constexpr int kChunk = 128 * 128;             // bytes of one [128 px][32 ch] chunk of the dy tile
 
 struct WgradTcParams {
@@ -51,11 +52,14 @@ struct WgradTcParams {
   int TWp, THp, HP;
   int x_chunk;           // taps_w == 1: bytes between 32-channel chunks of the x tile
   int x_bytes, stage_bytes;
+  int n_stages;          // shared-memory ring depth (2..kMaxStages)
+  int fs;                // "fully stacked": Cout <= 32, the kernel rows ride on N (one MMA / halo row)
+  int dpad;              // fs: zero rows in front of / behind the dy tile = (taps_h - 1) * dil
   int tmem_cols;
 };
 
 struct __align__(8) Ctl {
-  uint64_t full[kStages], empty[kStages], done;
+  uint64_t full[kMaxStages], empty[kMaxStages], done;
   uint32_t tmem_base, pad;
 };
 
@@ -75,10 +79,129 @@ __host__ __device__ inline uint32_t fdiv_mul(uint32_t P) {
   return P <= 1 ? 0u : (uint32_t)(((1ull << 32) + P - 1) / P);
 }
 
+constexpr int kGroups = 3;                    // loader groups (tiles round-robin)
+constexpr int kJB = 8;                        // 16 B channel pieces per pixel per load batch
+
+// One loader group (128 threads), thread = pixel.  Per tile a thread stages the dy pixel `gt`
+// and the x-halo pixels gt, gt+128, ...: one base address per pixel, then the pixel's channel
+// pieces are 16-byte loads at immediate offsets (no per-element index arithmetic), normalised
+// (BN affine from the shared-memory copy), rounded to TF32 and stored into the
+// SWIZZLE_128B_BASE32B tile layout (chunk = piece / 8, row = pixel, 16 B slot = piece % 8 XOR-ed
+// with the row's swizzle phase).
+__device__ __forceinline__ void wgrad_loader(const WgradTcParams& p, Ctl* ctl, uint32_t base,
+                                             const float4* s_aff, int grp, int gt, int t_begin,
+                                             int t_end, int co0, int ci0, int PD, int PX) {
+  const int lane = threadIdx.x & 31;
+  const bool stacked = p.taps_w > 1;
+  const int H = p.H, W = p.W, HP = p.HP;
+  const int tpi = p.tiles_w * p.tiles_h;
+  const uint32_t mulTpi = fdiv_mul(tpi), mulTw = fdiv_mul(p.tiles_w), mulT = fdiv_mul(p.TWp);
+  const uint32_t S = p.n_stages;
+  // a ring slot must have been consumed before a group can be two tiles ahead of it: with fewer
+  // slots than groups the third group sits out (parity aliasing otherwise)
+  const int n_groups = S >= (uint32_t)kGroups ? kGroups : 2;
+  if (grp >= n_groups) return;
+  // source split of the (possibly concatenated) x operand, in 16 B pieces of this channel block
+  const int c_split = p.S.nsrc > 1 ? p.S.s[0].C : (1 << 30);
+  const bool any_pool = p.S.s[0].pool || (p.S.nsrc > 1 && p.S.s[1].pool);
+  const bool has_aff = p.S.s[0].scale != nullptr || (p.S.nsrc > 1 && p.S.s[1].scale != nullptr);
+  // this thread's halo pixels (up to 5 slots of 128: dilated kernels), row/col within the halo
+  const uint32_t d_rel = p.x_bytes + (p.fs ? p.dpad * 1024 : 0);   // dy tile within a stage
+  const uint32_t d_row = d_rel + gt * 128, d_sw = (uint32_t)(gt & 3) << 5;
+  const int d_r = gt >> 3, d_c = gt & 7;
+  uint32_t st = grp % S, ph = ((grp / S) & 1) ^ 1;     // ring slot / empty-phase of this tile
+  for (int tile = t_begin + grp; tile < t_end; tile += n_groups) {
+    const uint32_t x0 = base + st * p.stage_bytes;
+    const int n = (int)fdiv(tile, tpi, mulTpi);
+    const int rem = tile - n * tpi;
+    const int th_i = (int)fdiv(rem, p.tiles_w, mulTw);
+    const int tw_i = rem - th_i * p.tiles_w;
+    const int h0 = th_i * kTileH, w0 = tw_i * kTileW;
+    const int h_org = h0 - p.dil * (p.taps_h >> 1), w_org = w0 - p.dil * (p.taps_w >> 1);
+    const size_t img = (size_t)n * H;
+    mbar_wait(smem_u32(&ctl->empty[st]), ph);
+    // ---------------- x halo pixels
+    for (int q = gt; q < HP; q += kGroupThreads) {
+      const uint32_t hh = fdiv(q, p.TWp, mulT), ww = q - hh * p.TWp;
+      const int gh = h_org + (int)hh, gw = w_org + (int)ww;
+      const bool ok = (unsigned)gh < (unsigned)H && (unsigned)gw < (unsigned)W;
+      const uint32_t row = x0 + q * 128, sw = (uint32_t)(q & 3) << 5;
+      if (!any_pool) {
+        const int ghc = min(max(gh, 0), H - 1), gwc = min(max(gw, 0), W - 1);
+        const size_t pixi = (img + ghc) * W + gwc;
+        const float* b0 = p.S.s[0].ptr + pixi * p.S.s[0].ld + ci0;
+        const float* b1 = p.S.nsrc > 1 ? p.S.s[1].ptr + pixi * p.S.s[1].ld + (ci0 - c_split) : b0;
+        const uint32_t msk = ok ? 0xFFFFFFFFu : 0u;
+        for (int jb = 0; jb < PX; jb += kJB) {
+          float4 v[kJB];
+#pragma unroll
+          for (int k = 0; k < kJB; ++k) {
+            const int j = jb + k;
+            if (j < PX) {
+              const float* src = (ci0 + j * 4 < c_split) ? b0 : b1;
+              v[k] = __ldg(reinterpret_cast<const float4*>(src + j * 4));
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < kJB; ++k) {
+            const int j = jb + k;
+            if (j < PX) {
+              float4 x = v[k];
+              if (has_aff) {
+                const float4 sc = s_aff[2 * j], sh = s_aff[2 * j + 1];
+                x.x = fmaf(x.x, sc.x, sh.x); x.y = fmaf(x.y, sc.y, sh.y);
+                x.z = fmaf(x.z, sc.z, sh.z); x.w = fmaf(x.w, sc.w, sh.w);
+              }
+              const uint32_t dst = (stacked ? row : row + (j >> 3) * p.x_chunk) +
+                                   (((uint32_t)(j & 7) << 4) ^ sw);
+              sts128u(dst, tf32b(x.x) & msk, tf32b(x.y) & msk, tf32b(x.z) & msk, tf32b(x.w) & msk);
+            }
+          }
+        }
+      } else {
+        // pooled source(s): the generic normalise / max-pool / pad loader, piece by piece
+        for (int j = 0; j < PX; ++j) {
+          const float4 x = load_src4(p.S, n, gh, gw, H, W, ci0 + j * 4);
+          const uint32_t dst = (stacked ? row : row + (j >> 3) * p.x_chunk) +
+                               (((uint32_t)(j & 7) << 4) ^ sw);
+          sts128u(dst, tf32b(x.x), tf32b(x.y), tf32b(x.z), tf32b(x.w));
+        }
+      }
+    }
+    // ---------------- dy pixel gt of the 16 x 8 tile
+    {
+      const int gh = h0 + d_r, gw = w0 + d_c;
+      const bool ok = gh < H && gw < W;
+      const uint32_t msk = ok ? 0xFFFFFFFFu : 0u;
+      const float* db = p.dy + ((img + min(gh, H - 1)) * W + min(gw, W - 1)) * p.ld_dy + co0;
+      for (int jb = 0; jb < PD; jb += kJB) {
+        float4 v[kJB];
+#pragma unroll
+        for (int k = 0; k < kJB; ++k)
+          if (jb + k < PD) v[k] = __ldg(reinterpret_cast<const float4*>(db + (jb + k) * 4));
+#pragma unroll
+        for (int k = 0; k < kJB; ++k) {
+          const int j = jb + k;
+          if (j < PD)
+            sts128u(x0 + d_row + (j >> 3) * kChunk + (((uint32_t)(j & 7) << 4) ^ d_sw),
+                    tf32b(v[k].x) & msk, tf32b(v[k].y) & msk, tf32b(v[k].z) & msk,
+                    tf32b(v[k].w) & msk);
+        }
+      }
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(smem_u32(&ctl->full[st]));
+    st += n_groups;
+    while (st >= S) { st -= S; ph ^= 1; }
+  }
+}
+
 __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const WgradTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   Ctl* ctl = reinterpret_cast<Ctl*>(smem);
-  const uint32_t base = (smem_u32(smem) + 128 + 1023) & ~1023u;
+  float4* s_aff = reinterpret_cast<float4*>(smem + 128);   // [piece][scale, shift] of this ci block
+  const uint32_t base = (smem_u32(smem) + 128 + 1024 + 1023) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool stacked = p.taps_w > 1;
 
@@ -98,8 +221,8 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const WgradTcPara
   const int Npad = (co_n + 31) & ~31;               // GEMM N (zero padded to the 32-wide atom)
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kStages; ++i) {
-      mbar_init(smem_u32(&ctl->full[i]), kNumLoadWarps / 2);
+    for (int i = 0; i < p.n_stages; ++i) {
+      mbar_init(smem_u32(&ctl->full[i]), 4);      // the 4 warps of the group staging that slot
       mbar_init(smem_u32(&ctl->empty[i]), 1);
     }
     mbar_init(smem_u32(&ctl->done), 1);
@@ -108,182 +231,39 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const WgradTcPara
   if (warp == kAllocWarp) tmem_alloc(smem_u32(&ctl->tmem_base), p.tmem_cols);
   // zero both stages once: channel padding (co >= co_n, ci >= ci_n) must contribute exact zeros,
   // and the don't-care rows behind the halo tile must at least be finite
-  for (int i = threadIdx.x; i < kStages * p.stage_bytes / 16; i += kThreads)
+  for (int i = threadIdx.x; i < p.n_stages * p.stage_bytes / 16; i += kThreads)
     sts128u(base + i * 16, 0u, 0u, 0u, 0u);
+  // BN scale / shift of this CTA's input channels, one (scale, shift) float4 pair per 16 B piece
+  for (int j = threadIdx.x; j < PX; j += kThreads) {
+    int c = ci0 + j * 4;
+    const SrcDev* sp = &p.S.s[0];
+    if (p.S.nsrc > 1 && c >= p.S.s[0].C) { sp = &p.S.s[1]; c -= p.S.s[0].C; }
+    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (sp->scale) {
+      sc = __ldg(reinterpret_cast<const float4*>(sp->scale + c));
+      sh = __ldg(reinterpret_cast<const float4*>(sp->shift + c));
+    }
+    s_aff[2 * j] = sc;
+    s_aff[2 * j + 1] = sh;
+  }
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = ctl->tmem_base;
 
-  if (warp >= kFirstLoadWarp) {
+  if (warp >= kFirstLoadWarp || warp < kNumEpiWarps) {
     // ===================== loaders: dy tile + x halo tile =====================
-    // Group g stages the tiles with (local index & 1) == g into stage g, so two tiles are in
-    // flight per SM.  Loads are issued in branch-free batches of kB from clamped addresses.
+    // Three groups of 4 warps (warps 8-11, 12-15 and — until the final flush — the epilogue
+    // warps 0-3): group g stages the tiles with local index = g (mod 3).
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsLoad));
-    const int grp = (warp - kFirstLoadWarp) >> 2;
-    const int gt = threadIdx.x - (kFirstLoadWarp + grp * 4) * 32;   // 0..127
-    const int n_d = PD * 128;     // 16 B pieces of the dy tile
-    const int n_x = PX * p.HP;    // 16 B pieces of the x halo block
-    const int H = p.H, W = p.W;
-    const uint32_t mulD = fdiv_mul(PD), mulX = fdiv_mul(PX), mulT = fdiv_mul(p.TWp);
-    const int tpi = p.tiles_w * p.tiles_h;
-    const uint32_t mulTpi = fdiv_mul(tpi), mulTw = fdiv_mul(p.tiles_w);
-    // a thread's channel piece is the same for every element when P divides the group size:
-    // hoist the source selection and the BN affine of the x operand
-    const bool x_const = (kGroupThreads % PX) == 0;
-    const uint32_t x0 = base + grp * p.stage_bytes, d0 = x0 + p.x_bytes;
-    uint32_t use = 0;
-    for (int tile = t_begin + grp; tile < t_end; tile += 2, ++use) {
-      const int n = (int)fdiv(tile, tpi, mulTpi);
-      const int rem = tile - n * tpi;
-      const int th_i = (int)fdiv(rem, p.tiles_w, mulTw);
-      const int tw_i = rem - th_i * p.tiles_w;
-      const int h0 = th_i * kTileH, w0 = tw_i * kTileW;
-      const int h_org = h0 - p.dil * (p.taps_h >> 1), w_org = w0 - p.dil * (p.taps_w >> 1);
-      mbar_wait(smem_u32(&ctl->empty[grp]), (use & 1) ^ 1);
-      const size_t img = (size_t)n * H;
-      const bool full_tile = h0 + kTileH <= H && w0 + kTileW <= W;
-      // ---- dy tile: piece e -> (pixel q = e / PD, channel piece j = e % PD)
-      const float* dyb = p.dy + ((img + h0) * W + w0) * p.ld_dy + co0;
-      for (int e0 = gt; e0 < n_d; e0 += kB * kGroupThreads) {
-        float4 v[kB];
-        uint32_t ok = 0;
-#pragma unroll
-        for (int k = 0; k < kB; ++k) {
-          const uint32_t e = min(e0 + k * kGroupThreads, n_d - 1);
-          const uint32_t q = fdiv(e, PD, mulD), j = e - q * PD;
-          int rr = q >> 3, cw = q & 7;
-          bool m = true;
-          if (!full_tile) {
-            m = h0 + rr < H && w0 + cw < W;
-            rr = min(rr, H - 1 - h0);
-            cw = min(cw, W - 1 - w0);
-          }
-          v[k] = __ldg(reinterpret_cast<const float4*>(
-              dyb + ((size_t)rr * W + cw) * p.ld_dy + j * 4));
-          ok |= (m ? 1u : 0u) << k;
-        }
-#pragma unroll
-        for (int k = 0; k < kB; ++k) {
-          const uint32_t e = e0 + k * kGroupThreads;
-          if (e < (uint32_t)n_d) {
-            const uint32_t q = fdiv(e, PD, mulD), j = e - q * PD;
-            const uint32_t msk = (ok >> k) & 1u ? 0xFFFFFFFFu : 0u;
-            sts128u(swz128_32(d0 + (j >> 3) * kChunk + q * 128 + (j & 7) * 16),
-                    tf32b(v[k].x) & msk, tf32b(v[k].y) & msk, tf32b(v[k].z) & msk,
-                    tf32b(v[k].w) & msk);
-          }
-        }
-      }
-      // ---- x halo block: piece e -> (halo pixel q = e / PX, channel piece j = e % PX), BN
-      // affine / 2x2 max-pool / zero padding applied on load (normalise-on-load)
-      const bool interior =
-          h_org >= 0 && w_org >= 0 && h_org + p.THp <= H && w_org + p.TWp <= W;
-      const SrcDev* spc = &p.S.s[0];
-      int cch = ci0 + (gt % PX) * 4;
-      if (p.S.nsrc > 1 && cch >= p.S.s[0].C) { spc = &p.S.s[1]; cch -= p.S.s[0].C; }
-      const bool fast = x_const && interior && !spc->pool;
-      if (fast) {
-        const uint32_t ld = spc->ld;
-        const float* xb = spc->ptr + ((img + h_org) * W + w_org) * ld + cch;
-        const bool aff = spc->scale != nullptr;
-        float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (aff) {
-          sc = __ldg(reinterpret_cast<const float4*>(spc->scale + cch));
-          sh = __ldg(reinterpret_cast<const float4*>(spc->shift + cch));
-        }
-        for (int e0 = gt; e0 < n_x; e0 += kB * kGroupThreads) {
-          float4 v[kB];
-#pragma unroll
-          for (int k = 0; k < kB; ++k) {
-            const uint32_t e = min(e0 + k * kGroupThreads, n_x - 1);
-            const uint32_t q = fdiv(e, PX, mulX);
-            const uint32_t hh = fdiv(q, p.TWp, mulT), ww = q - hh * p.TWp;
-            v[k] = __ldg(reinterpret_cast<const float4*>(xb + (hh * W + ww) * ld));
-          }
-#pragma unroll
-          for (int k = 0; k < kB; ++k) {
-            const uint32_t e = e0 + k * kGroupThreads;
-            if (e < (uint32_t)n_x) {
-              const uint32_t q = fdiv(e, PX, mulX), j = e - q * PX;
-              const uint32_t dst = stacked ? x0 + q * 128 + j * 16
-                                           : x0 + (j >> 3) * p.x_chunk + q * 128 + (j & 7) * 16;
-              sts128u(swz128_32(dst), tf32b(fmaf(v[k].x, sc.x, sh.x)),
-                      tf32b(fmaf(v[k].y, sc.y, sh.y)), tf32b(fmaf(v[k].z, sc.z, sh.z)),
-                      tf32b(fmaf(v[k].w, sc.w, sh.w)));
-            }
-          }
-        }
-      } else {
-        for (int e0 = gt; e0 < n_x; e0 += kB * kGroupThreads) {
-          float4 v[kB];
-#pragma unroll
-          for (int k = 0; k < kB; ++k) {
-            const uint32_t e = min(e0 + k * kGroupThreads, n_x - 1);
-            const uint32_t q = fdiv(e, PX, mulX), j = e - q * PX;
-            const uint32_t hh = fdiv(q, p.TWp, mulT), ww = q - hh * p.TWp;
-            v[k] = load_src4(p.S, n, h_org + (int)hh, w_org + (int)ww, H, W, ci0 + j * 4);
-          }
-#pragma unroll
-          for (int k = 0; k < kB; ++k) {
-            const uint32_t e = e0 + k * kGroupThreads;
-            if (e < (uint32_t)n_x) {
-              const uint32_t q = fdiv(e, PX, mulX), j = e - q * PX;
-              const uint32_t dst = stacked ? x0 + q * 128 + j * 16
-                                           : x0 + (j >> 3) * p.x_chunk + q * 128 + (j & 7) * 16;
-              sts128u(swz128_32(dst), tf32b(v[k].x), tf32b(v[k].y), tf32b(v[k].z), tf32b(v[k].w));
-            }
-          }
-        }
-      }
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&ctl->full[grp]));
-    }
-  } else if (warp >= kNumEpiWarps) {
-   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsMma));
-   if (warp == kMmaWarp) {
-    if (elect_one()) {   // one elected thread issues every MMA / commit
-      const uint32_t idesc = umma_idesc_tf32(128, Npad, 1, 1);
-      const uint64_t a_tmpl = umma_desc_ex(0, stacked ? p.dil * 128 : p.x_chunk, 512, 1, 0);
-      const uint64_t b_tmpl = umma_desc_ex(0, kChunk, 512, 1, 0);
-      const uint32_t a_row16 = stacked ? (uint32_t)p.TWp * 8 : 64u;   // next tile row of x
-      const uint32_t a_ty16 = (uint32_t)(p.dil * p.TWp) * 8;          // next kernel row
-      const uint32_t a_hi = (uint32_t)(a_tmpl >> 32), b_hi = (uint32_t)(b_tmpl >> 32);
-      const int th = p.taps_h;
-      uint32_t it = 0;
-      for (int tile = t_begin; tile < t_end; ++tile, ++it) {
-        const uint32_t st = it & 1;
-        mbar_wait(smem_u32(&ctl->full[st]), (it >> 1) & 1);
-        tc_fence_after();
-        const uint32_t x0 = base + st * p.stage_bytes, d0 = x0 + p.x_bytes;
-        uint32_t a_ty = (uint32_t)a_tmpl + (x0 >> 4);
-        const uint32_t b0 = (uint32_t)b_tmpl + (d0 >> 4);
-        uint32_t dcol = tmem_base;
-        for (int ty = 0; ty < th; ++ty, a_ty += a_ty16, dcol += Npad) {
-          uint32_t ad = a_ty, bd = b0;
-          uint32_t accum = it > 0 ? 1u : 0u;
-#pragma unroll
-          for (int h = 0; h < kTileH; ++h) {
-            umma_tf32_lh(dcol, ad, a_hi, bd, b_hi, idesc, accum);
-            accum = 1u;
-            ad += a_row16;         // next halo row (8 output pixels further down)
-            bd += 64;              // next 8 pixels of the dy tile (8 x 128 B)
-          }
-        }
-        umma_commit(smem_u32(&ctl->empty[st]));
-      }
-      umma_commit(smem_u32(&ctl->done));
-    }
-    __syncwarp();
-   }
-  } else {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsEpi));
-    // ===================== epilogue: TMEM -> atomics into dW (OIHW) =====================
-    // accumulator row m = chunk * 32 + lane: chunk = warp = horizontal tap (stacked) or 32-channel
-    // sub-block; column = ty * Npad + (co - co0)
-    if (t_end > t_begin) {
+    const int grp = warp >= kFirstLoadWarp ? (warp - kFirstLoadWarp) >> 2 : 2;
+    const int gt = threadIdx.x & (kGroupThreads - 1);   // warps 0-3, 8-11, 12-15 -> 0..127
+    wgrad_loader(p, ctl, base, s_aff, grp, gt, t_begin, t_end, co0, ci0, PD, PX);
+    if (warp < kNumEpiWarps && t_end > t_begin) {
+      // ===================== epilogue: TMEM -> atomics into dW (OIHW) =====================
+      // accumulator row m = chunk * 32 + lane: chunk = warp = horizontal tap (stacked) or
+      // 32-channel sub-block; column = ty * Npad + (co - co0)  (fs: (taps_h-1-ty) * 32 + ...)
       mbar_wait(smem_u32(&ctl->done), 0);
       tc_fence_after();
       const int taps = p.taps_h * p.taps_w;
@@ -292,9 +272,10 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const WgradTcPara
       const bool row_ok = ci < ci0 + ci_n && tx < p.taps_w;
       if (stacked ? warp < p.taps_w : warp * 32 < ci_n) {
         for (int ty = 0; ty < p.taps_h; ++ty) {
+          const int col0 = p.fs ? (p.taps_h - 1 - ty) * 32 : ty * Npad;
           for (int c0 = 0; c0 < co_n; c0 += 16) {
             float v[16];
-            tmem_ld16(tmem_base + ty * Npad + c0 + ((uint32_t)(warp * 32) << 16), v);
+            tmem_ld16(tmem_base + col0 + c0 + ((uint32_t)(warp * 32) << 16), v);
             if (row_ok) {
               float* o = p.dw + ((size_t)(co0 + c0) * p.Cin + ci) * taps + ty * p.taps_w + tx;
 #pragma unroll
@@ -305,6 +286,59 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const WgradTcPara
         }
       }
     }
+  } else if (warp >= kNumEpiWarps) {
+   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsMma));
+   if (warp == kMmaWarp) {
+    if (elect_one()) {   // one elected thread issues every MMA / commit
+      const uint32_t S = p.n_stages;
+      const int th = p.taps_h;
+      const uint32_t idesc = umma_idesc_tf32(128, p.fs ? th * 32 : Npad, 1, 1);
+      const uint64_t a_tmpl = umma_desc_ex(0, stacked ? p.dil * 128 : p.x_chunk, 512, 1, 0);
+      const uint64_t b_tmpl = umma_desc_ex(0, p.fs ? p.dil * 1024 : kChunk, 512, 1, 0);
+      const uint32_t a_row16 = stacked ? (uint32_t)p.TWp * 8 : 64u;   // next tile row of x
+      const uint32_t a_ty16 = (uint32_t)(p.dil * p.TWp) * 8;          // next kernel row
+      const uint32_t a_hi = (uint32_t)(a_tmpl >> 32), b_hi = (uint32_t)(b_tmpl >> 32);
+      uint32_t st = 0, ph = 0;
+      for (int tile = t_begin; tile < t_end; ++tile) {
+        mbar_wait(smem_u32(&ctl->full[st]), ph);
+        tc_fence_after();
+        const uint32_t x0 = base + st * p.stage_bytes, d0 = x0 + p.x_bytes;
+        const uint32_t a0 = (uint32_t)a_tmpl + (x0 >> 4);
+        const uint32_t b0 = (uint32_t)b_tmpl + (d0 >> 4);
+        uint32_t accum = tile > t_begin ? 1u : 0u;
+        if (p.fs) {
+          // one MMA per halo row r: A = x row r (tx on M), B = dy rows r-(th-1-c)*dil (ty on N)
+          uint32_t ad = a0, bd = b0;
+          const int rows = p.THp;
+#pragma unroll 2
+          for (int r = 0; r < rows; ++r) {
+            umma_tf32_lh(tmem_base, ad, a_hi, bd, b_hi, idesc, accum);
+            accum = 1u;
+            ad += a_row16;
+            bd += 64;
+          }
+        } else {
+          uint32_t a_ty = a0;
+          uint32_t dcol = tmem_base;
+          for (int ty = 0; ty < th; ++ty, a_ty += a_ty16, dcol += Npad) {
+            uint32_t ad = a_ty, bd = b0;
+            uint32_t acc2 = accum;
+#pragma unroll
+            for (int h = 0; h < kTileH; ++h) {
+              umma_tf32_lh(dcol, ad, a_hi, bd, b_hi, idesc, acc2);
+              acc2 = 1u;
+              ad += a_row16;         // next halo row (8 output pixels further down)
+              bd += 64;              // next 8 pixels of the dy tile (8 x 128 B)
+            }
+          }
+        }
+        umma_commit(smem_u32(&ctl->empty[st]));
+        if (++st == S) { st = 0; ph ^= 1; }
+      }
+      umma_commit(smem_u32(&ctl->done));
+    }
+    __syncwarp();
+   }
   }
 
   tc_fence_before();
@@ -335,25 +369,31 @@ int wgrad_plan(const ab_conv_t* d, WgradTcParams* p, int* smem_bytes) {
   const int d_bytes = (npad / 32) * kChunk;
   // A stage is [x tile][dy tile]: the don't-care rows of the M = 128 operand (chunk 3 of a 3-wide
   // kernel, chunks >= cib/32 of a 1x1 kernel) then alias the dy tile — finite and in bounds.
+  p->fs = stacked && d->Cout <= 32 && d->ks_h > 1;
+  p->dpad = p->fs ? (d->ks_h - 1) * d->dil : 0;
+  int dy_bytes = d_bytes;
+  if (p->fs) dy_bytes = (kTileH + 2 * p->dpad + (d->ks_h - 1) * d->dil) * 1024;   // + chunk over-read
   if (stacked) {
     p->cib = 32;
     p->x_chunk = 0;
     p->x_bytes = (p->HP * 128 + 1023) & ~1023;
-    AB_CHECK(3 * d->dil * 128 + 1024 <= d_bytes, "wgrad_tc: dilation %d too large", d->dil);
+    AB_CHECK(3 * d->dil * 128 + 1024 <= dy_bytes, "wgrad_tc: dilation %d too large", d->dil);
   } else {
     p->x_chunk = (p->HP * 128 + 1023) & ~1023;
     p->cib = 128;
-    if (kStages * (4 * p->x_chunk + d_bytes) + 2048 > 225 * 1024) p->cib = 64;
+    if (2 * (4 * p->x_chunk + d_bytes) + 3072 > 225 * 1024) p->cib = 64;
     p->x_bytes = (p->cib / 32) * p->x_chunk;
     AB_CHECK(p->cib == 128 || 2 * p->x_chunk <= d_bytes, "wgrad_tc: no shared-memory plan");
   }
-  p->stage_bytes = p->x_bytes + d_bytes;
-  *smem_bytes = kStages * p->stage_bytes + 128 + 1024;
-  AB_CHECK(*smem_bytes <= 225 * 1024, "wgrad_tc: halo tile too large for shared memory (dil=%d)",
-           d->dil);
+  p->stage_bytes = p->x_bytes + dy_bytes;
+  int ns = (225 * 1024 - 128 - 2048) / p->stage_bytes;
+  if (ns > kMaxStages) ns = kMaxStages;
+  AB_CHECK(ns >= 2, "wgrad_tc: halo tile too large for shared memory (dil=%d)", d->dil);
+  p->n_stages = ns;
+  *smem_bytes = ns * p->stage_bytes + 128 + 2048;
   p->n_cc = (p->Cin + p->cib - 1) / p->cib;
   int cols = 32;
-  while (cols < d->ks_h * npad) cols <<= 1;
+  while (cols < (p->fs ? d->ks_h * 32 : d->ks_h * npad)) cols <<= 1;
   AB_CHECK(cols <= 512, "wgrad_tc: too many accumulator columns");
   p->tmem_cols = cols;
   const int groups = p->n_cc * p->co_blocks;

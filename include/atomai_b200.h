@@ -223,6 +223,10 @@ int atomai_b200_gram(const float* x1, const float* x2, const float* inv_ls, floa
  * operands, used by tests to pin descriptor conventions. */
 int atomai_b200_selftest_umma(const float* A, const float* B, float* D, int N, int K,
                               int variant, void* stream);
+/* tcgen05 issue-rate probe (dev/test only): `issuers` threads each issue `iters` M128 x N x K8 TF32
+ * MMAs on resident operands; out[2*i] = SM clocks to issue, out[2*i+1] = clocks until retired.
+ * layout 0 = K-major no-swizzle (conv), 1 = MN-major SWIZZLE_128B_BASE32B (wgrad). */
+int atomai_b200_umma_rate(int N, int layout, int issuers, int iters, long long* out, void* stream);
 
 #ifdef __cplusplus
 }

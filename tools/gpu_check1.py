@@ -221,6 +221,10 @@ def run_group(name):
         wgrad_case("16to3_1x1", M, 2, 40, 48, [16], 3, ks=1)
         wgrad_case("cat_pool_affine", M, 2, 16, 24, [8, 12], 16, affine=True, pool=True)
         wgrad_case("70to130_dil2", M, 1, 17, 19, [70], 130, dil=2)
+        wgrad_case("1to16_affine", M, 3, 37, 29, [1], 16, affine=True)
+        wgrad_case("16to3_1x1_affine", M, 3, 37, 29, [16], 3, ks=1, affine=True)
+        wgrad_case("2to16_1x1", M, 2, 20, 24, [2], 16, ks=1)
+        wgrad_case("8to3_3x3", M, 2, 20, 24, [8], 3)
     elif name == "wgrad_tc":
         M = ops.MATH_TF32
         wgrad_case("32to32_16x8", M, 1, 16, 8, [32], 32)
