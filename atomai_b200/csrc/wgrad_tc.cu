@@ -160,11 +160,20 @@ __device__ __forceinline__ void wgrad_loader(const WgradTcParams& p, Ctl* ctl, u
         }
       } else {
         // pooled source(s): the generic normalise / max-pool / pad loader, piece by piece
-        for (int j = 0; j < PX; ++j) {
-          const float4 x = load_src4(p.S, n, gh, gw, H, W, ci0 + j * 4);
-          const uint32_t dst = (stacked ? row : row + (j >> 3) * p.x_chunk) +
-                               (((uint32_t)(j & 7) << 4) ^ sw);
-          sts128u(dst, tf32b(x.x), tf32b(x.y), tf32b(x.z), tf32b(x.w));
+        for (int jb = 0; jb < PX; jb += 4) {
+          float4 v[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (jb + k < PX) v[k] = load_src4(p.S, n, gh, gw, H, W, ci0 + (jb + k) * 4);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int j = jb + k;
+            if (j < PX) {
+              const uint32_t dst = (stacked ? row : row + (j >> 3) * p.x_chunk) +
+                                   (((uint32_t)(j & 7) << 4) ^ sw);
+              sts128u(dst, tf32b(v[k].x), tf32b(v[k].y), tf32b(v[k].z), tf32b(v[k].w));
+            }
+          }
         }
       }
     }
