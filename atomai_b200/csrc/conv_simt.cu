@@ -231,6 +231,127 @@ __global__ void __launch_bounds__(256) conv_pix_kernel(const ConvSimtParams p, i
   }
 }
 
+// First layer (Cin = 1, 3x3, one un-pooled source): an HBM stream that writes 16x more than it
+// reads.  Each thread owns two horizontally adjacent output pixels: 3 x 4 input samples from
+// L1, the 9 x CO weights as float4 broadcasts from shared memory (shared by both pixels), CO x 2
+// accumulators in registers, 2 x CO/4 float4 stores; BN statistics ride along in registers.
+template <int CO>
+__global__ void __launch_bounds__(256, 2) conv_c1_kernel(const ConvSimtParams p) {
+  __shared__ float4 s_w[9 * CO / 4];            // [tap][co]
+  __shared__ float4 s_b[CO / 4];
+  __shared__ float s_red[2 * CO];
+  for (int i = threadIdx.x; i < 9 * CO; i += blockDim.x)
+    reinterpret_cast<float*>(s_w)[i] = __ldg(p.w + i);          // packed [tap][Cin = 1][Cout]
+  if (threadIdx.x < CO)
+    reinterpret_cast<float*>(s_b)[threadIdx.x] = p.bias ? __ldg(p.bias + threadIdx.x) : 0.f;
+  if (threadIdx.x < 2 * CO) s_red[threadIdx.x] = 0.f;
+  __syncthreads();
+  const SrcDev sd = p.S.s[0];
+  float sc = 1.f, sh = 0.f;
+  if (sd.scale) { sc = __ldg(sd.scale); sh = __ldg(sd.shift); }
+  float ssum[CO], ssq[CO];
+#pragma unroll
+  for (int k = 0; k < CO; ++k) { ssum[k] = 0.f; ssq[k] = 0.f; }
+  const int H = p.H, W = p.W, d = p.dil;
+  const uint32_t Wh = (uint32_t)(W + 1) >> 1, per_img = Wh * (uint32_t)H;
+  const uint32_t total = per_img * (uint32_t)p.N;
+  const bool fast = p.act == AB_ACT_LRELU && p.alpha >= 0.f && p.alpha <= 1.f;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  // input patch of a pixel pair (w, w+1): rows h-d, h, h+d x columns {w-d, w, w+d} (+1 for the
+  // second pixel), zero padded; fetched one iteration ahead so the loads overlap the FMAs
+  auto fetch = [&](uint32_t idx, float (&x0)[9], float (&x1)[9], uint32_t& n, int& h, int& w) {
+    n = idx / per_img;
+    const uint32_t rem = idx - n * per_img;
+    h = (int)(rem / Wh);
+    w = (int)(rem - (uint32_t)h * Wh) * 2;
+#pragma unroll
+    for (int ty = 0; ty < 3; ++ty) {
+      const int hh = h + (ty - 1) * d;
+      const bool rok = (unsigned)hh < (unsigned)H;
+      const float* rowp = sd.ptr + ((size_t)n * H + (rok ? hh : 0)) * W * sd.ld;
+#pragma unroll
+      for (int tx = 0; tx < 3; ++tx) {
+        const int w0 = w + (tx - 1) * d, w1 = w0 + 1;
+        const bool ok0 = rok && (unsigned)w0 < (unsigned)W, ok1 = rok && (unsigned)w1 < (unsigned)W;
+        x0[ty * 3 + tx] = ok0 ? fmaf(__ldg(rowp + (size_t)w0 * sd.ld), sc, sh) : 0.f;
+        x1[ty * 3 + tx] = ok1 ? fmaf(__ldg(rowp + (size_t)w1 * sd.ld), sc, sh) : 0.f;
+      }
+    }
+  };
+  uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+  float nx0[9], nx1[9];
+  uint32_t nn = 0; int nh = 0, nw = 0;
+  if (idx < total) fetch(idx, nx0, nx1, nn, nh, nw);
+  for (; idx < total; idx += stride) {
+    float x0[9], x1[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) { x0[t] = nx0[t]; x1[t] = nx1[t]; }
+    const uint32_t n = nn; const int h = nh, w = nw;
+    if (idx + stride < total) fetch(idx + stride, nx0, nx1, nn, nh, nw);
+    float a0[CO], a1[CO];
+#pragma unroll
+    for (int k4 = 0; k4 < CO / 4; ++k4) {
+      const float4 bv = s_b[k4];
+      a0[k4 * 4] = bv.x; a0[k4 * 4 + 1] = bv.y; a0[k4 * 4 + 2] = bv.z; a0[k4 * 4 + 3] = bv.w;
+      a1[k4 * 4] = bv.x; a1[k4 * 4 + 1] = bv.y; a1[k4 * 4 + 2] = bv.z; a1[k4 * 4 + 3] = bv.w;
+    }
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+#pragma unroll
+      for (int k4 = 0; k4 < CO / 4; ++k4) {
+        const float4 wv = s_w[t * (CO / 4) + k4];
+        a0[k4 * 4 + 0] = fmaf(x0[t], wv.x, a0[k4 * 4 + 0]); a1[k4 * 4 + 0] = fmaf(x1[t], wv.x, a1[k4 * 4 + 0]);
+        a0[k4 * 4 + 1] = fmaf(x0[t], wv.y, a0[k4 * 4 + 1]); a1[k4 * 4 + 1] = fmaf(x1[t], wv.y, a1[k4 * 4 + 1]);
+        a0[k4 * 4 + 2] = fmaf(x0[t], wv.z, a0[k4 * 4 + 2]); a1[k4 * 4 + 2] = fmaf(x1[t], wv.z, a1[k4 * 4 + 2]);
+        a0[k4 * 4 + 3] = fmaf(x0[t], wv.w, a0[k4 * 4 + 3]); a1[k4 * 4 + 3] = fmaf(x1[t], wv.w, a1[k4 * 4 + 3]);
+      }
+    }
+    const bool two = w + 1 < W;
+#pragma unroll
+    for (int k = 0; k < CO; ++k) {
+      a0[k] = fast ? fmaxf(a0[k], a0[k] * p.alpha) : act_f(a0[k], p.act, p.alpha);
+      a1[k] = fast ? fmaxf(a1[k], a1[k] * p.alpha) : act_f(a1[k], p.act, p.alpha);
+      if (!two) a1[k] = 0.f;
+      ssum[k] += a0[k] + a1[k];
+      ssq[k] = fmaf(a0[k], a0[k], fmaf(a1[k], a1[k], ssq[k]));
+    }
+    float* o = p.out + (((size_t)n * H + h) * W + w) * p.ld_out;
+#pragma unroll
+    for (int k = 0; k < CO; k += 4) {
+      *reinterpret_cast<float4*>(o + k) = make_float4(a0[k], a0[k + 1], a0[k + 2], a0[k + 3]);
+      if (two)
+        *reinterpret_cast<float4*>(o + p.ld_out + k) = make_float4(a1[k], a1[k + 1], a1[k + 2], a1[k + 3]);
+    }
+  }
+  if (p.stats) {
+#pragma unroll
+    for (int k = 0; k < CO; ++k) {
+      const float a = warp_sum(ssum[k]), b = warp_sum(ssq[k]);
+      if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&s_red[k], a);
+        atomicAdd(&s_red[CO + k], b);
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < CO) {
+      atomicAdd(p.stats + threadIdx.x, (double)s_red[threadIdx.x]);
+      atomicAdd(p.stats + p.Cout + threadIdx.x, (double)s_red[CO + threadIdx.x]);
+    }
+  }
+}
+
+template <int CO>
+int launch_conv_c1(const ConvSimtParams& p, cudaStream_t stream) {
+  const int64_t pairs = (int64_t)p.N * p.H * ((p.W + 1) / 2);
+  AB_CHECK(pairs < (1ll << 31), "conv_c1: too many pixels");
+  int64_t blocks = (pairs + 255) / 256;
+  const int64_t cap = (int64_t)ab_num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  conv_c1_kernel<CO><<<(unsigned)blocks, 256, 0, stream>>>(p);
+  AB_LAUNCH_CHECK();
+  return 0;
+}
+
 template <int CO>
 int launch_conv_pix(const ConvSimtParams& p, cudaStream_t stream) {
   const int taps = p.th * p.tw, Cin = p.S.Ctot;
@@ -336,6 +457,85 @@ __global__ void __launch_bounds__(G_THREADS) conv_simt_wgrad_kernel(const WgradS
 // above would waste > 95 % of its FMAs, so here every thread walks pixels and keeps the whole
 // CO x CI x TW slice of dW in registers; one warp-shuffle reduction + atomics per CTA at the end.
 // grid: (pixel ranges, tap rows (ks_h), co-groups * ci-groups).
+// Weight gradient of the same layer: dW[co][0][ty][tx] = sum_p dy[p][co] * x[p + tap].  Thread =
+// two adjacent pixels x CO/2 output channels (blockIdx.y picks the half): the 3 x 4 input patch
+// is shared by both pixels, dy comes in as float4, the 9 x CO/2 partial sums live in registers.
+template <int CO>
+__global__ void __launch_bounds__(256, 2) wgrad_c1_kernel(const WgradSimtParams p) {
+  constexpr int CH = CO / 2;
+  const int co0 = blockIdx.y * CH;
+  const SrcDev sd = p.S.s[0];
+  float sc = 1.f, sh = 0.f;
+  if (sd.scale) { sc = __ldg(sd.scale); sh = __ldg(sd.shift); }
+  float acc[CH][9];
+#pragma unroll
+  for (int a = 0; a < CH; ++a)
+#pragma unroll
+    for (int t = 0; t < 9; ++t) acc[a][t] = 0.f;
+  const int H = p.H, W = p.W, d = p.dil;
+  const uint32_t Wh = (uint32_t)(W + 1) >> 1, per_img = Wh * (uint32_t)H;
+  const uint32_t total = per_img * (uint32_t)p.N;
+  for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += gridDim.x * blockDim.x) {
+    const uint32_t n = idx / per_img, rem = idx - n * per_img;
+    const int h = (int)(rem / Wh), w = (int)(rem - (uint32_t)h * Wh) * 2;
+    const bool two = w + 1 < W;
+    const float* dyp = p.dy + (((size_t)n * H + h) * W + w) * p.ld_dy + co0;
+    float d0[CH], d1[CH];
+#pragma unroll
+    for (int a = 0; a < CH; a += 4) {
+      const float4 v0 = __ldg(reinterpret_cast<const float4*>(dyp + a));
+      float4 v1 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (two) v1 = __ldg(reinterpret_cast<const float4*>(dyp + p.ld_dy + a));
+      d0[a] = v0.x; d0[a + 1] = v0.y; d0[a + 2] = v0.z; d0[a + 3] = v0.w;
+      d1[a] = v1.x; d1[a + 1] = v1.y; d1[a + 2] = v1.z; d1[a + 3] = v1.w;
+    }
+#pragma unroll
+    for (int ty = 0; ty < 3; ++ty) {
+      const int hh = h + (ty - 1) * d;
+      const bool rok = (unsigned)hh < (unsigned)H;
+      const float* rowp = sd.ptr + ((size_t)n * H + (rok ? hh : 0)) * W * sd.ld;
+#pragma unroll
+      for (int tx = 0; tx < 3; ++tx) {
+        const int w0 = w + (tx - 1) * d, w1 = w0 + 1;
+        const bool ok0 = rok && (unsigned)w0 < (unsigned)W, ok1 = rok && (unsigned)w1 < (unsigned)W;
+        const float x0 = ok0 ? fmaf(__ldg(rowp + (size_t)w0 * sd.ld), sc, sh) : 0.f;
+        const float x1 = ok1 ? fmaf(__ldg(rowp + (size_t)w1 * sd.ld), sc, sh) : 0.f;
+#pragma unroll
+        for (int a = 0; a < CH; ++a)
+          acc[a][ty * 3 + tx] = fmaf(d0[a], x0, fmaf(d1[a], x1, acc[a][ty * 3 + tx]));
+      }
+    }
+  }
+  __shared__ float s_acc[CH * 9];
+  for (int i = threadIdx.x; i < CH * 9; i += blockDim.x) s_acc[i] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int a = 0; a < CH; ++a)
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const float v = warp_sum(acc[a][t]);
+      if ((threadIdx.x & 31) == 0) atomicAdd(&s_acc[a * 9 + t], v);
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < CH * 9; i += blockDim.x)
+    atomicAdd(p.dw + (size_t)(co0 + i / 9) * 9 + i % 9, s_acc[i]);   // OIHW with Cin = 1
+}
+
+template <int CO>
+int launch_wgrad_c1(const WgradSimtParams& p, cudaStream_t stream) {
+  const int64_t pairs = (int64_t)p.N * p.H * ((p.W + 1) / 2);
+  AB_CHECK(pairs < (1ll << 31), "wgrad_c1: too many pixels");
+  int64_t bx = (pairs + 256 * 8 - 1) / (256 * 8);
+  const int64_t cap = (int64_t)ab_num_sms() * 4;
+  if (bx > cap) bx = cap;
+  if (bx < 1) bx = 1;
+  dim3 grid((unsigned)bx, 2, 1);
+  wgrad_c1_kernel<CO><<<grid, 256, 0, stream>>>(p);
+  AB_LAUNCH_CHECK();
+  return 0;
+}
+
 template <int CO, int CI, int TH, int TW>
 __global__ void __launch_bounds__(256) wgrad_small_kernel(const WgradSimtParams p, int co_groups) {
   const int cog = blockIdx.z % co_groups, cig = blockIdx.z / co_groups;
@@ -479,6 +679,10 @@ int ab_conv_simt_fwd(const ab_conv_t* d, const float* w, const float* bias, floa
   // thin-channel specialisations (first layer, pixel-wise head and its data-gradient)
   {
     const int Cin = p.S.Ctot, taps = d->ks_h * d->ks_w;
+    if (Cin == 1 && d->ks_h == 3 && d->ks_w == 3 && d->Cout == 16 && p.S.nsrc == 1 &&
+        !p.S.s[0].pool && !d->out_nchw && ld_y % 4 == 0 && ((uintptr_t)y & 15) == 0 &&
+        d->N * (int64_t)d->H * d->W > 0)
+      return launch_conv_c1<16>(p, stream);
     if (taps * Cin <= 64 && d->N * (int64_t)d->H * d->W > 0) {
       if (d->Cout <= 4) return launch_conv_pix<4>(p, stream);
       if (d->Cout == 8) return launch_conv_pix<8>(p, stream);
@@ -517,6 +721,9 @@ int ab_conv_simt_wgrad(const ab_conv_t* d, const float* dy, int ld_dy, float* dw
   p.co_tiles = (d->Cout + G_CT - 1) / G_CT;
   p.ci_tiles = (p.S.Ctot + G_CT - 1) / G_CT;
   p.px_per_cta = 0;
+  if (p.S.Ctot == 1 && d->ks_w == 3 && d->ks_h == 3 && d->Cout == 16 && p.S.nsrc == 1 &&
+      !p.S.s[0].pool && ld_dy % 4 == 0 && ((uintptr_t)dy & 15) == 0)
+    return launch_wgrad_c1<16>(p, stream);
   if (p.S.Ctot <= 2 && d->ks_w == 3 && d->ks_h == 3) return launch_wgrad_small<8, 1, 3, 3>(p, stream);
   if (p.S.Ctot <= 2 && d->ks_w == 3 && d->ks_h == 1) return launch_wgrad_small<16, 1, 1, 3>(p, stream);
   if (p.S.Ctot <= 2 && d->ks_w == 1 && d->ks_h == 1) return launch_wgrad_small<16, 2, 1, 1>(p, stream);

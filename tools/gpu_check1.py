@@ -139,6 +139,9 @@ def run_group(name):
     elif name == "simt":
         M = ops.MATH_FP32
         conv_case("c1_1to16", M, 2, 40, 48, [1], 16)
+        conv_case("c1_odd_w_affine", M, 3, 37, 29, [1], 16, affine=True)
+        conv_case("c1_dil2", M, 2, 24, 30, [1], 16, dil=2)
+        conv_case("c1_big", M, 4, 256, 256, [1], 16)
         conv_case("px_16to3", M, 2, 40, 48, [16], 3, ks=1, lrelu=1.0, stats=False)
         conv_case("mid_24to20_dil2", M, 2, 33, 29, [24], 20, dil=2)
         conv_case("cat_affine_pool", M, 2, 16, 24, [8, 12], 16, affine=True, pool=True)
@@ -222,6 +225,8 @@ def run_group(name):
         wgrad_case("cat_pool_affine", M, 2, 16, 24, [8, 12], 16, affine=True, pool=True)
         wgrad_case("70to130_dil2", M, 1, 17, 19, [70], 130, dil=2)
         wgrad_case("1to16_affine", M, 3, 37, 29, [1], 16, affine=True)
+        wgrad_case("1to16_dil2", M, 2, 24, 30, [1], 16, dil=2)
+        wgrad_case("1to16_big", M, 4, 256, 256, [1], 16)
         wgrad_case("16to3_1x1_affine", M, 3, 37, 29, [16], 3, ks=1, affine=True)
         wgrad_case("2to16_1x1", M, 2, 20, 24, [2], 16, ks=1)
         wgrad_case("8to3_3x3", M, 2, 20, 24, [8], 3)
