@@ -218,7 +218,6 @@ def run_ours(args):
     if world > 1:
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
     ms_total = float(t.item())
-    sampler.stop_flag = True
     final_losses = [float(v) for v in m.loss_acc["train_loss"][-2:]]
 
     # train-step-only timing (secondary figure)
@@ -260,6 +259,7 @@ def run_ours(args):
     if world > 1:
         torch.distributed.all_reduce(t3, op=torch.distributed.ReduceOp.MAX)
     ms_e2e = float(t3.item())
+    sampler.stop_flag = True          # clocks are sampled over all three timed regions
 
     if rank != 0:
         return
@@ -276,11 +276,20 @@ def run_ours(args):
         layers[tag] = {"ms": round(ms, 4), "tflops": round(tfl, 1), "gbs": round(gbs, 1),
                        "frac_tensor": round(tfl / tf32_peak, 3), "frac_hbm": round(gbs / pk["hbm"], 3)}
     dom = "bn.block.3"
+    # DRAM traffic of that kernel (dram__bytes_read.sum + dram__bytes_write.sum of one launch) from
+    # the committed `ncu --set full` capture of the same layer shape
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_roofline.json")))["traffic_bytes"]
+    except Exception:  # noqa
+        pass
     roof = {"bound": "tensor", "kernel": "conv_tc_kernel (fused conv3x3+bias+LeakyReLU+BN stats), "
             f"layer {dom} 128->128 @64x64, batch {BATCH}", "achieved": layers[dom]["tflops"],
             "peak": round(tf32_peak, 1), "unit": "TFLOP/s", "frac": layers[dom]["frac_tensor"],
             "peak_note": f"0.5 x {pk['src']} dense bf16 ({pk['bf16']} TF/s): TF32 operands",
-            "traffic": None, "layers": layers,
+            "traffic": traffic, "traffic_note": "bytes per launch, profiles/r01_roofline.json "
+            "(ncu --set full; algorithmic bytes = 4*N*H*W*(Cin+Cout) = 134.2 MB, the 126 MB L2 "
+            "holds back part of the output writes)", "layers": layers,
             "step_tflops_algorithmic": round(step_tflops, 1),
             "step_frac": round(step_tflops / tf32_peak, 3)}
 
@@ -336,3 +345,5 @@ if __name__ == "__main__":
         run_reference(a)
     else:
         run_ours(a)
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            torch.distributed.destroy_process_group()
