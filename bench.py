@@ -33,6 +33,19 @@ FLOP_PER_PIXEL_TRAIN = 196_992        # fwd 65,664 x 3 (fwd + dg
 FLOP_PER_PIXEL_FWD = 65_664
 
 
+def host_cores():
+    """Threads the CPU arm may really use: scheduler affinity, capped by the cgroup CPU quota
+    (os.cpu_count() reports the machine, not the container: oversubscribing it is 10x slower)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = max(1, min(n, int(float(q) / float(per) + 0.5)))
+    except Exception:  # noqa
+        pass
+    return n
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -97,7 +110,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    cores = host_cores()
     torch.set_num_threads(cores)
     sample_batch = args.ref_batch
     torch.manual_seed(1)
@@ -298,13 +311,13 @@ def run_ours(args):
     if world == 1 and not args.no_cpu_baseline:
         try:
             out = subprocess.check_output(
-                [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "2",
+                [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "4",
                  "--warmup", "1", "--ref-batch", str(args.ref_batch)], encoding="utf-8",
                 timeout=600, env={**os.environ, "CUDA_VISIBLE_DEVICES": ""})
             ref = json.loads([l for l in out.splitlines() if l.startswith("{")][-1])
             cpu = ref["cpu_baseline"]
         except Exception as ex:  # noqa
-            cpu = {"value": None, "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
+            cpu = {"value": None, "unit": "images/s", "cores": host_cores(), "kind": "port",
                    "sample": f"failed: {type(ex).__name__}: {ex}"[:200]}
 
     line = {
@@ -338,7 +351,8 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--math", default="tf32", choices=["tf32", "fp32"])
-    ap.add_argument("--ref-batch", type=int, default=8)
+    ap.add_argument("--ref-batch", type=int, default=8,
+                    help="images per step of the bounded CPU sample (reference arm / cpu_baseline)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
     if a.impl == "reference":
