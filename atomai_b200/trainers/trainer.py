@@ -191,12 +191,42 @@ class BaseTrainer:
             return (loss.item(), acc_score)
         return (loss.item() if self.sync_host else loss.detach(),)
 
+    def _issue_batches(self, e: int):
+        """The four tensors of cycle `e` on the device.  Host-resident (pinned) batches — data sets
+        larger than `memory_alloc`, the reference keeps those on the CPU too
+        (atomai/utils/preproc.py:170-201) — are copied on a side stream so that the transfer of
+        cycle e+1 overlaps the kernels of cycle e; returns (tensors, event or None)."""
+        f, t = self.dataloader(self.batch_idx_train[e], mode='train')
+        f_, t_ = self.dataloader(self.batch_idx_test[e], mode='test')
+        host = [x for x in (f, t, f_, t_) if isinstance(x, torch.Tensor) and not x.is_cuda]
+        if not host or self.device != 'cuda':
+            return (f, t, f_, t_), None
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream()
+        with torch.cuda.stream(self._copy_stream):
+            dev = tuple(x.to(self.device, non_blocking=True) for x in (f, t, f_, t_))
+            ev = torch.cuda.Event()
+            ev.record(self._copy_stream)
+        return dev, ev
+
     def step(self, e: int) -> None:
         """One train mini-batch + one test mini-batch (atomai/trainers/trainer.py:233-251)."""
-        features, targets = self.dataloader(self.batch_idx_train[e], mode='train')
+        pre = getattr(self, "_prefetched", None)
+        if pre is not None and pre[0] == e:
+            batches, ev = pre[1]
+        else:
+            batches, ev = self._issue_batches(e)
+        self._prefetched = None
+        if ev is not None:
+            cur = torch.cuda.current_stream()
+            cur.wait_event(ev)
+            for x in batches:
+                x.record_stream(cur)
+            if e + 1 < len(self.batch_idx_train) and self.augment_fn is None:
+                self._prefetched = (e + 1, self._issue_batches(e + 1))
+        features, targets, features_, targets_ = batches
         loss = self.train_step(features, targets)
         self.loss_acc["train_loss"].append(loss[0])
-        features_, targets_ = self.dataloader(self.batch_idx_test[e], mode='test')
         loss_ = self.test_step(features_, targets_)
         self.loss_acc["test_loss"].append(loss_[0])
         if self.compute_accuracy:

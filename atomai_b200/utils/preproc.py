@@ -97,6 +97,8 @@ def array2list_(x: Arr, batch_size: int, store_on_cpu: bool = False):
         raise TypeError("Provide data as numpy array or torch tensor")
     if isinstance(x, torch.Tensor):
         x = x.to('cuda' if torch.cuda.is_available() and not store_on_cpu else 'cpu')
+        if store_on_cpu and torch.cuda.is_available() and not x.is_pinned():
+            x = x.pin_memory()       # host-resident batches are copied asynchronously each step
     n_batches = x.shape[0] // batch_size
     x = x[:n_batches * batch_size]
     return np.split(x, n_batches) if isinstance(x, np.ndarray) else torch.chunk(x, n_batches)
