@@ -58,7 +58,7 @@ struct ConvTcParams {
   int plane_bytes;   // stride between 4-channel planes (== 128/P mod 128 -> conflict-free STS)
   int a_stage_bytes, b_stage_bytes;
   int n_a, n_b;      // pipeline depths
-  int tmem_cols;     // power of two >= 2*sub*Cout
+  int tmem_cols;     // power of two >= (2 or 4 accumulator buffers)*sub*Cout
   int sub;           // 8-pixel-wide sub-tiles per CTA tile (1 or 2): M = 128*sub per weight stage
   int w_resident;    // 1: all weights live in shared memory for the whole kernel
   int w_bytes;       // taps * Ctot * Cout * 4
@@ -67,7 +67,7 @@ struct ConvTcParams {
 struct __align__(8) SharedCtl {
   uint64_t full_a[kMaxAStages], empty_a[kMaxAStages];
   uint64_t full_b[kMaxBStages], empty_b[kMaxBStages];
-  uint64_t tmem_full[2], tmem_empty[2];
+  uint64_t tmem_full[4], tmem_empty[4];
   uint64_t w_full;
   uint32_t tmem_base;
   uint32_t pad;
@@ -107,15 +107,16 @@ __device__ __forceinline__ void mma_issue_loop(const ConvTcParams& p, SharedCtl*
   // with its own half of the activation-stage ring (a stage barrier must have ONE consumer, or a
   // fast consumer aliases the parity of a phase the other one has not seen yet).
   const uint32_t n_iss = RESIDENT ? 2u : 1u;
-  const uint32_t acc = RESIDENT ? (uint32_t)issuer : 0u;
-  uint32_t acc_phase = 0, acc_s = 0;
+  // TMEM accumulators: 2 (streamed weights) or 4 (two per pipeline) buffers, tile t -> t mod n
+  const uint32_t n_acc = RESIDENT ? 4u : 2u;
+  uint32_t tl = issuer;                                  // this issuer's running local tile index
   const uint32_t ring_n = RESIDENT ? n_a / 2 : n_a;
   const uint32_t ring0 = RESIDENT ? issuer * ring_n : 0u;
   const int num_tiles = p.num_tiles;
   const int tile_step = gridDim.x * n_iss;
   for (int tile = blockIdx.x + issuer * gridDim.x; tile < num_tiles; tile += tile_step) {
-    const uint32_t a_ = RESIDENT ? acc : acc_s;
-    mbar_wait(bar_tempty + a_ * 8, acc_phase ^ 1);
+    const uint32_t a_ = tl & (n_acc - 1);
+    mbar_wait(bar_tempty + a_ * 8, ((tl / n_acc) & 1) ^ 1);
     tc_fence_after();
     const uint32_t d_tmem = tmem_base + a_ * SUB * cout;
     uint32_t accum = 0u;
@@ -151,12 +152,7 @@ __device__ __forceinline__ void mma_issue_loop(const ConvTcParams& p, SharedCtl*
       if (++sa == ring_n) { sa = 0; pa ^= 1; }
     }
     umma_commit(bar_tfull + a_ * 8);
-    if (RESIDENT) {
-      acc_phase ^= 1;
-    } else {
-      acc_s ^= 1;
-      if (acc_s == 0) acc_phase ^= 1;
-    }
+    tl += n_iss;
   }
 }
 
@@ -343,7 +339,8 @@ __device__ __forceinline__ void epilogue_loop(const ConvTcParams& p, SharedCtl* 
                                               uint32_t tmem_base, float* s_stats,
                                               const float* s_bias) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint32_t acc = 0, acc_phase = 0;
+  const uint32_t n_acc = p.w_resident ? 4u : 2u;
+  uint32_t tl = 0;                                       // local tile counter -> accumulator buffer
   float* my_stats = s_stats + warp * 2 * p.Cout;
   const int row = warp * 32 + lane;
   const int r_h = row >> 3, r_w = row & 7;
@@ -362,7 +359,8 @@ __device__ __forceinline__ void epilogue_loop(const ConvTcParams& p, SharedCtl* 
     int th_i = __float2int_rz((float)rem * inv_tw);
     th_i += ((th_i + 1) * p.tiles_w <= rem) - (th_i * p.tiles_w > rem);
     const int tw_i = rem - th_i * p.tiles_w;
-    mbar_wait(smem_u32(&ctl->tmem_full[acc]), acc_phase);
+    const uint32_t acc = tl & (n_acc - 1);
+    mbar_wait(smem_u32(&ctl->tmem_full[acc]), (tl / n_acc) & 1);
     tc_fence_after();
     for (int sb_ = 0; sb_ < p.sub; ++sb_) {
       const int gh = th_i * kTileH + r_h, gw = (tw_i * p.sub + sb_) * kTileW + r_w;
@@ -429,8 +427,7 @@ __device__ __forceinline__ void epilogue_loop(const ConvTcParams& p, SharedCtl* 
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(smem_u32(&ctl->tmem_empty[acc]));
-    acc ^= 1;
-    if (acc == 0) acc_phase ^= 1;
+    ++tl;
   }
   if (do_stats) {
     if (NG > 0) {
@@ -451,7 +448,7 @@ __device__ __forceinline__ void epilogue_loop(const ConvTcParams& p, SharedCtl* 
   }
 }
 
-static_assert(sizeof(SharedCtl) <= 320, "SharedCtl must fit below the MMA offset table");
+static_assert(sizeof(SharedCtl) <= 640, "SharedCtl must fit below the statistics block at smem + 640");
 
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -475,7 +472,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
       mbar_init(smem_u32(&ctl->full_b[i]), 1);
       mbar_init(smem_u32(&ctl->empty_b[i]), 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 4; ++i) {
       mbar_init(smem_u32(&ctl->tmem_full[i]), 1);
       mbar_init(smem_u32(&ctl->tmem_empty[i]), kNumEpiWarps);
     }
@@ -717,7 +714,7 @@ static int conv_tc_plan(const ab_conv_t* d, ConvTcParams* p, int* smem_bytes) {
   p->n_chunks = S.Ctot / p->KC;
   AB_CHECK(p->plane_bytes / 16 < (1 << 14) && p->TWp < (1 << 14), "conv_tc: descriptor overflow");
   int cols = 32;
-  while (cols < 2 * p->sub * d->Cout) cols <<= 1;
+  while (cols < (p->w_resident ? 4 : 2) * p->sub * d->Cout) cols <<= 1;
   p->tmem_cols = cols;
   *smem_bytes = stats_bytes + p->n_a * p->a_stage_bytes +
                 (p->w_resident ? ((p->w_bytes + 127) & ~127) : p->n_b * p->b_stage_bytes);
