@@ -43,6 +43,28 @@ def test_fit_semantics_and_checkpoint_roundtrip(cuda, tmp_path):
     np.testing.assert_allclose(m3.loss_acc["train_loss"][:3], m.loss_acc["train_loss"][:3], rtol=2e-3)
 
 
+def test_host_resident_data_prefetch_matches_device_resident(cuda, tmp_path):
+    """Data sets larger than `memory_alloc` stay in (pinned) host memory, as in the reference
+    (atomai/utils/preproc.py:170-201); the trainer copies cycle e+1 on a side stream while cycle e
+    computes.  Same seed => same losses as the device-resident run."""
+    import atomai_b200 as ab
+    from atomai_b200.models import Segmentor
+    ab.set_math("fp32")
+    X, y = _data(32, 32, 32, 11)
+    Xt, yt = _data(16, 32, 32, 12)
+    losses = []
+    for alloc in (4, 0):
+        m = Segmentor("Unet", nb_classes=3, nb_filters=8)
+        m.fit(X, y, Xt, yt, training_cycles=5, batch_size=8, memory_alloc=alloc,
+              filename=str(tmp_path / f"pf{alloc}"), plot_training_history=False)
+        assert m.X_train[0].is_cuda == (alloc == 4)
+        if alloc == 0:
+            assert m.X_train[0].is_pinned()
+        losses.append((list(m.loss_acc["train_loss"]), list(m.loss_acc["test_loss"])))
+    np.testing.assert_allclose(losses[0][0], losses[1][0], rtol=1e-5)
+    np.testing.assert_allclose(losses[0][1], losses[1][1], rtol=1e-5)
+
+
 def test_full_epoch_mode_and_binary_loss(cuda, tmp_path):
     import atomai_b200 as ab
     from atomai_b200.models import Segmentor
