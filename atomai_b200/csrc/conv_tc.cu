@@ -18,6 +18,8 @@
 // Replaces nn.Conv2d(+bias) -> nn.LeakyReLU -> (batch statistics of) nn.BatchNorm2d of
 // atomai/nets/blocks.py:61-76,302-319, the preceding BatchNorm2d/max_pool2d/cat passes
 // (normalise-on-load, atomai/nets/fcnn.py:123-138) and, with flipped weights, autograd's dgrad.
+#include <cstdio>
+#include <cstdlib>
 #include "common.cuh"
 
 namespace {
@@ -27,7 +29,8 @@ constexpr int kTileW = 8;
 constexpr int kNumEpiWarps = 4;
 constexpr int kMmaWarp = 4;
 constexpr int kWgtWarp = 5;
-constexpr int kMmaWarp2 = 6;          // second issuing thread (resident-weight layers only)
+constexpr int kMmaWarp2 = 6;          // second issuing thread
+constexpr int kWgtWarp2 = 7;          // second weight producer (streamed weights)
 constexpr int kFirstLoadWarp = 8;   // warps 6,7 idle: roles are aligned to 4-warp groups (setmaxnreg)
 constexpr int kNumLoadWarps = 8;
 constexpr int kThreads = (kFirstLoadWarp + kNumLoadWarps) * 32;  // 512 -> 128 regs/thread at launch
@@ -35,7 +38,7 @@ constexpr int kThreads = (kFirstLoadWarp + kNumLoadWarps) * 32;  // 512 -> 128 r
 constexpr int kRegsEpi = 112, kRegsMma = 72, kRegsLoad = 160;
 static_assert(kRegsEpi + kRegsMma + 2 * kRegsLoad <= 512, "register budget");
 constexpr int kMaxAStages = 4;
-constexpr int kMaxBStages = 12;
+constexpr int kMaxBStages = 32;     // streamed weights: bytes in flight must cover the L2 latency
 constexpr int kGroupThreads = 128;  // loader threads per group (2 groups of 4 warps)
 constexpr int kMaxU = 12;           // register-staged 16B elements per loader thread per chunk
 
@@ -58,7 +61,8 @@ struct ConvTcParams {
   int plane_bytes;   // stride between 4-channel planes (== 128/P mod 128 -> conflict-free STS)
   int a_stage_bytes, b_stage_bytes;
   int n_a, n_b;      // pipeline depths
-  int tmem_cols;     // power of two >= (2 or 4 accumulator buffers)*sub*Cout
+  int n_acc;         // TMEM accumulator buffers: 4 (two per pipeline) or 2 (one per pipeline)
+  int tmem_cols;     // power of two >= n_acc*sub*Cout
   int sub;           // 8-pixel-wide sub-tiles per CTA tile (1 or 2): M = 128*sub per weight stage
   int w_resident;    // 1: all weights live in shared memory for the whole kernel
   int w_bytes;       // taps * Ctot * Cout * 4
@@ -102,16 +106,20 @@ __device__ __forceinline__ void mma_issue_loop(const ConvTcParams& p, SharedCtl*
     mbar_wait(smem_u32(&ctl->w_full), 0);
     tc_fence_after();
   }
-  // Resident-weight (thin, issue-bound) layers run two independent pipelines: loader group i ->
-  // issuing thread i -> TMEM accumulator i, on the CTA's tiles with local index = i (mod 2), each
-  // with its own half of the activation-stage ring (a stage barrier must have ONE consumer, or a
-  // fast consumer aliases the parity of a phase the other one has not seen yet).
-  const uint32_t n_iss = RESIDENT ? 2u : 1u;
-  // TMEM accumulators: 2 (streamed weights) or 4 (two per pipeline) buffers, tile t -> t mod n
-  const uint32_t n_acc = RESIDENT ? 4u : 2u;
+  // Two independent pipelines per CTA: loader group i -> issuing thread i -> TMEM accumulators
+  // {i, i+2}, on the CTA's tiles with local index = i (mod 2), each with its own half of the
+  // activation-stage ring and (streamed weights) its own weight ring fed by its own producer
+  // thread.  One issuing thread costs ~150 clocks per MMA in the streamed loop (barrier wait,
+  // descriptor moves, commit) against 40-64 clocks of tensor-pipe time, so a single issuer left
+  // the pipe two-thirds idle.  A stage barrier must have ONE consumer: with a shared ring a fast
+  // consumer aliases the parity of a phase the other one has not seen yet.
+  const uint32_t n_iss = 2u;
+  const uint32_t n_acc = p.n_acc;
   uint32_t tl = issuer;                                  // this issuer's running local tile index
-  const uint32_t ring_n = RESIDENT ? n_a / 2 : n_a;
-  const uint32_t ring0 = RESIDENT ? issuer * ring_n : 0u;
+  const uint32_t ring_n = n_a / 2;
+  const uint32_t ring0 = issuer * ring_n;
+  const uint32_t nb2 = n_b / 2;                          // weight stages of this pipeline's ring
+  const uint32_t b_ring0 = issuer * nb2;
   const int num_tiles = p.num_tiles;
   const int tile_step = gridDim.x * n_iss;
   for (int tile = blockIdx.x + issuer * gridDim.x; tile < num_tiles; tile += tile_step) {
@@ -131,9 +139,9 @@ __device__ __forceinline__ void mma_issue_loop(const ConvTcParams& p, SharedCtl*
         for (int tx = 0; tx < tw; ++tx, a_tap += dx16, b_tap += piece16) {
           uint32_t bd = b_tap;
           if (!RESIDENT) {
-            mbar_wait(bar_full_b + sb * 8, pb);
+            mbar_wait(bar_full_b + (b_ring0 + sb) * 8, pb);
             tc_fence_after();
-            bd = b_lo0 + sb * b_stage16;
+            bd = b_lo0 + (b_ring0 + sb) * b_stage16;
           }
           uint32_t ad = a_tap;
 #pragma unroll
@@ -143,8 +151,8 @@ __device__ __forceinline__ void mma_issue_loop(const ConvTcParams& p, SharedCtl*
             accum = 1u;
           }
           if (!RESIDENT) {
-            umma_commit(bar_empty_b + sb * 8);
-            if (++sb == n_b) { sb = 0; pb ^= 1; }
+            umma_commit(bar_empty_b + (b_ring0 + sb) * 8);
+            if (++sb == nb2) { sb = 0; pb ^= 1; }
           }
         }
       }
@@ -196,7 +204,7 @@ __device__ __forceinline__ void loader_loop(const ConvTcParams& p, SharedCtl* ct
   // Streamed weights: one pipeline, group g stages the chunks with (running counter & 1) == g.
   // Resident weights (dual pipelines): group g stages every chunk of the tiles with local index
   // = g (mod 2) into its own half of the stage ring.
-  const bool dual = p.w_resident != 0;
+  const bool dual = true;   // both weight modes run two pipelines (group g -> issuer g)
   const int ch_step = dual ? 1 : 2;
   const int tile_step = dual ? 2 * gridDim.x : gridDim.x;
   const uint32_t ring_n = dual ? n_a / 2 : n_a;
@@ -339,7 +347,7 @@ __device__ __forceinline__ void epilogue_loop(const ConvTcParams& p, SharedCtl* 
                                               uint32_t tmem_base, float* s_stats,
                                               const float* s_bias) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t n_acc = p.w_resident ? 4u : 2u;
+  const uint32_t n_acc = p.n_acc;
   uint32_t tl = 0;                                       // local tile counter -> accumulator buffer
   float* my_stats = s_stats + warp * 2 * p.Cout;
   const int row = warp * 32 + lane;
@@ -448,15 +456,16 @@ __device__ __forceinline__ void epilogue_loop(const ConvTcParams& p, SharedCtl* 
   }
 }
 
-static_assert(sizeof(SharedCtl) <= 640, "SharedCtl must fit below the statistics block at smem + 640");
+constexpr int kCtlBytes = 1024;     // SharedCtl, then the statistics / bias block
+static_assert(sizeof(SharedCtl) <= kCtlBytes, "SharedCtl must fit below the statistics block");
 
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   SharedCtl* ctl = reinterpret_cast<SharedCtl*>(smem);
-  float* s_stats = reinterpret_cast<float*>(smem + 640);  // [4 warps][2][Cout]
+  float* s_stats = reinterpret_cast<float*>(smem + kCtlBytes);  // [4 warps][2][Cout]
   const uint32_t stats_bytes = (kNumEpiWarps * 2 + 1) * p.Cout * sizeof(float);   // + bias copy
   float* s_bias = s_stats + kNumEpiWarps * 2 * p.Cout;
-  const uint32_t a_base = smem_u32(smem) + ((640 + stats_bytes + 127) & ~127u);
+  const uint32_t a_base = smem_u32(smem) + ((kCtlBytes + stats_bytes + 127) & ~127u);
   const uint32_t b_base = a_base + p.n_a * p.a_stage_bytes;
 
   const int warp = threadIdx.x >> 5;
@@ -510,8 +519,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
     }
   } else if (warp >= kNumEpiWarps) {
    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsMma));
-   if (warp == kWgtWarp) {
-    // ===================== weight producer =====================
+   if (warp == kWgtWarp || (warp == kWgtWarp2 && !p.w_resident)) {
+    // ===================== weight producer(s) =====================
     if (elect_one()) {
       if (p.w_resident) {
         // the packed blob is already in shared-memory order: copy it once, in 16 KB pieces
@@ -522,29 +531,32 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
           bulk_g2s(b_base + off, reinterpret_cast<const char*>(p.wblob) + off, n, bar);
         }
       } else {
+        // streamed: producer i (warp 5 / warp 7) feeds pipeline i's weight ring for its tiles
+        const int pipe = warp == kWgtWarp ? 0 : 1;
+        const uint32_t nb2 = p.n_b / 2, ring0 = pipe * nb2;
         uint32_t st = 0, ph = 1;
         const int ksteps = p.KC >> 3;
         const uint32_t piece = p.Cout * 32;  // bytes of one (k-step, tap) piece
-        const uint32_t n_b = p.n_b, b_stage = p.b_stage_bytes;
+        const uint32_t b_stage = p.b_stage_bytes;
         const uint32_t bar_full_b = smem_u32(&ctl->full_b[0]), bar_empty_b = smem_u32(&ctl->empty_b[0]);
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        for (int tile = blockIdx.x + pipe * gridDim.x; tile < p.num_tiles; tile += 2 * gridDim.x) {
           for (int ch = 0; ch < p.n_chunks; ++ch) {
             for (int t = 0; t < taps; ++t) {
-              mbar_wait(bar_empty_b + st * 8, ph);
-              const uint32_t bar = bar_full_b + st * 8;
+              mbar_wait(bar_empty_b + (ring0 + st) * 8, ph);
+              const uint32_t bar = bar_full_b + (ring0 + st) * 8;
               mbar_arrive_expect_tx(bar, b_stage);
               const float* src = p.wblob + ((size_t)ch * ksteps * taps + t) * (piece >> 2);
               for (int ks = 0; ks < ksteps; ++ks)
-                bulk_g2s(b_base + st * b_stage + ks * piece, src + (size_t)ks * taps * (piece >> 2),
-                         piece, bar);
-              if (++st == n_b) { st = 0; ph ^= 1; }
+                bulk_g2s(b_base + (ring0 + st) * b_stage + ks * piece,
+                         src + (size_t)ks * taps * (piece >> 2), piece, bar);
+              if (++st == nb2) { st = 0; ph ^= 1; }
             }
           }
         }
       }
     }
     __syncwarp();
-   } else if (warp == kMmaWarp || (warp == kMmaWarp2 && p.w_resident)) {
+   } else if (warp == kMmaWarp || warp == kMmaWarp2) {
     const int issuer = warp == kMmaWarp ? 0 : 1;
     // ===================== MMA issuer =====================
     // One elected thread issues every tcgen05.mma, so its instruction count per MMA bounds the
@@ -668,11 +680,15 @@ static int conv_tc_plan(const ab_conv_t* d, ConvTcParams* p, int* smem_bytes) {
   const int taps = d->ks_h * d->ks_w;
   p->w_bytes = taps * S.Ctot * d->Cout * 4;
   const int budget = 212 * 1024;
-  const int stats_bytes = (((kNumEpiWarps * 2 + 1) * d->Cout * 4 + 127) & ~127) + 640 + 128;
+  const int stats_bytes = (((kNumEpiWarps * 2 + 1) * d->Cout * 4 + 127) & ~127) + kCtlBytes + 128;
   // Try, in order of preference: (resident weights, 1 sub-tile), (streamed weights, 2 sub-tiles
   // so that every weight stage feeds M = 256), (streamed, 1 sub-tile).
+  // tuning hooks (bring-up only): ATOMAI_B200_PLAN="<attempt>,<KC>" pins the plan search
+  int force_attempt = -1, force_kc = 0;
+  if (const char* e = getenv("ATOMAI_B200_PLAN")) sscanf(e, "%d,%d", &force_attempt, &force_kc);
   bool ok = false;
   for (int attempt = 0; attempt < 3 && !ok; ++attempt) {
+    if (force_attempt >= 0 && attempt != force_attempt) continue;
     const int resident = attempt == 0;
     const int sub = attempt == 1 ? 2 : 1;
     if (sub == 2 && (4 * d->Cout > 512 || d->W <= kTileW)) continue;
@@ -683,6 +699,7 @@ static int conv_tc_plan(const ab_conv_t* d, ConvTcParams* p, int* smem_bytes) {
     p->HP = p->THp * p->TWp;
     for (int KC = pick_kc(S.Ctot); KC >= 8 && !ok; KC >>= 1) {
       if (S.Ctot % KC != 0) continue;
+      if (force_kc > 0 && KC != force_kc) continue;
       const int P = KC / 4;
       if (p->HP * P > kMaxU * kGroupThreads) continue;
       int plane = p->HP * 16;
@@ -695,16 +712,16 @@ static int conv_tc_plan(const ab_conv_t* d, ConvTcParams* p, int* smem_bytes) {
         avail -= (p->w_bytes + 127) & ~127;
       } else {
         // weight stages: cover ~1.5 us of L2 latency, leave room for >= 2 activation stages
-        n_b = (avail - 2 * a_stage) / b_stage;
+        n_b = ((avail - 2 * a_stage) / b_stage) & ~1;      // two rings of n_b/2 stages
         if (n_b > kMaxBStages) n_b = kMaxBStages;
-        if (n_b < 3) continue;
+        if (n_b < 4) continue;
         avail -= n_b * b_stage;
       }
       int na = avail / a_stage;
       if (na < 2) continue;
       p->KC = KC; p->plane_bytes = plane; p->a_stage_bytes = a_stage; p->b_stage_bytes = b_stage;
       p->n_a = na > kMaxAStages ? kMaxAStages : na;
-      if (resident) p->n_a &= ~1;   // two rings of n_a/2 stages
+      p->n_a &= ~1;   // two rings of n_a/2 stages
       p->n_b = n_b; p->sub = sub; p->w_resident = resident;
       ok = true;
     }
@@ -713,8 +730,9 @@ static int conv_tc_plan(const ab_conv_t* d, ConvTcParams* p, int* smem_bytes) {
   p->num_tiles = d->N * p->tiles_h * p->tiles_w;
   p->n_chunks = S.Ctot / p->KC;
   AB_CHECK(p->plane_bytes / 16 < (1 << 14) && p->TWp < (1 << 14), "conv_tc: descriptor overflow");
+  p->n_acc = 4 * p->sub * d->Cout <= 512 ? 4 : 2;
   int cols = 32;
-  while (cols < (p->w_resident ? 4 : 2) * p->sub * d->Cout) cols <<= 1;
+  while (cols < p->n_acc * p->sub * d->Cout) cols <<= 1;
   p->tmem_cols = cols;
   *smem_bytes = stats_bytes + p->n_a * p->a_stage_bytes +
                 (p->w_resident ? ((p->w_bytes + 127) & ~127) : p->n_b * p->b_stage_bytes);
