@@ -46,3 +46,15 @@ def transform_coordinates(coord: Union[np.ndarray, torch.Tensor],
     c, s = torch.cos(phi), torch.sin(phi)
     rot = torch.stack([torch.stack([c, s], 1), torch.stack([-s, c], 1)], 1)
     return torch.bmm(coord, rot) + coord_dx
+
+
+def remove_edge_coord(coordinates: np.ndarray, dim: Tuple, dist_edge: int) -> np.ndarray:
+    """Drops the coordinates closer than `dist_edge` to an image edge
+    (atomai/utils/coords.py:518-537; note the reference compares column 0 with the WIDTH and
+    column 1 with the HEIGHT — kept)."""
+    h, w = dim
+    c = np.asarray(coordinates)
+    if len(c) == 0:
+        return coordinates
+    bad = (c[:, 0] > w - dist_edge) | (c[:, 0] < dist_edge) | (c[:, 1] > h - dist_edge) | (c[:, 1] < dist_edge)
+    return c[~bad]

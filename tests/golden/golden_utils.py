@@ -75,3 +75,23 @@ def sample_flat(a: np.ndarray, stride: int = 97) -> np.ndarray:
 
 def load(name: str):
     return np.load(os.path.join(GOLDEN_DIR, name), allow_pickle=False)
+
+
+def subimage_inputs():
+    """Seeded inputs of the sub-image extraction goldens: a (3, 40, 36, 2) float32 stack with a few
+    NaNs, Locator-style coordinates {i: (N, 3)} with fractional, .5, edge and negative positions and
+    two classes, one 2-D image and an (N, 2) coordinate array for it."""
+    rs = np.random.RandomState(123)
+    stack = rs.rand(3, 40, 36, 2).astype(np.float32)
+    stack[1, 20, 20, 0] = np.nan
+    stack[2, 5, 30, 1] = np.nan
+    coords = {}
+    for i in range(3):
+        n = 60
+        xy = np.concatenate([rs.rand(n, 1) * 46 - 3, rs.rand(n, 1) * 42 - 3], axis=1)
+        xy[:6] = np.array([[3.5, 4.5], [2.5, 3.5], [0.0, 0.0], [39.0, 35.0], [-5.0, -6.0], [20.4, 20.6]])
+        cls = (rs.rand(n, 1) > 0.7).astype(np.float64)
+        coords[i] = np.concatenate([xy, cls], axis=1)
+    single = rs.rand(33, 31)
+    single_xy = np.concatenate([rs.rand(40, 1) * 33, rs.rand(40, 1) * 31], axis=1)
+    return stack, coords, single, single_xy
