@@ -1,3 +1,3 @@
-from .predictor import BasePredictor, Locator, SegPredictor
+from .predictor import BasePredictor, ImSpecPredictor, Locator, SegPredictor
 
-__all__ = ["BasePredictor", "SegPredictor", "Locator"]
+__all__ = ["BasePredictor", "SegPredictor", "ImSpecPredictor", "Locator"]

@@ -15,7 +15,7 @@ import torch.nn.functional as F
 from ..utils.coords import find_com
 from ..utils.img import cv_thresh, img_pad, img_resize
 from ..utils.nn import get_downsample_factor, get_nb_classes, set_train_rng
-from ..utils.preproc import torch_format_image
+from ..utils.preproc import torch_format_image, torch_format_spectra
 
 
 class BasePredictor:
@@ -155,6 +155,64 @@ class SegPredictor(BasePredictor):
                   "decoded in approximately " +
                   str(np.around(time.time() - start_time, decimals=4)) + ' seconds')
         return decoded_imgs, coordinates
+
+
+class ImSpecPredictor(BasePredictor):
+    """
+    Prediction with a trained im2spec / spec2im model (atomai/predictors/predictor.py:301-395).
+
+    Args:
+        trained_model: trained SignalED network
+        output_dim: (length,) for im2spec, (height, width) for spec2im
+        use_gpu: the native kernels need CUDA; the flag is kept for signature parity
+        **verbose (bool)
+
+    Example:
+        >>> prediction = ImSpecPredictor(trained_model, (16,), use_gpu=True).run(data)
+    """
+    def __init__(self, trained_model: Type[torch.nn.Module], output_dim: Tuple[int],
+                 use_gpu: bool = False, **kwargs: str) -> None:
+        super(ImSpecPredictor, self).__init__(trained_model, use_gpu)
+        if isinstance(output_dim, int):
+            output_dim = (output_dim,)
+        if len(output_dim) not in [1, 2]:
+            raise ValueError("output_dim must be a two-value tuple for images" +
+                             " and a single-value tuple for spectra")
+        set_train_rng(1)
+        self.output_dim = output_dim
+        self.verbose = kwargs.get("verbose", True)
+
+    def preprocess(self, signal: np.ndarray, norm: bool = True) -> torch.Tensor:
+        """Adds the batch / channel axes and (optionally) scales to (0, 1)."""
+        if len(self.output_dim) == 1:
+            if signal.ndim == 2:
+                signal = signal[np.newaxis, ...]
+            signal = torch_format_image(signal, norm)
+        elif len(self.output_dim) == 2:
+            if signal.ndim == 1:
+                signal = signal[np.newaxis, ...]
+            signal = torch_format_spectra(signal, norm)
+        return signal
+
+    def predict(self, signal: np.ndarray, **kwargs: int) -> np.ndarray:
+        """Spectra from images or vice versa; **num_batches (default 10), **norm (default True)."""
+        signal = self.preprocess(signal, kwargs.get("norm", True))
+        num_batches = kwargs.get("num_batches", 10)
+        output = self.batch_predict(signal, (len(signal), 1, *self.output_dim), num_batches)
+        return output[:, 0].numpy()
+
+    def run(self, signal: np.ndarray, **kwargs: int) -> np.ndarray:
+        """predict + the reference's timing line."""
+        start_time = time.time()
+        prediction = self.predict(signal, **kwargs)
+        if self.verbose:
+            if len(self.output_dim) == 1:
+                str_ = " image was " if prediction.shape[0] == 1 else " images were "
+            else:
+                str_ = " spectrum was " if prediction.shape[0] == 1 else " spectra were "
+            print("\n" + str(prediction.shape[0]) + str_ + "decoded in approximately "
+                  + str(np.around(time.time() - start_time, decimals=4)) + ' seconds')
+        return prediction
 
 
 class Locator:
