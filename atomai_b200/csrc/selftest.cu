@@ -178,6 +178,73 @@ __global__ void __launch_bounds__(128, 1)
 }
 
 
+// Feasibility probe for the TMA-fed convolution planned in DESIGN.md §6.1 (not used by the hot
+// path, not part of the tested selftest group): K-major operands in the SWIZZLE_128B layout —
+// rows (pixels) at a 128 B pitch holding 32 TF32 channels, 16 B chunks XOR-ed with (row mod 8),
+// which is what cp.async.bulk.tensor writes for a {32 ch, W, H} box with CU_TENSOR_MAP_SWIZZLE_128B.
+// variant bit 0: "halo" addressing — the 8-row groups of A sit TWp = 18 rows apart (SBO = 2304 B)
+// and the start is shifted by (variant >> 1) & 7 rows, i.e. a convolution tap of a 16 x 8 tile.
+__device__ __forceinline__ uint32_t swz128_16(uint32_t a) { return a ^ (((a >> 7) & 7u) << 4); }
+
+__global__ void __launch_bounds__(128, 1)
+    selftest_sw128_kernel(const float* __restrict__ A, const float* __restrict__ B,
+                          float* __restrict__ D, int N, int K, int variant) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const bool halo = variant & 1;
+  const uint32_t shift = halo ? (variant >> 1) & 7 : 0;
+  const uint32_t TWp = 18;
+  const uint32_t base0 = (smem_u32(smem) + 1023) & ~1023u;
+  uint8_t* gen0 = smem - smem_u32(smem);                         // generic pointer of smem offset 0
+  const uint32_t a_blk = 48 * 1024;                              // bytes between 32-wide k blocks of A
+  const uint32_t b0 = base0 + 2 * a_blk, b_blk = 32 * 1024;
+  const uint32_t a_sbo = halo ? TWp * 128 : 1024;
+  for (int i = tid; i < 128 * K; i += 128) {                     // A[m][k]
+    const int m = i / K, k = i % K;
+    const uint32_t row = halo ? (uint32_t)(m / 8) * TWp + (m % 8) + shift : (uint32_t)m;
+    const uint32_t la = base0 + (k / 32) * a_blk + row * 128 + (k % 32) * 4;
+    *reinterpret_cast<float*>(gen0 + swz128_16(la)) = to_tf32(A[i]);
+  }
+  for (int i = tid; i < N * K; i += 128) {                       // B[n][k]
+    const int n = i / K, k = i % K;
+    const uint32_t la = b0 + (k / 32) * b_blk + n * 128 + (k % 32) * 4;
+    *reinterpret_cast<float*>(gen0 + swz128_16(la)) = to_tf32(B[i]);
+  }
+  if (tid == 0) { mbar_init(smem_u32(&bar), 1); fence_barrier_init(); }
+  if (warp == 0) tmem_alloc(smem_u32(&tmem_base_s), 256);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  if (tid == 0) {
+    const uint32_t idesc = umma_idesc_tf32(128, N, 0, 0);
+    for (int ks = 0; ks < K / 8; ++ks) {
+      // one MMA = 8 k = 32 B of every row: advance the start address inside the 128 B row
+      const uint32_t sa = base0 + (ks / 4) * a_blk + shift * 128 + (ks % 4) * 32;
+      const uint32_t sb = b0 + (ks / 4) * b_blk + (ks % 4) * 32;
+      const uint64_t ad = umma_desc_ex(sa, 16, a_sbo, 2, 0);     // layout_type 2 = SWIZZLE_128B
+      const uint64_t bd = umma_desc_ex(sb, 16, 1024, 2, 0);
+      umma_tf32(tmem_base, ad, bd, idesc, ks > 0 ? 1u : 0u);
+    }
+    umma_commit(smem_u32(&bar));
+  }
+  __syncwarp();
+  mbar_wait(smem_u32(&bar), 0);
+  tc_fence_after();
+  for (int c0 = 0; c0 < N; c0 += 16) {
+    float v[16];
+    tmem_ld16(tmem_base + c0 + ((uint32_t)(warp * 32) << 16), v);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) D[tid * N + c0 + i] = v[i];
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, 256); }
+}
+
 // Issue-rate probe: `issuers` elected threads (one per warp) each issue `iters` back-to-back
 // tcgen05.mma (M = 128, N, K = 8, TF32) on resident shared-memory operands and commit; reports
 // the elapsed SM clocks.  layout 0 = K-major no-swizzle (conv_tc), 1 = MN-major SW128_32B
@@ -260,6 +327,18 @@ extern "C" int atomai_b200_umma_rate(int N, int layout, int issuers, int iters, 
   const int smem = 100 * 1024;
   AB_CUDA(cudaFuncSetAttribute(umma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   umma_rate_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(N, layout, issuers, iters, 1, out);
+  AB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int atomai_b200_selftest_sw128(const float* A, const float* B, float* D, int N, int K,
+                                          int variant, void* stream) {
+  AB_CHECK(N % 16 == 0 && N >= 16 && N <= 256 && K % 32 == 0 && K >= 32 && K <= 64,
+           "selftest_sw128: N=%d K=%d out of range", N, K);
+  const int smem = 200 * 1024;
+  AB_CUDA(cudaFuncSetAttribute(selftest_sw128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               smem));
+  selftest_sw128_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(A, B, D, N, K, variant);
   AB_LAUNCH_CHECK();
   return 0;
 }

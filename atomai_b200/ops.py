@@ -255,5 +255,9 @@ def gram(x1, x2, inv_ls, outputscale, kind, out) -> None:
                                  kind, ptr(out), out.stride(0), stream_ptr()))
 
 
+def selftest_sw128(A, B, D, N, K, variant) -> None:
+    check(lib().atomai_b200_selftest_sw128(ptr(A), ptr(B), ptr(D), N, K, variant, stream_ptr()))
+
+
 def selftest_umma(A, B, D, N, K, variant) -> None:
     check(lib().atomai_b200_selftest_umma(ptr(A), ptr(B), ptr(D), N, K, variant, stream_ptr()))

@@ -227,6 +227,11 @@ int atomai_b200_selftest_umma(const float* A, const float* B, float* D, int N, i
  * MMAs on resident operands; out[2*i] = SM clocks to issue, out[2*i+1] = clocks until retired.
  * layout 0 = K-major no-swizzle (conv), 1 = MN-major SWIZZLE_128B_BASE32B (wgrad). */
 int atomai_b200_umma_rate(int N, int layout, int issuers, int iters, long long* out, void* stream);
+/* K-major SWIZZLE_128B operand probe (dev only; feasibility of TMA-written activation tiles with
+ * tap-shifted starts): D[128][N] = A[128][K] * B[N][K]^T, K in {32, 64};
+ * variant bit 0 = halo addressing (8-row groups 18 rows apart), bits 1-3 = row shift. */
+int atomai_b200_selftest_sw128(const float* A, const float* B, float* D, int N, int K,
+                               int variant, void* stream);
 
 #ifdef __cplusplus
 }

@@ -9,7 +9,7 @@ import traceback
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-GROUPS = ["selftest", "simt", "tc_basic", "tc_fused", "tc_dgrad", "dgrad_diag", "wgrad_simt", "wgrad_tc",
+GROUPS = ["selftest", "selftest_next", "simt", "tc_basic", "tc_fused", "tc_dgrad", "dgrad_diag", "wgrad_simt", "wgrad_tc",
           "elementwise", "vae", "bigshape"]
 
 
@@ -136,6 +136,15 @@ def run_group(name):
                 ops.selftest_umma(Xin, Bt.contiguous(), D, N, K, 32 + stack)
                 torch.cuda.synchronize()
                 res[f"stack{stack}_N{N}_K{K}"] = {"rel": rel(D, ref)}
+    elif name == "selftest_next":
+        # feasibility probes for the next round (not asserted by the test-suite): K-major SWIZZLE_128B
+        for variant in [0] + [1 + 2 * sh for sh in range(8)]:
+            for (N, K) in [(32, 32), (64, 64), (128, 64)]:
+                A = rnd(128, K); B = rnd(N, K)
+                D = torch.zeros(128, N, device=dev)
+                ops.selftest_sw128(A.contiguous(), B.contiguous(), D, N, K, variant)
+                torch.cuda.synchronize()
+                res[f"sw128_v{variant}_N{N}_K{K}"] = {"rel": rel(D, A @ B.t())}
     elif name == "simt":
         M = ops.MATH_FP32
         conv_case("c1_1to16", M, 2, 40, 48, [1], 16)
