@@ -255,6 +255,12 @@ def gram(x1, x2, inv_ls, outputscale, kind, out) -> None:
                                  kind, ptr(out), out.stride(0), stream_ptr()))
 
 
+def selftest_tma(x, c0, w0, h0, n0, TWp, THp, swizzle_mode, smem_offset, out) -> None:
+    N, H, W, Cc = x.shape
+    check(lib().atomai_b200_selftest_tma(ptr(x), N, H, W, Cc, c0, w0, h0, n0, TWp, THp, swizzle_mode,
+                                         smem_offset, ptr(out), stream_ptr()))
+
+
 def selftest_sw128(A, B, D, N, K, variant) -> None:
     check(lib().atomai_b200_selftest_sw128(ptr(A), ptr(B), ptr(D), N, K, variant, stream_ptr()))
 

@@ -232,6 +232,13 @@ int atomai_b200_umma_rate(int N, int layout, int issuers, int iters, long long* 
  * variant bit 0 = halo addressing (8-row groups 18 rows apart), bits 1-3 = row shift. */
 int atomai_b200_selftest_sw128(const float* A, const float* B, float* D, int N, int K,
                                int variant, void* stream);
+/* TMA probe (dev only): one cp.async.bulk.tensor of a {32 ch, TWp, THp, 1} box at (c0, w0, h0, n0)
+ * of an NHWC fp32 tensor (out-of-range coordinates are zero-filled) into shared memory at
+ * `smem_offset` past a 1024 B boundary, swizzle_mode 0 none / 1 32B / 2 64B / 3 128B /
+ * 4 128B_ATOM_32B; `out` receives the raw shared-memory image (TWp*THp*32 floats). */
+int atomai_b200_selftest_tma(const float* x, int N, int H, int W, int C, int c0, int w0, int h0,
+                             int n0, int TWp, int THp, int swizzle_mode, int smem_offset,
+                             float* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -145,6 +145,27 @@ def run_group(name):
                 ops.selftest_sw128(A.contiguous(), B.contiguous(), D, N, K, variant)
                 torch.cuda.synchronize()
                 res[f"sw128_v{variant}_N{N}_K{K}"] = {"rel": rel(D, A @ B.t())}
+        # TMA box load of an NHWC halo tile: zero fill outside the image, swizzle = f(absolute address)
+        x = rnd(2, 24, 20, 32)
+        TWp, THp = 10, 6
+        for mode, chunk, mask in [(0, 16, 0), (3, 16, 7), (4, 32, 3)]:
+            for off in (0, 128, 384):
+                for (w0, h0) in [(3, 4), (-1, -1), (15, 20)]:
+                    out = torch.full((THp * TWp * 32,), float("nan"), device=dev)
+                    ops.selftest_tma(x, 0, w0, h0, 1, TWp, THp, mode, off, out)
+                    torch.cuda.synchronize()
+                    exp = torch.zeros(THp, TWp, 32, device=dev)
+                    for hh in range(THp):
+                        for ww in range(TWp):
+                            gh, gw = h0 + hh, w0 + ww
+                            if 0 <= gh < 24 and 0 <= gw < 20:
+                                exp[hh, ww] = x[1, gh, gw]
+                    img = torch.zeros(THp * TWp * 32, device=dev)
+                    byte = torch.arange(THp * TWp * 32, device=dev) * 4
+                    absb = byte + off
+                    sw = absb ^ (((absb >> 7) & mask) * chunk) if mask else absb
+                    img[((sw - off) // 4).long()] = exp.reshape(-1)
+                    res[f"tma_m{mode}_off{off}_{w0}_{h0}"] = {"rel": float((out - img).abs().max())}
     elif name == "simt":
         M = ops.MATH_FP32
         conv_case("c1_1to16", M, 2, 40, 48, [1], 16)
