@@ -23,6 +23,7 @@ ACT_LRELU = 0
 ACT_TANH = 1
 MATH_FP32 = 0
 MATH_TF32 = 1
+MATH_TF32X3 = 2
 WMODE_FWD = 0
 WMODE_DGRAD = 1
 

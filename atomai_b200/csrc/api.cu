@@ -7,9 +7,9 @@
 
 // implemented in conv_tc.cu / conv_simt.cu / wgrad_tc.cu
 int ab_conv_tc_supported(const ab_conv_t* d);
-int64_t ab_pack_weights_tc_elems(int Cout, int Cin, int th, int tw, int mode);
-int ab_pack_weights_tc(const float* w, int Cout, int Cin, int th, int tw, int mode, float* out,
-                       cudaStream_t stream);
+int64_t ab_pack_weights_tc_elems(int Cout, int Cin, int th, int tw, int mode, int x3);
+int ab_pack_weights_tc(const float* w, int Cout, int Cin, int th, int tw, int mode, int x3,
+                       float* out, cudaStream_t stream);
 int ab_conv_tc_fwd(const ab_conv_t* d, const float* wblob, const float* bias, float* y, int ld_y,
                    double* stats, cudaStream_t stream);
 int ab_conv_tc_info(const ab_conv_t* d, int* grid, int* block, int* smem_bytes);
@@ -87,7 +87,8 @@ int atomai_b200_device_ok(int device) {
 }
 
 int64_t atomai_b200_prep_weights_elems(int Cout, int Cin, int ks_h, int ks_w, int mode, int math) {
-  if (math == AB_MATH_TF32) return ab_pack_weights_tc_elems(Cout, Cin, ks_h, ks_w, mode);
+  if (math == AB_MATH_TF32 || math == AB_MATH_TF32X3)
+    return ab_pack_weights_tc_elems(Cout, Cin, ks_h, ks_w, mode, math == AB_MATH_TF32X3);
   return (int64_t)Cout * Cin * ks_h * ks_w;
 }
 
@@ -95,8 +96,9 @@ int atomai_b200_prep_weights(const float* w_oihw, int Cout, int Cin, int ks_h, i
                              int math, float* out, void* stream) {
   AB_CHECK(w_oihw && out, "prep_weights: null pointer");
   AB_CHECK(mode == AB_WMODE_FWD || mode == AB_WMODE_DGRAD, "prep_weights: mode=%d", mode);
-  if (math == AB_MATH_TF32)
-    return ab_pack_weights_tc(w_oihw, Cout, Cin, ks_h, ks_w, mode, out, (cudaStream_t)stream);
+  if (math == AB_MATH_TF32 || math == AB_MATH_TF32X3)
+    return ab_pack_weights_tc(w_oihw, Cout, Cin, ks_h, ks_w, mode, math == AB_MATH_TF32X3, out,
+                              (cudaStream_t)stream);
   return ab_pack_weights_simt(w_oihw, Cout, Cin, ks_h, ks_w, mode, out, (cudaStream_t)stream);
 }
 
@@ -104,7 +106,7 @@ int atomai_b200_conv_fwd(const ab_conv_t* d, const float* w_prepped, const float
                          int ld_y, double* stats, void* stream) {
   AB_CHECK(d && w_prepped && y, "conv_fwd: null pointer");
   AB_CHECK(d->out_nchw || ld_y >= d->Cout, "conv_fwd: ld_y=%d < Cout=%d", ld_y, d->Cout);
-  if (d->math == AB_MATH_TF32) {
+  if (d->math == AB_MATH_TF32 || d->math == AB_MATH_TF32X3) {
     AB_CHECK(ab_conv_tc_supported(d),
              "conv_fwd: shape not supported by the tcgen05 path (need C%%8==0, Cout%%16==0, "
              "16<=Cout<=256, 16B-aligned sources); use AB_MATH_FP32");
@@ -121,7 +123,8 @@ int atomai_b200_conv_supported(const ab_conv_t* d, int which) {
 
 int atomai_b200_conv_info(const ab_conv_t* d, int* grid, int* block, int* smem_bytes) {
   AB_CHECK(d && grid && block && smem_bytes, "conv_info: null pointer");
-  AB_CHECK(d->math == AB_MATH_TF32 && ab_conv_tc_supported(d), "conv_info: tcgen05 path only");
+  AB_CHECK((d->math == AB_MATH_TF32 || d->math == AB_MATH_TF32X3) && ab_conv_tc_supported(d),
+           "conv_info: tcgen05 path only");
   return ab_conv_tc_info(d, grid, block, smem_bytes);
 }
 
@@ -129,7 +132,7 @@ int atomai_b200_conv_wgrad(const ab_conv_t* d, const float* dy, int ld_dy, float
                            void* stream) {
   AB_CHECK(d && dy && dw_oihw, "conv_wgrad: null pointer");
   AB_CHECK(ld_dy >= d->Cout, "conv_wgrad: ld_dy=%d < Cout=%d", ld_dy, d->Cout);
-  if (d->math == AB_MATH_TF32) {
+  if (d->math == AB_MATH_TF32 || d->math == AB_MATH_TF32X3) {
     AB_CHECK(ab_wgrad_tc_supported(d), "conv_wgrad: shape not supported by the tcgen05 path");
     return ab_conv_tc_wgrad(d, dy, ld_dy, dw_oihw, (cudaStream_t)stream);
   }

@@ -65,7 +65,8 @@ struct ConvTcParams {
   int tmem_cols;     // power of two >= n_acc*sub*Cout
   int sub;           // 8-pixel-wide sub-tiles per CTA tile (1 or 2): M = 128*sub per weight stage
   int w_resident;    // 1: all weights live in shared memory for the whole kernel
-  int w_bytes;       // taps * Ctot * Cout * 4
+  int w_bytes;       // taps * Ctot * Cout * 4  (x3: twice that — hi and lo parts)
+  int x3;            // AB_MATH_TF32X3: every k-chunk runs three passes (a_hi*w_hi, a_lo*w_hi, a_hi*w_lo)
 };
 
 struct __align__(8) SharedCtl {
@@ -96,8 +97,12 @@ __device__ __forceinline__ void mma_issue_loop(const ConvTcParams& p, SharedCtl*
   const uint32_t dx16 = p.dil, dy16 = (uint32_t)p.dil * p.TWp;     // tap steps of A (16 B units)
   const int th = p.taps_h, tw = p.taps_w, taps = th * tw;
   // resident weights: piece index = (chunk*KSTEPS + ks)*taps + t
-  const uint32_t b_ks16 = RESIDENT ? (uint32_t)taps * piece16 : piece16;
-  const uint32_t chunk_w16 = (uint32_t)(KSTEPS * taps) * piece16;
+  // (x3: the blob interleaves a hi and a lo piece set per k-step, see pack_weights_tc_kernel)
+  const uint32_t wmult = p.x3 ? 2u : 1u;
+  const uint32_t b_ks16 = RESIDENT ? wmult * (uint32_t)taps * piece16 : piece16;
+  const uint32_t chunk_w16 = wmult * (uint32_t)(KSTEPS * taps) * piece16;
+  const uint32_t lo_w16 = (uint32_t)taps * piece16;                // lo piece set of a k-step
+  const uint32_t n_pass = p.x3 ? 3u : 1u;
   uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
   const uint32_t bar_full_a = smem_u32(&ctl->full_a[0]), bar_empty_a = smem_u32(&ctl->empty_a[0]);
   const uint32_t bar_full_b = smem_u32(&ctl->full_b[0]), bar_empty_b = smem_u32(&ctl->empty_b[0]);
@@ -129,11 +134,12 @@ __device__ __forceinline__ void mma_issue_loop(const ConvTcParams& p, SharedCtl*
     const uint32_t d_tmem = tmem_base + a_ * SUB * cout;
     uint32_t accum = 0u;
     uint32_t b_tap = b_lo0;                                        // resident: running piece
-    for (uint32_t ch = 0; ch < n_chunks; ++ch) {
+    for (uint32_t ch = 0; ch < n_chunks; ++ch)
+     for (uint32_t ps = 0; ps < n_pass; ++ps) {
       mbar_wait(bar_full_a + (ring0 + sa) * 8, pa);
       tc_fence_after();
       uint32_t a_row = a_lo0 + (ring0 + sa) * a_stage16;
-      if (RESIDENT) b_tap = b_lo0 + ch * chunk_w16;
+      if (RESIDENT) b_tap = b_lo0 + ch * chunk_w16 + (ps == 2 ? lo_w16 : 0u);
       for (int ty = 0; ty < th; ++ty, a_row += dy16) {
         uint32_t a_tap = a_row;
         for (int tx = 0; tx < tw; ++tx, a_tap += dx16, b_tap += piece16) {
@@ -210,12 +216,18 @@ __device__ __forceinline__ void loader_loop(const ConvTcParams& p, SharedCtl* ct
   const uint32_t ring_n = dual ? n_a / 2 : n_a;
   const uint32_t ring0 = dual ? grp * ring_n : 0u;
   int tile = dual ? blockIdx.x + grp * gridDim.x : blockIdx.x;
+  // x3: chunk counter `ch` runs over (real chunk, pass) pairs; pass 1 stages the low part
+  // a - rn_tf32(a) of the activations (exact in fp32), passes 0 and 2 the high part.
+  const int n_pass = p.x3 ? 3 : 1;
+  const int n_chunks_eff = n_chunks * n_pass;
   int ch = dual ? 0 : grp;
   uint32_t st = dual ? 0u : grp % n_a;
   uint32_t ph = dual ? 1u : ((grp / n_a) & 1) ^ 1;   // stage / empty-phase of the current chunk
   for (;;) {
-    while (ch >= n_chunks) { ch -= n_chunks; tile += tile_step; }
+    while (ch >= n_chunks_eff) { ch -= n_chunks_eff; tile += tile_step; }
     if (tile >= p.num_tiles) break;
+    const int ch_real = p.x3 ? ch / 3 : ch;
+    const bool lo_pass = p.x3 && (ch - 3 * ch_real) == 1;
     // tile -> (n, th_i, tw_i) without integer division
     int n = __float2int_rz((float)tile * inv_tpi);
     n += ((n + 1) * tpi <= tile) - (n * tpi > tile);
@@ -225,7 +237,7 @@ __device__ __forceinline__ void loader_loop(const ConvTcParams& p, SharedCtl* ct
     const int tw_i = rem - th_i * p.tiles_w;
     const int h_org = th_i * kTileH - p.dil * (p.taps_h >> 1);
     const int w_org = tw_i * kTileW * p.sub - p.dil * (p.taps_w >> 1);
-    int c = ch * p.KC + j * 4;
+    int c = ch_real * p.KC + j * 4;
     const SrcDev* sp = &p.S.s[0];
     if (p.S.nsrc > 1 && c >= p.S.s[0].C) {
       sp = &p.S.s[1];
@@ -298,6 +310,15 @@ __device__ __forceinline__ void loader_loop(const ConvTcParams& p, SharedCtl* ct
         const float mw = fmaxf(fmaxf(fmaf(a0.w, sc.w, sh.w), fmaf(a1.w, sc.w, sh.w)),
                                fmaxf(fmaf(a2.w, sc.w, sh.w), fmaf(a3.w, sc.w, sh.w)));
         v[u] = make_float4(ok ? mx : 0.f, ok ? my : 0.f, ok ? mz : 0.f, ok ? mw : 0.f);
+      }
+    }
+    if (lo_pass) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        v[u].x -= __uint_as_float(tf32_bits(v[u].x) & 0xFFFFE000u);
+        v[u].y -= __uint_as_float(tf32_bits(v[u].y) & 0xFFFFE000u);
+        v[u].z -= __uint_as_float(tf32_bits(v[u].z) & 0xFFFFE000u);
+        v[u].w -= __uint_as_float(tf32_bits(v[u].w) & 0xFFFFE000u);
       }
     }
     mbar_wait(bar_empty_a + (ring0 + st) * 8, ph);
@@ -540,17 +561,22 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
         const uint32_t b_stage = p.b_stage_bytes;
         const uint32_t bar_full_b = smem_u32(&ctl->full_b[0]), bar_empty_b = smem_u32(&ctl->empty_b[0]);
         for (int tile = blockIdx.x + pipe * gridDim.x; tile < p.num_tiles; tile += 2 * gridDim.x) {
+          const int wmult = p.x3 ? 2 : 1, n_pass = p.x3 ? 3 : 1;
           for (int ch = 0; ch < p.n_chunks; ++ch) {
+           for (int ps = 0; ps < n_pass; ++ps) {
             for (int t = 0; t < taps; ++t) {
               mbar_wait(bar_empty_b + (ring0 + st) * 8, ph);
               const uint32_t bar = bar_full_b + (ring0 + st) * 8;
               mbar_arrive_expect_tx(bar, b_stage);
-              const float* src = p.wblob + ((size_t)ch * ksteps * taps + t) * (piece >> 2);
+              // piece (k-step s, kind, tap) of the blob lives at ((s*wmult + kind)*taps + tap)
+              const float* src = p.wblob +
+                  (((size_t)ch * ksteps * wmult + (ps == 2 ? 1 : 0)) * taps + t) * (piece >> 2);
               for (int ks = 0; ks < ksteps; ++ks)
                 bulk_g2s(b_base + (ring0 + st) * b_stage + ks * piece,
-                         src + (size_t)ks * taps * (piece >> 2), piece, bar);
+                         src + (size_t)ks * wmult * taps * (piece >> 2), piece, bar);
               if (++st == nb2) { st = 0; ph ^= 1; }
             }
+           }
           }
         }
       }
@@ -604,8 +630,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
 // piece is a ready-made UMMA K-major B operand for one tcgen05.mma (N rows x 8 k).
 //   FWD  : B[n = co][k = ci]            = W[co][ci][ty][tx]
 //   DGRAD: B[n = ci][k = co] (roles swap) = W[co][ci][Th-1-ty][Tw-1-tx]
+// x3 (AB_MATH_TF32X3): blob[k-step][kind (hi, lo)][tap][plane][n][4] with hi = rn_tf32(W) and
+// lo = rn_tf32(W - hi), so that a_hi*w_hi + a_lo*w_hi + a_hi*w_lo carries ~2^-21 relative error.
 __global__ void pack_weights_tc_kernel(const float* __restrict__ w, int Cout, int Cin, int th,
-                                       int tw, int mode, float* __restrict__ out,
+                                       int tw, int mode, int x3, float* __restrict__ out,
                                        int64_t total) {
   const int taps = th * tw;
   const int Nn = mode == AB_WMODE_FWD ? Cout : Cin;   // GEMM N (rows of B)
@@ -617,6 +645,8 @@ __global__ void pack_weights_tc_kernel(const float* __restrict__ w, int Cout, in
     const int nn = r % Nn; r /= Nn;
     const int j = r % 2; r /= 2;
     const int t = r % taps; r /= taps;
+    int kind = 0;
+    if (x3) { kind = r % 2; r /= 2; }
     const int ks = (int)r;
     const int k = ks * 8 + j * 4 + e;
     float v = 0.f;
@@ -628,7 +658,8 @@ __global__ void pack_weights_tc_kernel(const float* __restrict__ w, int Cout, in
         v = w[(((int64_t)k * Cin + nn) * th + (th - 1 - ty)) * tw + (tw - 1 - tx)];
       }
     }
-    out[i] = to_tf32(v);
+    const float hi = to_tf32(v);
+    out[i] = kind ? to_tf32(v - hi) : hi;
   }
 }
 
@@ -649,21 +680,21 @@ int ab_conv_tc_supported(const ab_conv_t* d) {
   return 1;
 }
 
-int64_t ab_pack_weights_tc_elems(int Cout, int Cin, int th, int tw, int mode) {
+int64_t ab_pack_weights_tc_elems(int Cout, int Cin, int th, int tw, int mode, int x3) {
   const int Nn = mode == AB_WMODE_FWD ? Cout : Cin;
   const int Kk = mode == AB_WMODE_FWD ? Cin : Cout;
-  return (int64_t)(Kk / 8) * th * tw * 8 * Nn;
+  return (int64_t)(Kk / 8) * th * tw * 8 * Nn * (x3 ? 2 : 1);
 }
 
-int ab_pack_weights_tc(const float* w, int Cout, int Cin, int th, int tw, int mode, float* out,
-                       cudaStream_t stream) {
+int ab_pack_weights_tc(const float* w, int Cout, int Cin, int th, int tw, int mode, int x3,
+                       float* out, cudaStream_t stream) {
   const int Kk = mode == AB_WMODE_FWD ? Cin : Cout;
   AB_CHECK(Kk % 8 == 0, "tf32 weight pack: K=%d not a multiple of 8", Kk);
-  const int64_t total = ab_pack_weights_tc_elems(Cout, Cin, th, tw, mode);
+  const int64_t total = ab_pack_weights_tc_elems(Cout, Cin, th, tw, mode, x3);
   const int threads = 256;
   const int blocks = (int)((total + threads - 1) / threads);
   pack_weights_tc_kernel<<<blocks > 4096 ? 4096 : blocks, threads, 0, stream>>>(
-      w, Cout, Cin, th, tw, mode, out, total);
+      w, Cout, Cin, th, tw, mode, x3, out, total);
   AB_LAUNCH_CHECK();
   return 0;
 }
@@ -678,7 +709,8 @@ static int conv_tc_plan(const ab_conv_t* d, ConvTcParams* p, int* smem_bytes) {
   p->act = d->act;
   p->out_nchw = d->out_nchw;
   const int taps = d->ks_h * d->ks_w;
-  p->w_bytes = taps * S.Ctot * d->Cout * 4;
+  p->x3 = d->math == AB_MATH_TF32X3 ? 1 : 0;
+  p->w_bytes = taps * S.Ctot * d->Cout * 4 * (p->x3 ? 2 : 1);
   const int budget = 212 * 1024;
   const int stats_bytes = (((kNumEpiWarps * 2 + 1) * d->Cout * 4 + 127) & ~127) + kCtlBytes + 128;
   // Try, in order of preference: (resident weights, 1 sub-tile), (streamed weights, 2 sub-tiles

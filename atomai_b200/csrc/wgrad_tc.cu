@@ -56,6 +56,7 @@ struct WgradTcParams {
   int fs;                // "fully stacked": Cout <= 32, the kernel rows ride on N (one MMA / halo row)
   int dpad;              // fs: zero rows in front of / behind the dy tile = (taps_h - 1) * dil
   int tmem_cols;
+  int x3;                // AB_MATH_TF32X3: every tile runs three passes (x_hi*dy_hi, x_lo*dy_hi, x_hi*dy_lo)
 };
 
 struct __align__(8) Ctl {
@@ -71,6 +72,13 @@ __device__ __forceinline__ void sts128u(uint32_t addr, uint32_t a, uint32_t b, u
 }
 // RN-to-TF32: the tensor core reads the upper 19 bits only (see conv_tc.cu tf32_bits)
 __device__ __forceinline__ uint32_t tf32b(float x) { return __float_as_uint(x) + 0x1000u; }
+// x3 operand part: the value itself (RN happens in tf32b) or its exact fp32 remainder x - rn_tf32(x)
+__device__ __forceinline__ float part(float x, bool lo) {
+  return lo ? x - __uint_as_float(tf32b(x) & 0xFFFFE000u) : x;
+}
+__device__ __forceinline__ float4 part4(float4 x, bool lo) {
+  return make_float4(part(x.x, lo), part(x.y, lo), part(x.z, lo), part(x.w, lo));
+}
 // exact e / P for e < 65536 (mul = ceil(2^32 / P), P >= 2)
 __device__ __forceinline__ uint32_t fdiv(uint32_t e, uint32_t P, uint32_t mul) {
   return P == 1 ? e : __umulhi(e, mul);
@@ -110,7 +118,13 @@ __device__ __forceinline__ void wgrad_loader(const WgradTcParams& p, Ctl* ctl, u
   const uint32_t d_row = d_rel + gt * 128, d_sw = (uint32_t)(gt & 3) << 5;
   const int d_r = gt >> 3, d_c = gt & 7;
   uint32_t st = grp % S, ph = ((grp / S) & 1) ^ 1;     // ring slot / empty-phase of this tile
-  for (int tile = t_begin + grp; tile < t_end; tile += n_groups) {
+  const int n_pass = p.x3 ? 3 : 1;
+  const uint32_t mul3 = fdiv_mul(3);
+  for (int vt = t_begin * n_pass + grp; vt < t_end * n_pass; vt += n_groups) {
+    // x3: virtual tile vt = 3 * tile + pass; pass 1 stages the low part of x, pass 2 of dy
+    const int tile = p.x3 ? (int)fdiv(vt, 3, mul3) : vt;
+    const int pass = vt - tile * n_pass;
+    const bool x_lo = pass == 1, d_lo = pass == 2;
     const uint32_t x0 = base + st * p.stage_bytes;
     const int n = (int)fdiv(tile, tpi, mulTpi);
     const int rem = tile - n * tpi;
@@ -152,6 +166,7 @@ __device__ __forceinline__ void wgrad_loader(const WgradTcParams& p, Ctl* ctl, u
                 x.x = fmaf(x.x, sc.x, sh.x); x.y = fmaf(x.y, sc.y, sh.y);
                 x.z = fmaf(x.z, sc.z, sh.z); x.w = fmaf(x.w, sc.w, sh.w);
               }
+              x = part4(x, x_lo);
               const uint32_t dst = (stacked ? row : row + (j >> 3) * p.x_chunk) +
                                    (((uint32_t)(j & 7) << 4) ^ sw);
               sts128u(dst, tf32b(x.x) & msk, tf32b(x.y) & msk, tf32b(x.z) & msk, tf32b(x.w) & msk);
@@ -164,7 +179,7 @@ __device__ __forceinline__ void wgrad_loader(const WgradTcParams& p, Ctl* ctl, u
           float4 v[4];
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            if (jb + k < PX) v[k] = load_src4(p.S, n, gh, gw, H, W, ci0 + (jb + k) * 4);
+            if (jb + k < PX) v[k] = part4(load_src4(p.S, n, gh, gw, H, W, ci0 + (jb + k) * 4), x_lo);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const int j = jb + k;
@@ -187,7 +202,7 @@ __device__ __forceinline__ void wgrad_loader(const WgradTcParams& p, Ctl* ctl, u
         float4 v[kJB];
 #pragma unroll
         for (int k = 0; k < kJB; ++k)
-          if (jb + k < PD) v[k] = __ldg(reinterpret_cast<const float4*>(db + (jb + k) * 4));
+          if (jb + k < PD) v[k] = part4(__ldg(reinterpret_cast<const float4*>(db + (jb + k) * 4)), d_lo);
 #pragma unroll
         for (int k = 0; k < kJB; ++k) {
           const int j = jb + k;
@@ -308,13 +323,14 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const WgradTcPara
       const uint32_t a_ty16 = (uint32_t)(p.dil * p.TWp) * 8;          // next kernel row
       const uint32_t a_hi = (uint32_t)(a_tmpl >> 32), b_hi = (uint32_t)(b_tmpl >> 32);
       uint32_t st = 0, ph = 0;
-      for (int tile = t_begin; tile < t_end; ++tile) {
+      const int n_pass = p.x3 ? 3 : 1;
+      for (int tile = t_begin * n_pass; tile < t_end * n_pass; ++tile) {
         mbar_wait(smem_u32(&ctl->full[st]), ph);
         tc_fence_after();
         const uint32_t x0 = base + st * p.stage_bytes, d0 = x0 + p.x_bytes;
         const uint32_t a0 = (uint32_t)a_tmpl + (x0 >> 4);
         const uint32_t b0 = (uint32_t)b_tmpl + (d0 >> 4);
-        uint32_t accum = tile > t_begin ? 1u : 0u;
+        uint32_t accum = tile > t_begin * n_pass ? 1u : 0u;
         if (p.fs) {
           // one MMA per halo row r: A = x row r (tx on M), B = dy rows r-(th-1-c)*dil (ty on N)
           uint32_t ad = a0, bd = b0;
@@ -362,11 +378,13 @@ int wgrad_plan(const ab_conv_t* d, WgradTcParams* p, int* smem_bytes) {
   if (ab_make_srcset(d, &p->S)) return 1;
   p->N = d->N; p->H = d->H; p->W = d->W; p->Cout = d->Cout; p->Cin = p->S.Ctot;
   p->taps_h = d->ks_h; p->taps_w = d->ks_w; p->dil = d->dil;
+  p->x3 = d->math == AB_MATH_TF32X3 ? 1 : 0;
   AB_CHECK(d->ks_w <= 4 && d->ks_h <= 4, "wgrad_tc: kernel %dx%d too large", d->ks_h, d->ks_w);
   p->tiles_h = (d->H + kTileH - 1) / kTileH;
   p->tiles_w = (d->W + kTileW - 1) / kTileW;
   p->num_tiles = d->N * p->tiles_h * p->tiles_w;
-  AB_CHECK((uint64_t)p->num_tiles * (uint64_t)(p->tiles_h * p->tiles_w) < (1ull << 32),
+  AB_CHECK((uint64_t)p->num_tiles * (uint64_t)(p->tiles_h * p->tiles_w) < (1ull << 32) &&
+               (uint64_t)p->num_tiles * 9 < (1ull << 32),
            "wgrad_tc: too many tiles");
   p->THp = kTileH + d->dil * (d->ks_h - 1);
   p->TWp = kTileW + d->dil * (d->ks_w - 1);

@@ -16,21 +16,29 @@ from typing import List, Optional, Sequence, Union
 import torch
 
 from . import ops
-from .ops import ACT_LRELU, ACT_TANH, MATH_FP32, MATH_TF32, Source
+from .ops import ACT_LRELU, ACT_TANH, MATH_FP32, MATH_TF32, MATH_TF32X3, Source
 
 _MATH = {"mode": MATH_TF32, "wgrad_tc": True}
 
 
+_MODES = {"fp32": MATH_FP32, "tf32": MATH_TF32, "tf32x3": MATH_TF32X3}
+
+
 def set_math(mode: str = "tf32", wgrad_tc: Optional[bool] = None) -> None:
-    """'tf32' (tcgen05 tensor cores, default) or 'fp32' (exact FFMA kernels)."""
-    assert mode in ("tf32", "fp32")
-    _MATH["mode"] = MATH_TF32 if mode == "tf32" else MATH_FP32
+    """Arithmetic of the convolution family:
+      'tf32'   tcgen05 tensor cores, operands RN-rounded to TF32 (what stock PyTorch/cuDNN does by
+               default on CUDA); ~1e-3 relative on the logits of a 17-layer Unet;
+      'tf32x3' the same kernels with every operand split into a TF32 high and low part (three MMAs
+               per product, fp32 accumulate): matches the reference's fp32 CPU results to ~1e-6;
+      'fp32'   exact FFMA (CUDA-core) kernels."""
+    assert mode in _MODES, f"math mode must be one of {sorted(_MODES)}"
+    _MATH["mode"] = _MODES[mode]
     if wgrad_tc is not None:
         _MATH["wgrad_tc"] = bool(wgrad_tc)
 
 
 def get_math() -> str:
-    return "tf32" if _MATH["mode"] == MATH_TF32 else "fp32"
+    return {v: k for k, v in _MODES.items()}[_MATH["mode"]]
 
 
 class Act:
@@ -113,8 +121,8 @@ class Tape:
         return Act(x_nhwc, needs_grad=needs_grad)
 
     def _math_for(self, srcs: Sequence[Act], cout: int) -> int:
-        if _MATH["mode"] == MATH_TF32 and ops.tc_supported([s.source() for s in srcs], cout):
-            return MATH_TF32
+        if _MATH["mode"] != MATH_FP32 and ops.tc_supported([s.source() for s in srcs], cout):
+            return _MATH["mode"]
         return MATH_FP32
 
     def _add_pgrad(self, p, g: torch.Tensor) -> None:
@@ -212,10 +220,13 @@ class Tape:
             assert dy is not None, "BatchNorm output has no gradient"
             sums = torch.zeros(2 * cout, device=dev, dtype=torch.float64)
             ops.bn_bwd_reduce(dy, a, r.mean, r.invstd, sums)
-            if self.comm is not None:
-                self.comm.allreduce_sum_(sums)
+            # gamma/beta gradients come from the LOCAL sums (the gradient bucket sums them over
+            # ranks like every other parameter, as torch's SyncBatchNorm does); only the dx
+            # formula needs the global sums.
             self._add_pgrad(r.bn.bias, sums[:cout].float())
             self._add_pgrad(r.bn.weight, sums[cout:].float())
+            if self.comm is not None:
+                self.comm.allreduce_sum_(sums)
         dpre = torch.empty((n, h, w, cout), device=dev, dtype=torch.float32)
         dbias = torch.zeros(cout, device=dev, dtype=torch.float64) if r.conv.bias is not None else None
         ops.bn_act_bwd(dy, a, r.mean, r.invstd, r.scale if r.bn is not None else None, sums,
@@ -230,7 +241,7 @@ class Tape:
         dw = torch.zeros((wt.shape[0], wt.shape[1], r.ks[0], r.ks[1]), device=dev,
                          dtype=torch.float32)
         dsc = ops.conv_desc(srcs_s, n, h, w, cout, r.ks, r.dil, 1.0, r.math)
-        if r.math == MATH_TF32 and not (_MATH["wgrad_tc"] and ops.conv_supported(dsc, 1)):
+        if r.math != MATH_FP32 and not (_MATH["wgrad_tc"] and ops.conv_supported(dsc, 1)):
             dsc.math = MATH_FP32
         ops.conv_wgrad(dsc, dpre, dw)
         self._add_pgrad(wt, dw)
@@ -238,7 +249,7 @@ class Tape:
         if r.needs_in_grad:
             ctot = wt.shape[1]
             dsrc = [Source(dpre)]
-            dmath = MATH_TF32 if (_MATH["mode"] == MATH_TF32 and ops.tc_supported(dsrc, ctot)) \
+            dmath = _MATH["mode"] if (_MATH["mode"] != MATH_FP32 and ops.tc_supported(dsrc, ctot)) \
                 else MATH_FP32
             wpd = ops.prep_weights(_w4(wt), ops.WMODE_DGRAD, dmath)
             dd = ops.conv_desc(dsrc, n, h, w, ctot, r.ks, r.dil, 1.0, dmath)

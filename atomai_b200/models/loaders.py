@@ -65,9 +65,15 @@ def load_vae_model(meta_dict):
     optimizer = meta.pop("optimizer", None)
     in_dim, latent_dim = meta.pop("in_dim"), meta.pop("latent_dim")
     meta.pop("coord", None)
-    cls = rVAE if coord == 3 else VAE
-    m = cls(in_dim, latent_dim, **meta)
+    # any non-zero coord is an rVAE; coord == 3 adds translation (atomai/models/loaders.py:163-195)
+    if coord:
+        meta.pop("translation", None)
+        m = rVAE(in_dim, latent_dim, translation=(coord == 3), **meta)
+    else:
+        m = VAE(in_dim, latent_dim, **meta)
     m.encoder_net.load_state_dict(enc)
+    m.encoder_net.eval()
     m.decoder_net.load_state_dict(dec)
+    m.decoder_net.eval()
     m.optim = optimizer
     return m

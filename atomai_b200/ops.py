@@ -13,7 +13,7 @@ from typing import Optional, Sequence, Tuple
 import torch
 
 from . import _C
-from ._C import (ACT_LRELU, ACT_TANH, MATH_FP32, MATH_TF32, WMODE_DGRAD, WMODE_FWD, check,
+from ._C import (ACT_LRELU, ACT_TANH, MATH_FP32, MATH_TF32, MATH_TF32X3, WMODE_DGRAD, WMODE_FWD, check,
                  lib, ptr, stream_ptr)
 
 
@@ -99,14 +99,41 @@ def prep_weights(w_oihw: torch.Tensor, mode: int, math: int) -> torch.Tensor:
     return out
 
 
+# Optional per-launch timing of the convolution family (bench.py's live roofline): a list that
+# receives (kernel, algorithmic FLOPs, algorithmic bytes, start event, end event) per launch.
+PROFILE = None
+
+
+def _conv_work(d: _C.Conv):
+    ctot = sum(d.src[i].C for i in range(d.nsrc))
+    pix = d.N * d.H * d.W
+    flops = 2.0 * pix * d.ks_h * d.ks_w * ctot * d.Cout
+    rd = sum(d.src[i].C * (4 if d.src[i].pool else 1) for i in range(d.nsrc))
+    return flops, 4.0 * pix * (rd + d.Cout)
+
+
+def _timed(kernel: str, d: _C.Conv, fn) -> None:
+    if PROFILE is None:
+        fn()
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    fn()
+    e1.record()
+    fl, by = _conv_work(d)
+    PROFILE.append((kernel, fl, by, e0, e1))
+
+
 def conv_fwd(d: _C.Conv, w_prepped, bias, out: torch.Tensor, stats=None) -> None:
     ld_y = d.Cout if d.out_nchw else _ld(out)
-    check(lib().atomai_b200_conv_fwd(C.byref(d), ptr(w_prepped), ptr(bias), ptr(out), ld_y,
-                                     ptr(stats), stream_ptr()))
+    _timed("conv_tc_kernel" if d.math != MATH_FP32 else "conv_simt",  d, lambda: check(
+        lib().atomai_b200_conv_fwd(C.byref(d), ptr(w_prepped), ptr(bias), ptr(out), ld_y,
+                                   ptr(stats), stream_ptr())))
 
 
 def conv_wgrad(d: _C.Conv, dy: torch.Tensor, dw_oihw: torch.Tensor) -> None:
-    check(lib().atomai_b200_conv_wgrad(C.byref(d), ptr(dy), _ld(dy), ptr(dw_oihw), stream_ptr()))
+    _timed("wgrad_tc_kernel" if d.math != MATH_FP32 else "wgrad_simt", d, lambda: check(
+        lib().atomai_b200_conv_wgrad(C.byref(d), ptr(dy), _ld(dy), ptr(dw_oihw), stream_ptr())))
 
 
 def bn_finalize(stats, count, gamma, beta, rmean, rvar, momentum, eps, training, scale, shift,

@@ -17,6 +17,21 @@ class FusedAdam(torch.optim.Optimizer):
         self._tables = {}
         self.grad_scale = 1.0    # set by the data-parallel trainer to 1/world_size
 
+    def __getstate__(self):
+        st = super().__getstate__()
+        st = dict(st)
+        st["_tables"] = {}        # device pointer tables are never valid in another process
+        return st
+
+    def __setstate__(self, state):
+        super().__setstate__(state)
+        self._tables = {}
+        self.__dict__.setdefault("grad_scale", 1.0)
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        self._tables = {}
+
     def __repr__(self):
         return super().__repr__().replace("FusedAdam", "Adam", 1)
 
@@ -41,7 +56,8 @@ class FusedAdam(torch.optim.Optimizer):
             steps = {int(self.state[p]["step"]) for p in ps}
             assert len(steps) == 1, "parameters of one group must share the step count"
             step = steps.pop() + 1
-            key = (gi, tuple((p.data_ptr(), p.grad.data_ptr()) for p in ps))
+            key = (gi, tuple((p.data_ptr(), p.grad.data_ptr(), self.state[p]["exp_avg"].data_ptr(),
+                              self.state[p]["exp_avg_sq"].data_ptr()) for p in ps))
             tab = self._tables.get(gi)
             if tab is None or tab[0] != key:
                 rows = []

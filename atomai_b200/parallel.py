@@ -62,6 +62,7 @@ class GradBucket:
             v = self.flat[off:off + p.numel()].view_as(p)
             self.views.append(v)
             off += p.numel()
+        self.post_scale = 1.0     # 1/world for optimizers that do not fold the averaging in
 
     def attach(self) -> None:
         """(Re)point every param.grad at its slice of the bucket (call after zero_grad())."""
@@ -76,6 +77,8 @@ class GradBucket:
 
     def allreduce(self, comm: Comm) -> None:
         comm.allreduce_any_(self.flat)
+        if self.post_scale != 1.0:
+            self.flat.mul_(self.post_scale)
 
 
 def init_distributed(backend: Optional[str] = None) -> Comm:

@@ -197,7 +197,9 @@ class BaseTrainer:
         (atomai/utils/preproc.py:170-201) — are copied on a side stream so that the transfer of
         cycle e+1 overlaps the kernels of cycle e; returns (tensors, event or None)."""
         f, t = self.dataloader(self.batch_idx_train[e], mode='train')
-        f_, t_ = self.dataloader(self.batch_idx_test[e], mode='test')
+        # the reference fetches the test batch after appending the train loss, i.e. its
+        # augmentation seed is one higher (atomai/trainers/trainer.py:239-246)
+        f_, t_ = self.dataloader(self.batch_idx_test[e], mode='test', _seed_offset=1)
         host = [x for x in (f, t, f_, t_) if isinstance(x, torch.Tensor) and not x.is_cuda]
         if not host or self.device != 'cuda':
             return (f, t, f_, t_), None
@@ -294,7 +296,7 @@ class BaseTrainer:
             if self.compute_accuracy:
                 print('Model (final state) accuracy:', np.around(running_acc_test / c, 4))
 
-    def dataloader(self, batch_num: int, mode: str = 'train') -> Tuple[torch.Tensor]:
+    def dataloader(self, batch_num: int, mode: str = 'train', _seed_offset: int = 0) -> Tuple[torch.Tensor]:
         """Picks one pre-chunked batch (atomai/trainers/trainer.py:326-342)."""
         if mode == 'test':
             features = self.X_test[batch_num][:self.batch_size]
@@ -304,7 +306,7 @@ class BaseTrainer:
             targets = self.y_train[batch_num][:self.batch_size]
         if self.augment_fn is not None:
             features, targets = self.augment_fn(
-                features, targets, seed=len(self.loss_acc["train_loss"]))
+                features, targets, seed=len(self.loss_acc["train_loss"]) + _seed_offset)
         return features, targets
 
     # ------------------------------------------------------------------ bookkeeping
@@ -403,9 +405,13 @@ class BaseTrainer:
                 raise ValueError(f"batch_size={batch_size} must be divisible by the number of "
                                  f"data-parallel ranks ({self.comm.world})")
 
+        data_was_set = False
         if not self.data_is_set or kwargs.get("overwrite_train_data", True):
             self.set_data(*train_data, memory_alloc=alloc)
-        if self.comm is not None and not self.full_epoch:
+            data_was_set = True
+        if self.comm is not None and not self.full_epoch and not data_was_set:
+            self.batch_size = batch_size // self.comm.world      # batches are already sharded
+        if self.comm is not None and not self.full_epoch and data_was_set:
             r, w = self.comm.rank, self.comm.world
             self.X_train, self.y_train = shard_batches(self.X_train, r, w), shard_batches(self.y_train, r, w)
             self.X_test, self.y_test = shard_batches(self.X_test, r, w), shard_batches(self.y_test, r, w)
@@ -435,8 +441,13 @@ class BaseTrainer:
                 self.optimizer = optimizer(params)
         if self.comm is not None:
             self._bucket = GradBucket(params)
+            # 1/world averaging: folded into the fused Adam kernel, or applied to the bucket for
+            # any other (user-supplied) optimizer
             if isinstance(self.optimizer, FusedAdam):
                 self.optimizer.grad_scale = 1.0 / self.comm.world
+                self._bucket.post_scale = 1.0
+            else:
+                self._bucket.post_scale = 1.0 / self.comm.world
         if self.criterion is None:
             self.criterion = self.get_loss_fn(loss, self.nb_classes)
 

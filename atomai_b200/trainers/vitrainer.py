@@ -135,6 +135,9 @@ class viBaseTrainer:
             self._bucket = GradBucket(params)
             if isinstance(self.optim, FusedAdam):
                 self.optim.grad_scale = 1.0 / self.comm.world
+                self._bucket.post_scale = 1.0
+            else:
+                self._bucket.post_scale = 1.0 / self.comm.world
         self.filename = kwargs.get("filename", "./model")
 
     @classmethod

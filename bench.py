@@ -1,36 +1,57 @@
 #!/usr/bin/env python
 """
 bench.py — Segmentor.fit throughput on B200 (BASELINE.json metric:
-"Segmentor.fit images/sec (512x512, 3-class)"; workload = configs[1]: Unet nb_classes=3,
+"Segmentor.fit images/sec (512x512, 3-class)"; default workload = configs[1]: Unet nb_classes=3,
 batch 32 of 512x512 fp32 synthetic stacks per GPU).
 
-  python bench.py --gpus N --steps K --warmup W           (N > 1: launched by torchrun)
-  python bench.py --impl reference ...                    (the reference algorithm on host cores)
+  python bench.py --gpus N --steps K --warmup W             our arm (N > 1: launched by torchrun)
+  python bench.py --impl reference ...                      the UNMODIFIED reference (baseline/_ref) on
+                                                            the host cores, same config (batch 32)
+  python bench.py --impl torch-cuda ...                     the UNMODIFIED reference with device='cuda':
+                                                            stock PyTorch/cuDNN sm_100 kernels, the
+                                                            "existing Blackwell path" 
+  python bench.py --workload {seg512,seg256,rvae,imspec,gram}   the other BASELINE.json configs
+  python bench.py --scaling strong                          global batch fixed at 32 (32/N per GPU)
 
 A "step" is one Segmentor.fit training cycle of the reference (atomai/trainers/trainer.py:233-251):
 one train mini-batch (forward + backward + Adam) followed by one test mini-batch forward.
-Prints ONE JSON line (rank 0).  Multi-GPU runs are data-parallel with weak scaling: every rank
-trains on its own shard of a global batch of 32*N images.
-"""
-import argparse
-import json
-import os
-import subprocess
-import sys
-import threading
-import time
+Prints ONE JSON line (rank 0).
 
-import numpy as np
-import torch
+Arithmetic: --math auto (default) measures the cycle in both tensor-core modes, 'tf32x3' (every
+operand split into a TF32 high and low part; meets the north-star 1e-3 logits bound with ~1e-6,
+tests/test_unet_gpu.py) and 'tf32' (single TF32 rounding, what stock PyTorch does on CUDA; 1-2e-3 on
+the logits).  The top-level `value`/`e2e` are the mode that meets the tolerance (tf32x3); the other
+mode is reported under `math_modes`.
+"""
+import os
+import sys
+
+# the CPU arm must not see the GPUs: the reference picks 'cuda' whenever torch finds one
+if "--impl" in sys.argv and sys.argv[sys.argv.index("--impl") + 1:][:1] == ["reference"]:
+    os.environ["CUDA_VISIBLE_DEVICES"] = ""
+
+import argparse  # noqa: E402
+import json  # noqa: E402
+import subprocess  # noqa: E402
+import threading  # noqa: E402
+import time  # noqa: E402
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-H = W = 512
 BATCH = 32
 NB_CLASSES = 3
 FLOP_PER_PIXEL_TRAIN = 196_992        # fwd 65,664 x 3 (fwd + dgrad + wgrad)
 FLOP_PER_PIXEL_FWD = 65_664
+PARITY_MODE = "tf32x3"                # the mode that meets the 1e-3 logits tolerance
+METRIC = {"seg512": "Segmentor.fit images/sec (512x512, 3-class)",
+          "seg256": "Segmentor.fit images/sec (256x256, 3-class)",
+          "rvae": "rVAE.fit images/sec (64x64, latent_dim=2, conv encoder)",
+          "imspec": "ImSpec.fit images/sec (64x64 -> 128)",
+          "gram": "dense RBF Gram GB/s written (50k x 128)"}
 
 
 def host_cores():
@@ -89,135 +110,188 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons}
 
 
-def synth(n, seed):
+def synth(n, seed, hw):
     """Synthetic microscopy-like stack: uniform [0,1) images, labels in {0,1,2} (all present)."""
     rs = np.random.RandomState(seed)
-    X = rs.rand(n, 1, H, W).astype(np.float32)
-    y = rs.randint(0, NB_CLASSES, (n, H, W)).astype(np.int64)
+    X = rs.rand(n, 1, hw, hw).astype(np.float32)
+    y = rs.randint(0, NB_CLASSES, (n, hw, hw)).astype(np.int64)
     y[:, 0, :NB_CLASSES] = np.arange(NB_CLASSES)
     return X, y
 
 
-# ------------------------------------------------------------------------------ reference arm
+def seg_hw(workload):
+    return 256 if workload == "seg256" else 512
+
+
+# ------------------------------------------------------------------------------ reference arms
+def _reference_seg_loop(aoi, X, y, Xt, yt, batch, steps, warmup, memory_alloc, cuda):
+    """compile_trainer + `step(e)` of the reference's own Segmentor (its public trainer API:
+    atomai/trainers/trainer.py:233-251, 441-565); returns seconds for `steps` cycles."""
+    m = aoi.models.Segmentor("Unet", nb_classes=NB_CLASSES)
+    m.compile_trainer((X, y, Xt, yt), loss="ce", training_cycles=steps + warmup + 1,
+                      batch_size=batch, full_epoch=False, memory_alloc=memory_alloc,
+                      plot_training_history=False, filename="/tmp/bench_ref_model")
+    e = 0
+    for _ in range(warmup):
+        m.step(e)
+        e += 1
+    if cuda:
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        m.step(e)
+        e += 1
+    if cuda:
+        ev1.record()
+        torch.cuda.synchronize()
+        return ev0.elapsed_time(ev1) / 1e3, m
+    return time.perf_counter() - t0, m
+
+
 def run_reference(args):
-    """The reference's algorithm for this path on the host cores: oracle/nets_ref.py (plain torch
-    CPU fp32 restatement, pinned against the unmodified reference's goldens).  /root/reference is
-    Python and cannot travel to the GPU box, so this port is the reference arm (kind "port").
-    Each step is a bounded sample of the workload: a batch of `sample_batch` 512x512 images."""
-    from collections import OrderedDict
-    from oracle import nets_ref
-    from atomai_b200.nets import Unet
+    """`--impl reference`: the unmodified reference (pip-installed into baseline/_ref, imported
+    through baseline/ref_loader.py) on the host cores, the same Segmentor.fit cycle at the same
+    batch size as our arm (a cycle of 32 512x512 images takes ~18 s on 16 cores)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    from baseline.ref_loader import import_reference
     cores = host_cores()
     torch.set_num_threads(cores)
-    sample_batch = args.ref_batch
-    torch.manual_seed(1)
-    net = Unet(nb_classes=NB_CLASSES)
-    sd = OrderedDict((k, v.detach().clone()) for k, v in net.state_dict().items())
-    cfg = dict(nb_classes=NB_CLASSES)
-    X, y = synth(2 * sample_batch, 1)
-    X, y = torch.from_numpy(X), torch.from_numpy(y)
-    state = {}
-
-    def step(i):
-        nets_ref.unet_train_step(X[:sample_batch], y[:sample_batch], sd, cfg, state)
-        with torch.no_grad():
-            lt = nets_ref.unet_forward(X[sample_batch:], sd, cfg, training=False)
-            nets_ref.seg_loss(lt, y[sample_batch:], NB_CLASSES)
-
-    for i in range(args.warmup):
-        step(i)
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        step(i)
-    dt = time.perf_counter() - t0
-    ips = sample_batch * args.steps / dt
+    hw = seg_hw(args.workload)
+    batch = args.ref_batch
+    try:
+        aoi = import_reference()
+    except Exception as ex:  # noqa
+        print(json.dumps({"impl": "reference", "unavailable": f"{type(ex).__name__}: {ex}"[:300]}))
+        return
+    X, y = synth(2 * batch, 1, hw)
+    Xt, yt = synth(batch, 2, hw)
+    dt, m = _reference_seg_loop(aoi, X, y, Xt, yt, batch, args.steps, args.warmup, 4, False)
+    ips = batch * args.steps / dt
+    sample = (f"{args.steps} cycles of batch {batch} (train step + test forward), unmodified reference "
+              f"v{aoi.__version__} on torch {torch.__version__} CPU fp32, {cores} threads")
     line = {
-        "impl": "reference", "metric": "Segmentor.fit images/sec (512x512, 3-class)",
+        "impl": "reference", "metric": METRIC[args.workload],
         "value": ips, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"Unet nb_classes=3, {H}x{W}x1 fp32, train step + test forward per "
-                               f"cycle; bounded sample: batch {sample_batch} instead of {BATCH}"},
-        "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} cycles of batch {sample_batch} (train step + "
-                                   f"test forward), torch CPU fp32, {cores} threads"},
+        "config": {"workload": f"Segmentor('Unet', nb_classes=3).fit cycle = 1 train step + 1 test "
+                               f"forward; batch {batch} x {hw}x{hw}x1 fp32" +
+                               ("" if batch == BATCH else f" (bounded sample: batch {batch} instead of {BATCH})"),
+                   "parallelism": "cpu", "final_train_losses": [float(v) for v in m.loss_acc["train_loss"][-2:]]},
+        "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "reference",
+                         "sample": sample},
         "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
+def run_torch_cuda(args):
+    """`--impl torch-cuda`: the unmodified reference with device='cuda' on ONE B200 — every conv is a
+    stock ATen -> cuDNN call (the existing Blackwell kernels to beat).  Variants:
+    stock (cuDNN TF32 allowed = PyTorch default; deterministic algorithms as the reference's
+    set_train_rng sets them), fp32 (cudnn.allow_tf32 = False), tuned (cudnn.benchmark, non-
+    deterministic), channels_last (tuned + NHWC weights)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("--impl torch-cuda needs a CUDA device")
+    from baseline.ref_loader import import_reference
+    aoi = import_reference()
+    import atomai.utils.nn as ref_nn
+    hw = seg_hw(args.workload)
+    batch = BATCH
+    X, y = synth(2 * batch, 1, hw)
+    Xt, yt = synth(batch, 2, hw)
+    out = {}
+    stock_rng = ref_nn.set_train_rng
+
+    def tuned_rng(seed=1):
+        stock_rng(seed)
+        torch.backends.cudnn.deterministic = False
+        torch.backends.cudnn.benchmark = True
+
+    for name in ("stock", "fp32", "tuned", "channels_last", "stock_e2e"):
+        torch.backends.cudnn.allow_tf32 = name != "fp32"
+        patched = name in ("tuned", "channels_last")
+        for mod in (ref_nn, sys.modules["atomai.trainers.trainer"]):
+            mod.set_train_rng = tuned_rng if patched else stock_rng
+        if name == "channels_last":
+            Seg = aoi.models.Segmentor
+            orig_init = Seg.__init__
+
+            def init_cl(self, *a, **k):
+                orig_init(self, *a, **k)
+                self.net.to(memory_format=torch.channels_last)
+            Seg.__init__ = init_cl
+        try:
+            dt, m = _reference_seg_loop(aoi, X, y, Xt, yt, batch, args.steps, args.warmup,
+                                        0 if name == "stock_e2e" else 4, True)
+            out[name] = {"images_per_s": batch * args.steps / dt, "ms_per_step": 1e3 * dt / args.steps,
+                         "final_train_loss": float(m.loss_acc["train_loss"][-1])}
+        except Exception as ex:  # noqa
+            out[name] = {"error": f"{type(ex).__name__}: {ex}"[:200]}
+        finally:
+            if name == "channels_last":
+                Seg.__init__ = orig_init
+        del m
+        torch.cuda.empty_cache()
+    ips = out["stock"].get("images_per_s")
+    e2e = out["stock_e2e"].get("images_per_s")
+    h2d = batch * hw * hw * (4 + 8) * 2
+    line = {
+        "impl": "torch-cuda", "metric": METRIC[args.workload], "value": ips, "unit": "images/s",
+        "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": out["stock"].get("ms_per_step"), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "tf32 (cuDNN default)", "data": "synthetic",
+        "config": {"workload": f"unmodified reference Segmentor('Unet', nb_classes=3).fit cycle on "
+                               f"device='cuda'; batch {batch} x {hw}x{hw}x1 fp32",
+                   "torch": torch.__version__, "cudnn": torch.backends.cudnn.version()},
+        "gpu_baseline": {"kind": "reference on stock PyTorch/cuDNN, 1 x B200", "unit": "images/s",
+                         "variants": out},
+        "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
+                "note": "memory_alloc=0: the reference keeps the batches on the host and copies "
+                        "them (pageable) every step"},
+    }
+    print(json.dumps(line), flush=True)
+
+
 # ------------------------------------------------------------------------------ our arm
-def time_layer(ops, Source, N, hh, ww, cin, cout, reps=10):
-    """Live CUDA-event timing of the fused conv kernel on one UNet layer shape (roofline)."""
-    dev = "cuda"
-    x = torch.rand(N, hh, ww, cin, device=dev)
-    sc = torch.rand(cin, device=dev) + 0.5
-    sh = torch.rand(cin, device=dev)
-    w = torch.randn(cout, cin, 3, 3, device=dev) * 0.05
-    b = torch.randn(cout, device=dev) * 0.1
-    out = torch.empty(N, hh, ww, cout, device=dev)
-    st = torch.zeros(2 * cout, device=dev, dtype=torch.float64)
-    d = ops.conv_desc([Source(x, sc, sh)], N, hh, ww, cout, (3, 3), 1, 0.01, ops.MATH_TF32)
-    wp = ops.prep_weights(w, ops.WMODE_FWD, ops.MATH_TF32)
-    for _ in range(3):
-        ops.conv_fwd(d, wp, b, out, st)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(reps):
-        ops.conv_fwd(d, wp, b, out, st)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / reps
-    flops = 2.0 * N * hh * ww * cin * cout * 9
-    byts = 4.0 * N * hh * ww * (cin + cout)
-    return ms, flops / ms / 1e9, byts / ms / 1e6
+def _maxreduce_ms(ms, dev, world):
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    return float(t.item())
 
 
-def run_ours(args):
+def measure_seg_mode(math, args, world, rank, dev, data, gb, per_gpu, hw):
+    """One math mode: device-resident cycle (value), train-step-only, in-situ per-kernel profile of
+    one cycle (roofline) and the end-to-end cycle from pinned host buffers."""
     import atomai_b200 as ab
     from atomai_b200 import _C, ops
     from atomai_b200.models import Segmentor
-    from atomai_b200.ops import Source
-    from atomai_b200.parallel import init_distributed
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    assert world == args.gpus or world == 1, "launch N > 1 with torchrun --nproc-per-node N"
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (no CPU path); use --impl reference for the host arm")
-    torch.cuda.set_device(local_rank)
-    comm = init_distributed()
-    ab.set_math(args.math)
-    pk = peaks()
-
-    gb = BATCH * world                       # weak scaling: 32 images per GPU
-    n_train_batches = 2
-    X, y = synth(gb * n_train_batches, 1)
-    Xt, yt = synth(gb, 2)
-    m = Segmentor("Unet", nb_classes=NB_CLASSES, seed=1)
-    cycles = args.warmup + args.steps
-    m.compile_trainer((X, y, Xt, yt), loss="ce", training_cycles=2 * cycles + 8, batch_size=gb,
-                      full_epoch=False, memory_alloc=64, plot_training_history=False,
-                      sync_host=False, sync_bn=True, filename="/tmp/bench_model")
-    dev = torch.device("cuda", local_rank)
+    X, y, Xt, yt = data
+    ab.set_math(math)
 
     def barrier():
         if world > 1:
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
-    # ---------------- device-resident loop (value)
+    m = Segmentor("Unet", nb_classes=NB_CLASSES, seed=1)
+    cycles = args.warmup + args.steps
+    m.compile_trainer((X, y, Xt, yt), loss="ce", training_cycles=2 * cycles + 8, batch_size=gb,
+                      full_epoch=False, memory_alloc=64, plot_training_history=False,
+                      sync_host=False, sync_bn=True, filename="/tmp/bench_model")
     e = 0
     for _ in range(args.warmup):
         m.step(e)
         e += 1
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     calls0 = _C.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
@@ -227,10 +301,7 @@ def run_ours(args):
     ev1.record()
     barrier()
     launches = _C.launch_count() - calls0
-    t = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
-    if world > 1:
-        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-    ms_total = float(t.item())
+    ms_total = _maxreduce_ms(ev0.elapsed_time(ev1), dev, world)
     final_losses = [float(v) for v in m.loss_acc["train_loss"][-2:]]
 
     # train-step-only timing (secondary figure)
@@ -241,29 +312,43 @@ def run_ours(args):
         m.train_step(f, tg)
     ev1.record()
     barrier()
-    t2 = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
-    if world > 1:
-        torch.distributed.all_reduce(t2, op=torch.distributed.ReduceOp.MAX)
-    ms_train_only = float(t2.item()) / args.steps
+    ms_train_only = _maxreduce_ms(ev0.elapsed_time(ev1), dev, world) / args.steps
 
-    # ---------------- end-to-end loop: the same public call (Segmentor.fit's cycle, `step`) on a
-    # HOST-resident data set (memory_alloc = 0 GB keeps the batches in pinned host memory, as the
-    # reference does for data sets that do not fit): every cycle copies its images + labels
-    # host->device (on the trainer's copy stream, overlapping the previous cycle's kernels) and
-    # reads the losses back (loss.item()), all inside the timed region.
+    # in-situ profile: every conv-family launch of one more cycle bracketed by CUDA events on the
+    # launching stream -> per-kernel algorithmic FLOP/s and bytes/s over ALL its launches
+    prof = {}
+    if rank == 0:
+        ops.PROFILE = []
+        m.step(e)
+        e += 1
+        torch.cuda.synchronize()
+        for kern, fl, by, a, b in ops.PROFILE:
+            d = prof.setdefault(kern, {"launches": 0, "ms": 0.0, "flop": 0.0, "bytes": 0.0})
+            d["launches"] += 1
+            d["ms"] += a.elapsed_time(b)
+            d["flop"] += fl
+            d["bytes"] += by
+        ops.PROFILE = None
+    elif world > 1:
+        m.step(e)      # keep the collectives of the profiled cycle matched
+        e += 1
     del m
     torch.cuda.empty_cache()
+
+    # end-to-end: the same public call (Segmentor.fit's cycle, `step`) on a HOST-resident data set
+    # (memory_alloc = 0 GB keeps the batches in pinned host memory, as the reference does for data
+    # sets that do not fit): every cycle copies its images + labels host->device and reads the
+    # losses back (loss.item()), all inside the timed region.
     m2 = Segmentor("Unet", nb_classes=NB_CLASSES, seed=1)
-    n_e2e = max(1, args.warmup // 2) + args.steps
-    m2.compile_trainer((X, y, Xt, yt), loss="ce", training_cycles=n_e2e + 2, batch_size=gb,
-                       full_epoch=False, memory_alloc=0, plot_training_history=False,
+    n_w = max(1, args.warmup // 2)
+    m2.compile_trainer((X, y, Xt, yt), loss="ce", training_cycles=n_w + args.steps + 2,
+                       batch_size=gb, full_epoch=False, memory_alloc=0, plot_training_history=False,
                        sync_host=True, sync_bn=True, filename="/tmp/bench_model_e2e")
     assert not m2.X_train[0].is_cuda and m2.X_train[0].is_pinned(), "e2e data must be pinned host memory"
-    lb = BATCH
-    h2d = sum(t_[0][:lb].numel() * t_[0].element_size()
+    h2d = sum(t_[0][:per_gpu].numel() * t_[0].element_size()
               for t_ in (m2.X_train, m2.y_train, m2.X_test, m2.y_test))
     e = 0
-    for _ in range(max(1, args.warmup // 2)):
+    for _ in range(n_w):
         m2.step(e)
         e += 1
     barrier()
@@ -273,77 +358,146 @@ def run_ours(args):
         e += 1
     ev1.record()
     barrier()
-    t3 = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
-    if world > 1:
-        torch.distributed.all_reduce(t3, op=torch.distributed.ReduceOp.MAX)
-    ms_e2e = float(t3.item())
-    sampler.stop_flag = True          # clocks are sampled over all three timed regions
+    ms_e2e = _maxreduce_ms(ev0.elapsed_time(ev1), dev, world)
+    del m2
+    torch.cuda.empty_cache()
+    return {"math": math, "images_per_s": gb * args.steps / (ms_total / 1e3),
+            "ms_per_step": ms_total / args.steps, "train_step_only_ms": ms_train_only,
+            "e2e_images_per_s": gb * args.steps / (ms_e2e / 1e3), "e2e_ms_per_step": ms_e2e / args.steps,
+            "h2d_bytes_per_step": h2d * world, "gpu_launches": launches,
+            "final_train_losses": final_losses, "profile": prof}
 
-    if rank != 0:
-        return
-    ips = gb * args.steps / (ms_total / 1e3)
-    ips_e2e = gb * args.steps / (ms_e2e / 1e3)
-    step_tflops = FLOP_PER_PIXEL_TRAIN * H * W * BATCH * world / (ms_train_only / 1e3) / 1e12
 
-    # ---------------- roofline of the dominant kernel (conv_tc_kernel), timed live on this GPU
-    tf32_peak = pk["bf16"] / 2.0             # TF32 dense = half the measured bf16 rate
-    layers = {}
-    for tag, (hh, cin, cout) in {"c5.block.0": (256, 64, 32), "c4.block.0": (128, 128, 64),
-                                 "bn.block.3": (64, 128, 128), "c6.block.0": (512, 32, 16)}.items():
-        ms, tfl, gbs = time_layer(ops, Source, BATCH, hh, hh, cin, cout)
-        layers[tag] = {"ms": round(ms, 4), "tflops": round(tfl, 1), "gbs": round(gbs, 1),
-                       "frac_tensor": round(tfl / tf32_peak, 3), "frac_hbm": round(gbs / pk["hbm"], 3)}
-    dom = "bn.block.3"
-    # DRAM traffic of that kernel (dram__bytes_read.sum + dram__bytes_write.sum of one launch) from
-    # the committed `ncu --set full` capture of the same layer shape
-    traffic = None
+def roofline_from_profile(res, pk, world, per_gpu, hw):
+    """Kernel-wide roofline of the dominant kernel from the in-situ profile (all of its launches
+    in one fit cycle, CUDA events on the launching stream)."""
+    prof = res["profile"]
+    if not prof:
+        return None
+    passes = 3.0 if res["math"] == "tf32x3" else 1.0
+    tf32_peak = pk["bf16_sustained"] / 2.0      # kernel timed inside a long step -> sustained figure
+    kern = {}
+    for k, d in prof.items():
+        tf = d["flop"] / (d["ms"] * 1e-3) / 1e12 if d["ms"] > 0 else 0.0
+        kern[k] = {"launches": d["launches"], "ms": round(d["ms"], 3),
+                   "algorithmic_tflops": round(tf, 1),
+                   "issued_tflops": round(tf * (passes if k.endswith("_tc_kernel") else 1.0), 1),
+                   "algorithmic_gbs": round(d["bytes"] / (d["ms"] * 1e-3) / 1e9, 1) if d["ms"] > 0 else 0.0}
+    dom = max((k for k in kern if k.endswith("_tc_kernel")), key=lambda k: kern[k]["ms"], default=None)
+    if dom is None:
+        return {"bound": "tensor", "achieved": None, "peak": round(tf32_peak, 1), "unit": "TFLOP/s",
+                "frac": None, "traffic": None, "kernels": kern}
+    step_tflops = FLOP_PER_PIXEL_TRAIN * hw * hw * per_gpu * world / (res["train_step_only_ms"] / 1e3) / 1e12
+    traffic, traffic_src = None, None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_roofline.json")))["traffic_bytes"]
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r02_roofline.json")))
+        traffic, traffic_src = tj.get("traffic_bytes_per_launch"), tj.get("source")
     except Exception:  # noqa
         pass
-    roof = {"bound": "tensor", "kernel": "conv_tc_kernel (fused conv3x3+bias+LeakyReLU+BN stats), "
-            f"layer {dom} 128->128 @64x64, batch {BATCH}", "achieved": layers[dom]["tflops"],
-            "peak": round(tf32_peak, 1), "unit": "TFLOP/s", "frac": layers[dom]["frac_tensor"],
-            "peak_note": f"0.5 x {pk['src']} dense bf16 ({pk['bf16']} TF/s): TF32 operands",
-            "traffic": traffic, "traffic_note": "bytes per launch, profiles/r01_roofline.json "
-            "(ncu --set full; algorithmic bytes = 4*N*H*W*(Cin+Cout) = 134.2 MB, the 126 MB L2 "
-            "holds back part of the output writes)", "layers": layers,
+    return {"bound": "tensor", "kernel": f"{dom}, all {kern[dom]['launches']} launches of one fit cycle "
+            f"(forward train + forward test + dgrad), math {res['math']}",
+            "achieved": kern[dom]["algorithmic_tflops"], "peak": round(tf32_peak, 1), "unit": "TFLOP/s",
+            "frac": round(kern[dom]["algorithmic_tflops"] / tf32_peak, 3),
+            "frac_issued": round(kern[dom]["issued_tflops"] / tf32_peak, 3),
+            "peak_note": f"0.5 x {pk['src']} sustained dense bf16 ({pk['bf16_sustained']} TF/s): TF32 "
+                         "operands, kernel timed inside the step; `achieved` counts ALGORITHMIC FLOPs "
+                         "(2*taps*Cin*Cout per pixel) — tf32x3 issues 3 MMAs per product (frac_issued)",
+            "traffic": traffic, "traffic_note": traffic_src, "kernels": kern,
             "step_tflops_algorithmic": round(step_tflops, 1),
             "step_frac": round(step_tflops / tf32_peak, 3)}
 
-    # ---------------- CPU baseline (oracle port) on a bounded sample, rank 0, N = 1 only
-    cpu = None
-    if world == 1 and not args.no_cpu_baseline:
+
+def _sub_json(argv, timeout, env=None):
+    out = subprocess.check_output([sys.executable, os.path.abspath(__file__)] + argv, encoding="utf-8",
+                                  timeout=timeout, env=env or dict(os.environ))
+    return json.loads([l for l in out.splitlines() if l.startswith("{")][-1])
+
+
+def run_ours(args):
+    from atomai_b200.parallel import init_distributed
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus or world == 1, "launch N > 1 with torchrun --nproc-per-node N"
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU path); use --impl reference for the host arm")
+    torch.cuda.set_device(local_rank)
+    init_distributed()
+    dev = torch.device("cuda", local_rank)
+    pk = peaks()
+    if args.workload in ("rvae", "imspec", "gram"):
+        from tools.bench_workloads import run_other
+        line = run_other(args, world, rank, dev, pk)
+        if rank == 0:
+            print(json.dumps(line), flush=True)
+        return
+
+    hw = seg_hw(args.workload)
+    strong = args.scaling == "strong"
+    per_gpu = BATCH // world if strong else BATCH
+    assert per_gpu >= 1 and per_gpu * world == (BATCH if strong else BATCH * world)
+    gb = per_gpu * world
+    X, y = synth(gb * 2, 1, hw)
+    Xt, yt = synth(gb, 2, hw)
+    modes = [PARITY_MODE, "tf32"] if args.math == "auto" else [args.math]
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    results = {}
+    for mth in modes:
+        results[mth] = measure_seg_mode(mth, args, world, rank, dev, (X, y, Xt, yt), gb, per_gpu, hw)
+    sampler.stop_flag = True
+    if rank != 0:
+        return
+    head = results[modes[0]]
+    roof = roofline_from_profile(head, pk, world, per_gpu, hw)
+
+    # ---------------- the other two arms on a bounded sample (rank 0, N = 1 only)
+    cpu = gpu_base = None
+    if world == 1 and not args.no_baselines:
         try:
-            out = subprocess.check_output(
-                [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "4",
-                 "--warmup", "1", "--ref-batch", str(args.ref_batch)], encoding="utf-8",
-                timeout=600, env={**os.environ, "CUDA_VISIBLE_DEVICES": ""})
-            ref = json.loads([l for l in out.splitlines() if l.startswith("{")][-1])
-            cpu = ref["cpu_baseline"]
+            gpu_base = _sub_json(["--impl", "torch-cuda", "--workload", args.workload, "--steps", "5",
+                                  "--warmup", "3"], 900)["gpu_baseline"]
+            gpu_base["value"] = gpu_base["variants"]["stock"].get("images_per_s")
         except Exception as ex:  # noqa
-            cpu = {"value": None, "unit": "images/s", "cores": host_cores(), "kind": "port",
+            gpu_base = {"value": None, "unit": "images/s", "error": f"{type(ex).__name__}: {ex}"[:200]}
+        try:
+            cpu = _sub_json(["--impl", "reference", "--workload", args.workload, "--steps", "1",
+                             "--warmup", "0", "--ref-batch", str(args.ref_batch)], 900,
+                            {**os.environ, "CUDA_VISIBLE_DEVICES": ""})["cpu_baseline"]
+        except Exception as ex:  # noqa
+            cpu = {"value": None, "unit": "images/s", "cores": host_cores(), "kind": "reference",
                    "sample": f"failed: {type(ex).__name__}: {ex}"[:200]}
 
+    others = {k: {kk: vv for kk, vv in v.items() if kk != "profile"} for k, v in results.items()}
+    for k, v in results.items():
+        r_ = roofline_from_profile(v, pk, world, per_gpu, hw)
+        if r_:
+            others[k]["conv_tc_frac"] = r_["frac"]
+            others[k]["kernels"] = r_["kernels"]
     line = {
-        "metric": "Segmentor.fit images/sec (512x512, 3-class)",
-        "value": ips, "unit": "images/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "tf32" if args.math == "tf32" else "f32",
-        "data": "synthetic",
+        "metric": METRIC[args.workload],
+        "value": head["images_per_s"], "unit": "images/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True,
+        "scaling": args.scaling, "vs_baseline": None, "dtype": head["math"], "data": "synthetic",
         "config": {"workload": f"Segmentor('Unet', nb_classes=3).fit cycle = 1 train step "
-                               f"(fwd+bwd+fused Adam) + 1 test forward; batch {BATCH} x {H}x{W}x1 "
+                               f"(fwd+bwd+fused Adam) + 1 test forward; batch {per_gpu} x {hw}x{hw}x1 "
                                f"fp32 per GPU, global batch {gb}",
-                   "parallelism": f"dp{world}", "sync_bn": True, "math": args.math,
-                   "l2": "inputs larger than L2: ~19 GB of activations per step, no flush needed",
-                   "train_step_only_ms": ms_train_only,
-                   "train_step_only_images_per_s": gb / (ms_train_only / 1e3),
-                   "final_train_losses": final_losses},
-        "e2e": {"value": ips_e2e, "unit": "images/s", "h2d_bytes_per_step": h2d * world,
-                "d2h_bytes_per_step": 8 * world, "ms_per_step": ms_e2e / args.steps},
-        "gpu_launches": launches,
+                   "parallelism": f"dp{world}", "sync_bn": True, "math": head["math"],
+                   "math_note": "tf32x3 meets the 1e-3 logits bound (measured ~1e-6); tf32 (single "
+                                "rounding, = stock cuDNN default) is listed under math_modes",
+                   "l2": "inputs larger than L2: >10 GB of activations per step, no flush needed",
+                   "train_step_only_ms": head["train_step_only_ms"],
+                   "train_step_only_images_per_s": gb / (head["train_step_only_ms"] / 1e3),
+                   "final_train_losses": head["final_train_losses"]},
+        "e2e": {"value": head["e2e_images_per_s"], "unit": "images/s",
+                "h2d_bytes_per_step": head["h2d_bytes_per_step"], "d2h_bytes_per_step": 8 * world,
+                "ms_per_step": head["e2e_ms_per_step"]},
+        "gpu_launches": head["gpu_launches"],
         "clocks": sampler.summary(),
         "roofline": roof,
+        "math_modes": others,
+        "gpu_baseline": gpu_base,
         "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)
@@ -354,14 +508,18 @@ if __name__ == "__main__":
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--math", default="tf32", choices=["tf32", "fp32"])
-    ap.add_argument("--ref-batch", type=int, default=8,
-                    help="images per step of the bounded CPU sample (reference arm / cpu_baseline)")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torch-cuda"])
+    ap.add_argument("--workload", default="seg512", choices=sorted(METRIC))
+    ap.add_argument("--math", default="auto", choices=["auto", "tf32", "tf32x3", "fp32"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--ref-batch", type=int, default=BATCH,
+                    help="images per step of the CPU arm (default: the full batch of 32)")
+    ap.add_argument("--no-baselines", "--no-cpu-baseline", dest="no_baselines", action="store_true")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)
+    elif a.impl == "torch-cuda":
+        run_torch_cuda(a)
     else:
         run_ours(a)
         if torch.distributed.is_available() and torch.distributed.is_initialized():

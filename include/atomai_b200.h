@@ -15,7 +15,9 @@
  *    memory.  Return value: 0 = ok, non-zero = error, text via
  *    atomai_b200_last_error() (thread-local).  No exceptions cross the ABI.
  *  - math: 0 = exact fp32 FFMA kernels, 1 = TF32 tcgen05 tensor-core kernels
- *    (fp32 accumulate in TMEM).  There is no CPU path.
+ *    (fp32 accumulate in TMEM), 2 = the same kernels with every operand split into
+ *    a TF32 high and low part (three MMAs per product; meets the reference's fp32
+ *    results to ~1e-6 relative).  There is no CPU path.
  */
 #ifndef ATOMAI_B200_H
 #define ATOMAI_B200_H
@@ -28,6 +30,7 @@ extern "C" {
 
 #define AB_MATH_FP32 0
 #define AB_MATH_TF32 1
+#define AB_MATH_TF32X3 2 /* 3xTF32 split: a_hi*w_hi + a_lo*w_hi + a_hi*w_lo, ~fp32 accuracy */
 
 #define AB_ACT_LRELU 0
 #define AB_ACT_TANH 1

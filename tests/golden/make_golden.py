@@ -103,6 +103,28 @@ def bfo_case():
     print("bfo", logits.shape, np.abs(logits).max())
 
 
+def bfo_full_case():
+    """pretrained/bfo.tar through the reference's whole predict pipeline on its own 1024x1024 test
+    image: Segmentor.predict -> softmax output + Locator coordinates (2410 atoms).
+    Stores the image (the GPU box has no /root/reference), a strided sample of the eval logits and
+    of the softmax output, the coordinates, and how close any pixel's class probability comes to
+    the Locator threshold 0.5 (the margin a different arithmetic has before a mask pixel flips)."""
+    from atomai.models import load_model
+    m = load_model("/root/reference/pretrained/bfo.tar")
+    img = np.load("/root/reference/test/predictors/test_data/test_inputimg.npy").astype(np.float32)
+    nn_out, coords = m.predict(img)
+    net = m.net.cpu().eval()
+    x = (img - img.min()) / np.ptp(img)
+    with torch.no_grad():
+        logits = net(torch.from_numpy(x.astype(np.float32))[None, None]).numpy()
+    margin = np.sort(np.abs(nn_out[..., :-1].astype(np.float64) - 0.5).reshape(-1))[:16]
+    np.savez_compressed(os.path.join(HERE, "bfo_1024.npz"), image=img,
+                        logits=gu.sample_flat(logits, 61), logits_absmax=np.float64(np.abs(logits).max()),
+                        nn_output=gu.sample_flat(nn_out, 61), coordinates=coords[0],
+                        threshold_margins=margin)
+    print("bfo_1024", nn_out.shape, coords[0].shape, "closest |p-0.5|:", margin[:4])
+
+
 def locator_case():
     """Locator.run on a crop of the reference's golden NN output (test/predictors/test_locator.py)."""
     from atomai.predictors import Locator
@@ -117,6 +139,13 @@ def locator_case():
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "locator":
         locator_case()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "big512":
+        # BASELINE.json configs[1] geometry (512x512, default 3-class Unet), N = 2
+        fcnn_case("unet_default_3c_512", "Unet", 3, 700, 2, 512, 512, logit_stride=61)
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "bfo1024":
+        bfo_full_case()
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "big":
         fcnn_case("unet_default_3c_128", "Unet", 3, 600, 4, 128, 128, logit_stride=5)

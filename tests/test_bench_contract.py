@@ -32,7 +32,7 @@ def test_reference_arm_json_line():
     assert line["impl"] == "reference" and line["unit"] == "images/s" and line["value"] > 0
     assert line["metric"].startswith("Segmentor.fit images/sec")
     assert line["higher_is_better"] is True and line["steps"] == 1 and line["warmup"] == 0
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["cpu_baseline"]["kind"] == "reference" and line["cpu_baseline"]["cores"] >= 1
     assert line["cpu_baseline"]["value"] == line["value"] == line["e2e"]["value"]
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
 

@@ -20,6 +20,8 @@ CASES = {
                          cfg=dict(batch_norm=False, layers=[2, 2, 2, 2])),
     "dilnet_default_3c": dict(model="dilnet", nb_classes=3, seed=500, n=2, h=32, w=32, cfg={}),
     "unet_default_3c_128": dict(model="Unet", nb_classes=3, seed=600, n=4, h=128, w=128, cfg={}),
+    # BASELINE.json configs[1] geometry: default 3-class Unet on 512x512 images (N = 2)
+    "unet_default_3c_512": dict(model="Unet", nb_classes=3, seed=700, n=2, h=512, w=512, cfg={}),
 }
 
 
