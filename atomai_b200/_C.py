@@ -104,7 +104,8 @@ SIGNATURES = {
     "atomai_b200_coord_latent_bwd": (_i, [C.POINTER(CoordLat), _vp, _vp, _vp, _vp, _vp, _vp,
                                           _vp]),
     "atomai_b200_sqerr_reduce": (_i, [_vp, _vp, _i64, _vp, _vp, _f, _vp, _vp]),
-    "atomai_b200_gram": (_i, [_vp, _vp, _vp, _f, _i, _i, _i, _i, _vp, _i64, _vp]),
+    "atomai_b200_gram_workspace_bytes": (_i64, [_i, _i, _i]),
+    "atomai_b200_gram": (_i, [_vp, _vp, _vp, _f, _i, _i, _i, _i, _i, _vp, _i64, _vp, _i64, _vp]),
     "atomai_b200_umma_rate": (_i, [_i, _i, _i, _i, _vp, _vp]),
     "atomai_b200_selftest_tma": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "atomai_b200_selftest_sw128": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),

@@ -40,8 +40,17 @@ __device__ __forceinline__ float to_tf32(float x) {
 }
 __device__ __forceinline__ float lrelu_f(float v, float a) { return v > 0.f ? v : v * a; }
 // forward activation and its derivative expressed through the OUTPUT value a = act(pre)
+// AB_ACT_RBF / AB_ACT_MATERN25: v is a squared scaled distance, slope the outputscale
+// (gpytorch RBFKernel / MaternKernel(nu=2.5) under a ScaleKernel, atomai/nets/gp.py:41-46,100-111)
 __device__ __forceinline__ float act_f(float v, int act, float slope) {
-  return act == AB_ACT_TANH ? tanhf(v) : (v > 0.f ? v : v * slope);
+  if (act == AB_ACT_TANH) return tanhf(v);
+  if (act == AB_ACT_RBF) return slope * expf(-0.5f * fmaxf(v, 0.f));
+  if (act == AB_ACT_MATERN25) {
+    const float d2 = fmaxf(v, 0.f);
+    const float s5r = 2.2360679775f * sqrtf(d2);
+    return slope * (1.f + s5r + 1.6666666667f * d2) * expf(-s5r);
+  }
+  return v > 0.f ? v : v * slope;
 }
 __device__ __forceinline__ float act_grad_from_out(float a, int act, float slope) {
   return act == AB_ACT_TANH ? 1.f - a * a : (a > 0.f ? 1.f : slope);

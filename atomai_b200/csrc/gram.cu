@@ -1,33 +1,55 @@
-// gram.cu — dense deep-kernel Gram matrix K[i][j] = os * k(|| (x1_i - x2_j) * inv_ls ||):
-// tiled pairwise distances (||a||^2 + ||b||^2 - 2 a.b, row norms by warp shuffles) with the
-// exponentiation fused into the epilogue so the n1 x n2 matrix is written exactly once.
+// gram.cu — dense deep-kernel Gram matrix K[i][j] = os * k(|| (x1_i - x2_j) * inv_ls ||).
+// The squared distance is ONE contraction over augmented operands,
+//     a' = [a/l, ||a/l||^2, 1, 0..]   b' = [-2 b/l, 1, ||b/l||^2, 0..]   =>  a'.b' = ||a/l - b/l||^2
+// (row norms by warp shuffles while scaling), so the -2ab^T term, both norms and the
+// exponentiation ride on the tcgen05 convolution kernel as a 1x1 convolution with an RBF /
+// Matern "activation" in its TMEM epilogue: x1 rows = pixels of a (1, n1/8, 8, K') image, column
+// blocks of <= 256 rows of x2 = output channels.  The n1 x n2 matrix is written exactly once.
+// AB_MATH_FP32 (and the < 8-row / < 16-column remainders of the tensor path) use the exact FFMA
+// tile kernel below.
 // RBF / Matern-2.5 / outputscale follow gpytorch's public kernel definitions as configured at
 // atomai/nets/gp.py:41-46 and :100-111 (gpytorch itself is not vendored by the reference).
 #include "common.cuh"
 
+
+// implemented in conv_tc.cu
+int64_t ab_pack_weights_tc_elems(int Cout, int Cin, int th, int tw, int mode, int x3);
+int ab_pack_weights_tc(const float* w, int Cout, int Cin, int th, int tw, int mode, int x3,
+                       float* out, cudaStream_t stream);
+int ab_conv_tc_fwd(const ab_conv_t* d, const float* wblob, const float* bias, float* y, int ld_y,
+                   double* stats, cudaStream_t stream);
+
 namespace {
 
 constexpr int TM = 64, TN = 64, TK = 16, GT = 256;
+constexpr int kColBlock = 256;      // output channels (columns of K) per tcgen05 launch
 
-// scaled copy xs = x * inv_ls and squared row norms (one warp per row)
-__global__ void scale_norm_kernel(const float* __restrict__ x, const float* __restrict__ inv_ls,
-                                  int n, int d, float* __restrict__ xs, float* __restrict__ nrm) {
+// one warp per row: out[row] = [x*inv_ls * fac, (side 0: |.|^2, 1) | (side 1: 1, |.|^2), 0-pad]
+__global__ void augment_kernel(const float* __restrict__ x, const float* __restrict__ inv_ls,
+                               int n, int d, int Kp, int side, float* __restrict__ out) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= n) return;
   float acc = 0.f;
-  for (int k = lane; k < d; k += 32) {
-    const float v = x[(int64_t)row * d + k] * inv_ls[k];
-    xs[(int64_t)row * d + k] = v;
-    acc = fmaf(v, v, acc);
+  const float fac = side ? -2.f : 1.f;
+  for (int k = lane; k < Kp; k += 32) {
+    float v = 0.f;
+    if (k < d) {
+      v = x[(int64_t)row * d + k] * inv_ls[k];
+      acc = fmaf(v, v, acc);
+      v *= fac;
+    }
+    out[(int64_t)row * Kp + k] = v;
   }
   acc = warp_sum(acc);
-  if (lane == 0) nrm[row] = acc;
+  if (lane == 0) {
+    out[(int64_t)row * Kp + d + (side ? 1 : 0)] = acc;
+    out[(int64_t)row * Kp + d + (side ? 0 : 1)] = 1.f;
+  }
 }
 
 __global__ void __launch_bounds__(GT)
-    gram_kernel(const float* __restrict__ a, const float* __restrict__ b,
-                const float* __restrict__ na, const float* __restrict__ nb, int n1, int n2, int d,
+    gram_kernel(const float* __restrict__ a, const float* __restrict__ b, int n1, int n2, int d,
                 float os, int kind, float* __restrict__ K, int64_t ldk) {
   __shared__ float sA[TK][TM + 4];
   __shared__ float sB[TK][TN + 4];
@@ -63,23 +85,11 @@ __global__ void __launch_bounds__(GT)
   for (int i = 0; i < 4; ++i) {
     const int m = m0 + tm + i;
     if (m >= n1) continue;
-    const float nam = na[m];
     float out[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int n = n0 + tn + j;
-      float d2 = n < n2 ? nam + nb[n] - 2.f * acc[i][j] : 0.f;
-      d2 = fmaxf(d2, 0.f);
-      if (kind == 0) {
-        out[j] = os * __expf(-0.5f * d2);
-      } else {  // Matern nu = 2.5: (1 + sqrt5 r + 5/3 r^2) exp(-sqrt5 r)
-        const float r = sqrtf(d2);
-        const float s5r = 2.2360679775f * r;
-        out[j] = os * (1.f + s5r + 1.6666666667f * d2) * __expf(-s5r);
-      }
-    }
+    for (int j = 0; j < 4; ++j) out[j] = act_f(acc[i][j], kind == 0 ? AB_ACT_RBF : AB_ACT_MATERN25, os);
     float* o = K + (int64_t)m * ldk + n0 + tn;
-    if (n0 + tn + 3 < n2 && ((ldk & 3) == 0) && (((uintptr_t)K & 15) == 0)) {
+    if (n0 + tn + 3 < n2 && ((ldk & 3) == 0) && (((uintptr_t)o & 15) == 0)) {
       *reinterpret_cast<float4*>(o) = make_float4(out[0], out[1], out[2], out[3]);
     } else {
       for (int j = 0; j < 4; ++j)
@@ -88,39 +98,81 @@ __global__ void __launch_bounds__(GT)
   }
 }
 
-}  // namespace
-
-// scratch layout inside the caller's K is not possible (K is the product), so the scaled copies
-// live in a small cached workspace owned by the library per device (n*(d+1) floats per side).
-static float* g_ws = nullptr;
-static size_t g_ws_bytes = 0;
-
-extern "C" int atomai_b200_gram(const float* x1, const float* x2, const float* inv_ls,
-                                float outputscale, int n1, int n2, int d, int kind, float* K,
-                                int64_t ldk, void* stream) {
-  AB_CHECK(x1 && x2 && inv_ls && K, "gram: null pointer");
-  AB_CHECK(n1 >= 0 && n2 >= 0 && d > 0 && ldk >= n2, "gram: bad dims n1=%d n2=%d d=%d", n1, n2, d);
-  AB_CHECK(kind == 0 || kind == 1, "gram: kind=%d", kind);
-  if (n1 == 0 || n2 == 0) return 0;
-  cudaStream_t st = (cudaStream_t)stream;
-  const size_t need = ((size_t)(n1 + n2) * (d + 1) + 64) * sizeof(float);
-  if (need > g_ws_bytes) {
-    if (g_ws) cudaFree(g_ws);
-    g_ws = nullptr; g_ws_bytes = 0;
-    AB_CUDA(cudaMalloc(&g_ws, need));
-    g_ws_bytes = need;
-  }
-  float* a = g_ws;
-  float* b = a + (size_t)n1 * d;
-  float* na = b + (size_t)n2 * d;
-  float* nb = na + n1;
-  scale_norm_kernel<<<(n1 + 7) / 8, 256, 0, st>>>(x1, inv_ls, n1, d, a, na);
-  AB_LAUNCH_CHECK();
-  scale_norm_kernel<<<(n2 + 7) / 8, 256, 0, st>>>(x2, inv_ls, n2, d, b, nb);
-  AB_LAUNCH_CHECK();
+int gram_simt(const float* a, const float* b, int n1, int n2, int Kp, float os, int kind, float* K,
+              int64_t ldk, cudaStream_t st) {
+  if (n1 <= 0 || n2 <= 0) return 0;
   dim3 grid((n2 + TN - 1) / TN, (n1 + TM - 1) / TM);
   AB_CHECK(grid.y <= 65535, "gram: n1 too large for one launch");
-  gram_kernel<<<grid, GT, 0, st>>>(a, b, na, nb, n1, n2, d, outputscale, kind, K, ldk);
+  gram_kernel<<<grid, GT, 0, st>>>(a, b, n1, n2, Kp, os, kind, K, ldk);
   AB_LAUNCH_CHECK();
+  return 0;
+}
+
+inline int64_t align256(int64_t v) { return (v + 255) & ~(int64_t)255; }
+// K' = d + 2 padded to the conv kernel's k-chunk (32 channels once there is more than one chunk)
+inline int aug_k(int d) { return d + 2 <= 8 ? 8 : (d + 2 <= 16 ? 16 : (d + 2 + 31) & ~31); }
+
+}  // namespace
+
+extern "C" int64_t atomai_b200_gram_workspace_bytes(int n1, int n2, int d) {
+  if (n1 < 0 || n2 < 0 || d <= 0) return -1;
+  const int Kp = aug_k(d);
+  return align256((int64_t)n1 * Kp * 4) + align256((int64_t)n2 * Kp * 4) +
+         align256(ab_pack_weights_tc_elems(kColBlock, Kp, 1, 1, AB_WMODE_FWD, 1) * 4) + 256;
+}
+
+extern "C" int atomai_b200_gram(const float* x1, const float* x2, const float* inv_ls,
+                                float outputscale, int n1, int n2, int d, int kind, int math,
+                                float* K, int64_t ldk, void* workspace, int64_t workspace_bytes,
+                                void* stream) {
+  AB_CHECK(x1 && x2 && inv_ls && K && workspace, "gram: null pointer");
+  AB_CHECK(n1 >= 0 && n2 >= 0 && d > 0 && ldk >= n2, "gram: bad dims n1=%d n2=%d d=%d", n1, n2, d);
+  AB_CHECK(kind == 0 || kind == 1, "gram: kind=%d", kind);
+  AB_CHECK(math == AB_MATH_FP32 || math == AB_MATH_TF32 || math == AB_MATH_TF32X3, "gram: math=%d",
+           math);
+  AB_CHECK(workspace_bytes >= atomai_b200_gram_workspace_bytes(n1, n2, d) &&
+               ((uintptr_t)workspace & 255) == 0,
+           "gram: workspace too small or unaligned (need %lld bytes, 256 B aligned)",
+           (long long)atomai_b200_gram_workspace_bytes(n1, n2, d));
+  if (n1 == 0 || n2 == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Kp = aug_k(d);
+  char* ws = static_cast<char*>(workspace);
+  float* a = reinterpret_cast<float*>(ws);
+  float* b = reinterpret_cast<float*>(ws + align256((int64_t)n1 * Kp * 4));
+  float* blob = reinterpret_cast<float*>(ws + align256((int64_t)n1 * Kp * 4) +
+                                         align256((int64_t)n2 * Kp * 4));
+  augment_kernel<<<(n1 + 7) / 8, 256, 0, st>>>(x1, inv_ls, n1, d, Kp, 0, a);
+  AB_LAUNCH_CHECK();
+  augment_kernel<<<(n2 + 7) / 8, 256, 0, st>>>(x2, inv_ls, n2, d, Kp, 1, b);
+  AB_LAUNCH_CHECK();
+  const int act = kind == 0 ? AB_ACT_RBF : AB_ACT_MATERN25;
+  int n1m = 0, n2m = 0;
+  if (math != AB_MATH_FP32 && (ldk % 4) == 0 && ((uintptr_t)K & 15) == 0) {
+    n1m = n1 & ~7;
+    n2m = n2 & ~15;
+  }
+  if (n1m > 0 && n2m > 0) {
+    // tensor path: K[0:n1m, c0:c1] = act(a'[0:n1m] . b'[c0:c1]^T), one launch per column block
+    ab_conv_t cd;
+    memset(&cd, 0, sizeof(cd));
+    cd.N = 1; cd.H = n1m / 8; cd.W = 8;
+    cd.ks_h = cd.ks_w = 1; cd.dil = 1; cd.nsrc = 1;
+    cd.src[0].ptr = a; cd.src[0].C = Kp; cd.src[0].ld = Kp;
+    cd.lrelu = outputscale; cd.math = math; cd.act = act;
+    const int x3 = math == AB_MATH_TF32X3;
+    for (int c0 = 0; c0 < n2m; c0 += kColBlock) {
+      const int cb = (n2m - c0) < kColBlock ? (n2m - c0) : kColBlock;
+      cd.Cout = cb;
+      if (ab_pack_weights_tc(b + (int64_t)c0 * Kp, cb, Kp, 1, 1, AB_WMODE_FWD, x3, blob, st)) return 1;
+      if (ab_conv_tc_fwd(&cd, blob, nullptr, K + c0, (int)ldk, nullptr, st)) return 1;
+    }
+  }
+  // exact FFMA tiles: everything (fp32 math) or the right / bottom remainders of the tensor path
+  if (gram_simt(a, b + (int64_t)n2m * Kp, n1m, n2 - n2m, Kp, outputscale, kind, K + n2m, ldk, st))
+    return 1;
+  if (gram_simt(a + (int64_t)n1m * Kp, b, n1 - n1m, n2, Kp, outputscale, kind,
+                K + (int64_t)n1m * ldk, ldk, st))
+    return 1;
   return 0;
 }

@@ -114,6 +114,7 @@ class Tape:
         self.comm = comm              # optional: object with allreduce_sum_(tensor) for SyncBN
         self.ops = []                 # recorded (kind, payload) in forward order
         self.param_grads = {}         # nn.Parameter -> grad tensor
+        self.alias = {}               # id(padded weight view) -> fn(grad) -> (nn.Parameter, grad)
         self.widths = []              # feature-map widths seen (get_downsample_factor)
 
     # ------------------------------------------------------------------ helpers
@@ -128,6 +129,11 @@ class Tape:
     def _add_pgrad(self, p, g: torch.Tensor) -> None:
         if p is None:
             return
+        h = self.alias.get(id(p))
+        if h is not None:             # gradient of a padded / blocked copy of a parameter
+            p, g = h(g)
+            if p is None:
+                return
         g = g.reshape(p.shape)
         if p in self.param_grads:
             self.param_grads[p] = self.param_grads[p] + g
@@ -136,7 +142,7 @@ class Tape:
 
     # ------------------------------------------------------------------ convolution layer
     def conv(self, srcs: Union[Act, Sequence[Act]], conv_mod, bn_mod=None, slope: float = 1.0,
-             act: int = ACT_LRELU, out_nchw: bool = False) -> Act:
+             act: int = ACT_LRELU, out_nchw: bool = False, out_t: Optional[torch.Tensor] = None) -> Act:
         """conv (+bias) -> activation -> [BatchNorm as a pending affine].
         conv_mod: nn.Conv2d / nn.Conv1d (k in {1,3}, stride 1, padding = dilation*(k//2));
         bn_mod: nn.BatchNorm2d/1d or None.  Reference: atomai/nets/blocks.py:61-76, 302-319."""
@@ -162,7 +168,9 @@ class Tape:
                           out_nchw, act)
         wp = ops.prep_weights(_w4(wt), ops.WMODE_FWD, math)
         dev = wt.device
-        if out_nchw:
+        if out_t is not None:          # caller-provided (channel slice of a wider) output buffer
+            assert not out_nchw and tuple(out_t.shape) == (n, h, w, cout)
+        elif out_nchw:
             out_t = torch.empty((n, cout, h, w), device=dev, dtype=torch.float32)
         else:
             out_t = torch.empty((n, h, w, cout), device=dev, dtype=torch.float32)
@@ -400,6 +408,64 @@ class Tape:
             self.ops.append(("lin", (x, out, lin_mod, act)))
         return out
 
+    def mlp(self, x: Act, lins: Sequence, acts: Sequence) -> Act:
+        """Chain of nn.Linear (+ReLU / tanh) layers on a (B,1,1,K) activation — the DKL feature
+        extractor (atomai/nets/gp.py:14-26: feat -> 1000 -> 500 -> 50 -> embedim) — on the tcgen05
+        convolution kernel: the B rows become the pixels of a (1, B/8, 8, K) image, each layer is a
+        1x1 convolution with fused bias + activation, wide layers run as column blocks of <= 256
+        outputs writing channel slices of one buffer.  Channel counts are zero-padded to the MMA
+        granularity (K % 8, N % 16) once per call; padded rows / channels stay exact zeros through
+        forward and backward.  fp32 math mode and tiny batches take the per-layer SIMT path."""
+        if x.pending():
+            x = self.materialize(x)
+        b, k = x.t.shape[0], x.t.shape[3]
+        if _MATH["mode"] == MATH_FP32 or b < 64:
+            for lin, a in zip(lins, acts):
+                x = self.linear(x, lin, a)
+            return x
+        dev = x.t.device
+        rows, kp = -(-b // 8) * 8, -(-k // 8) * 8
+        if rows != b or kp != k:
+            xin = torch.zeros((1, rows // 8, 8, kp), device=dev, dtype=torch.float32)
+            xin.view(rows, kp)[:b, :k] = x.t.view(b, k)
+        else:
+            xin = x.t.view(1, rows // 8, 8, k)
+        cur = Act(xin, needs_grad=x.needs_grad)
+        if self.record:
+            self.ops.append(("custom", _PadRec(x, cur, b, k)))
+        for lin, a in zip(lins, acts):
+            o, kk = lin.weight.shape
+            op = -(-o // 16) * 16
+            kcur = cur.t.shape[3]
+            wpad = torch.zeros((op, kcur), device=dev, dtype=torch.float32)
+            wpad[:o, :kk] = lin.weight.detach()
+            bpad = torch.zeros(op, device=dev, dtype=torch.float32)
+            if lin.bias is not None:
+                bpad[:o] = lin.bias.detach()
+            nblk = -(-op // 256)
+            per = -(-(op // 16) // nblk) * 16
+            buf = torch.empty((1, rows // 8, 8, op), device=dev, dtype=torch.float32)
+            a_id, slope = (ACT_TANH, 1.0) if a == ACT_TANH else \
+                (ACT_LRELU, 0.0 if a == "relu" else 1.0)
+            blocks = []
+            for c0 in range(0, op, per):
+                c1 = min(op, c0 + per)
+                ad = _PaddedBlock(wpad[c0:c1], bpad[c0:c1])
+                self.alias[id(ad.weight)] = _unpad_w(lin.weight, c0, min(c1, o), kk)
+                self.alias[id(ad.bias)] = _unpad_b(lin.bias, c0, min(c1, o))
+                blk = self.conv(cur, ad, None, slope, a_id, out_t=buf[..., c0:c1])
+                blocks.append((blk, c0, c1))
+            cur = Act(buf)
+            if self.record:
+                self.ops.append(("custom", _SplitRec(cur, blocks)))
+        o_last = lins[-1].weight.shape[0]
+        y = torch.empty((b, 1, 1, o_last), device=dev, dtype=torch.float32)
+        y.view(b, o_last).copy_(cur.t.view(rows, -1)[:b, :o_last])
+        out = Act(y)
+        if self.record:
+            self.ops.append(("custom", _PadRec(cur, out, b, o_last, unpad=True)))
+        return out
+
     def _lin_bwd(self, rec) -> None:
         x, out, lin_mod, act = rec
         if out.grad is None:
@@ -558,6 +624,69 @@ class Tape:
             else:
                 raise RuntimeError(kind)
         self.ops = []
+
+
+class _PaddedBlock:
+    """A row block of a zero-padded nn.Linear weight, presented as a 1x1 convolution."""
+    __slots__ = ("weight", "bias", "dilation", "stride", "padding")
+
+    def __init__(self, w, b):
+        self.weight, self.bias = w, b
+        self.dilation, self.stride, self.padding = (1, 1), (1, 1), (0, 0)
+
+
+def _unpad_w(param, r0, r1, k):
+    def fn(g):
+        if r1 <= r0:
+            return None, None
+        full = torch.zeros_like(param)
+        full[r0:r1] = g.reshape(g.shape[0], -1)[:r1 - r0, :k]
+        return param, full
+    return fn
+
+
+def _unpad_b(param, r0, r1):
+    def fn(g):
+        if param is None or r1 <= r0:
+            return None, None
+        full = torch.zeros_like(param)
+        full[r0:r1] = g.reshape(-1)[:r1 - r0]
+        return param, full
+    return fn
+
+
+class _PadRec:
+    """(B,1,1,K) <-> zero-padded (1, rows/8, 8, Kp) copy at the two ends of Tape.mlp."""
+    def __init__(self, src, dst, b, k, unpad=False):
+        self.src, self.dst, self.b, self.k, self.unpad = src, dst, b, k, unpad
+
+    def backward(self, tape):
+        src, dst = self.src, self.dst
+        if dst.grad is None or not src.needs_grad:
+            dst.grad = None
+            return
+        g = _dense(dst.grad)
+        dst.grad = None
+        gs = torch.zeros_like(src.t)
+        if self.unpad:      # forward sliced rows/channels out of the padded buffer
+            gs.view(gs.shape[1] * gs.shape[2], -1)[:self.b, :self.k] = g.view(self.b, self.k)
+        else:               # forward copied into the padded buffer
+            gs.view(self.b, self.k).copy_(g.view(g.shape[1] * g.shape[2], -1)[:self.b, :self.k])
+        _acc_grad(src, gs, True)
+
+
+class _SplitRec:
+    """Column blocks of one layer write channel slices of `merged`; route its gradient back."""
+    def __init__(self, merged, blocks):
+        self.merged, self.blocks = merged, blocks
+
+    def backward(self, tape):
+        g = self.merged.grad
+        self.merged.grad = None
+        if g is None:
+            return
+        for blk, c0, c1 in self.blocks:
+            blk.grad, blk.grad_owned = g[..., c0:c1], False
 
 
 def _d(p):

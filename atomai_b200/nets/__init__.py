@@ -3,9 +3,11 @@ from .ed import (SignalDecoder, SignalED, SignalEncoder, convDecoderNet, convEnc
                  coord_latent, fcDecoderNet, fcEncoderNet, init_imspec_model, init_VAE_nets,
                  rDecoderNet)
 from .fcnn import Unet, dilnet, init_fcnn_model
-from .gp import DeepKernel, GPRegressionModel, dense_gram, fcFeatureExtractor
+from .gp import (DeepKernel, GPRegressionModel, ScaleToBounds, dense_gram, dense_rbf,
+                 fcFeatureExtractor)
 
 __all__ = ["ConvBlock", "UpsampleBlock", "DilatedBlock", "Unet", "dilnet", "init_fcnn_model",
            "SignalEncoder", "SignalDecoder", "SignalED", "convEncoderNet", "convDecoderNet",
            "fcEncoderNet", "fcDecoderNet", "rDecoderNet", "coord_latent", "init_imspec_model",
-           "init_VAE_nets", "fcFeatureExtractor", "DeepKernel", "dense_gram", "GPRegressionModel"]
+           "init_VAE_nets", "fcFeatureExtractor", "DeepKernel", "dense_gram", "dense_rbf",
+           "ScaleToBounds", "GPRegressionModel"]

@@ -275,11 +275,15 @@ def coord_latent_bwd(d: _C.CoordLat, dpre0, dwc, dbc, sb, dphi, ddx) -> None:
                                              ptr(dphi), ptr(ddx), stream_ptr()))
 
 
-def gram(x1, x2, inv_ls, outputscale, kind, out) -> None:
+def gram(x1, x2, inv_ls, outputscale, kind, out, math=MATH_TF32X3) -> None:
     n1, d = x1.shape
     n2 = x2.shape[0]
+    nbytes = lib().atomai_b200_gram_workspace_bytes(n1, n2, d)
+    ws = torch.empty(nbytes + 256, device=x1.device, dtype=torch.uint8)
+    off = (-ws.data_ptr()) % 256
     check(lib().atomai_b200_gram(ptr(x1), ptr(x2), ptr(inv_ls), float(outputscale), n1, n2, d,
-                                 kind, ptr(out), out.stride(0), stream_ptr()))
+                                 kind, math, ptr(out), out.stride(0), ws.data_ptr() + off, nbytes,
+                                 stream_ptr()))
 
 
 def selftest_tma(x, c0, w0, h0, n0, TWp, THp, swizzle_mode, smem_offset, out) -> None:

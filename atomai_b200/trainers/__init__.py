@@ -1,3 +1,4 @@
+from .gptrainer import GPTrainer, dklGPTrainer
 from .trainer import BaseTrainer, ImSpecTrainer, SegTrainer
 
-__all__ = ["BaseTrainer", "SegTrainer", "ImSpecTrainer"]
+__all__ = ["BaseTrainer", "SegTrainer", "ImSpecTrainer", "GPTrainer", "dklGPTrainer"]

@@ -34,6 +34,8 @@ extern "C" {
 
 #define AB_ACT_LRELU 0
 #define AB_ACT_TANH 1
+#define AB_ACT_RBF 2      /* y = lrelu * exp(-0.5 * max(x, 0))        (Gram epilogue)      */
+#define AB_ACT_MATERN25 3 /* y = lrelu * (1 + s + s^2/3) exp(-s), s = sqrt(5 max(x, 0))   */
 
 #define AB_WMODE_FWD 0   /* weights as used by the forward conv           */
 #define AB_WMODE_DGRAD 1 /* flipped + transposed weights for data-gradient */
@@ -217,9 +219,15 @@ int atomai_b200_sqerr_reduce(const float* x, const float* xhat, int64_t n, doubl
 /* ---- DKL ----------------------------------------------------------------------
  * Dense Gram K[i][j] = os * k(||(x1_i - x2_j) * inv_ls||), kind 0 = RBF,
  * 1 = Matern-2.5 (gpytorch RBFKernel/MaternKernel/ScaleKernel as configured at
- * atomai/nets/gp.py:41-46, :100-111).  x: [n][d] row-major fp32, inv_ls: [d]. */
+ * atomai/nets/gp.py:41-46, :100-111).  x: [n][d] row-major fp32, inv_ls: [d].
+ * math: AB_MATH_TF32 / AB_MATH_TF32X3 run the contraction on the tcgen05 convolution kernel
+ * with the exponentiation in its TMEM epilogue, AB_MATH_FP32 on exact FFMA tiles.
+ * `workspace` (256 B aligned, >= atomai_b200_gram_workspace_bytes) is caller-owned scratch
+ * for the scaled/augmented operands; the library allocates nothing. */
+int64_t atomai_b200_gram_workspace_bytes(int n1, int n2, int d);
 int atomai_b200_gram(const float* x1, const float* x2, const float* inv_ls, float outputscale,
-                     int n1, int n2, int d, int kind, float* K, int64_t ldk, void* stream);
+                     int n1, int n2, int d, int kind, int math, float* K, int64_t ldk,
+                     void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ---- self-test hooks (tests only) ------------------------------------------------
  * Raw tcgen05 GEMM D[128][N] = A[128][K] B[N][K]^T on core-matrix ("interleave")

@@ -48,4 +48,5 @@ def test_error_convention_without_gpu():
     rc = lib.atomai_b200_conv_fwd(ctypes.byref(d), 1, None, 1, 16, None, None)
     assert rc != 0
     assert b"conv" in lib.atomai_b200_last_error()
-    assert lib.atomai_b200_gram(None, None, None, 1.0, 1, 1, 1, 0, None, 1, None) != 0
+    assert lib.atomai_b200_gram(None, None, None, 1.0, 1, 1, 1, 0, 2, None, 1, None, 0, None) != 0
+    assert lib.atomai_b200_gram_workspace_bytes(1000, 500, 128) >= (1000 + 500) * 160 * 4
