@@ -66,7 +66,9 @@ struct ConvTcParams {
   int sub;           // 8-pixel-wide sub-tiles per CTA tile (1 or 2): M = 128*sub per weight stage
   int w_resident;    // 1: all weights live in shared memory for the whole kernel
   int w_bytes;       // taps * Ctot * Cout * 4  (x3: twice that — hi and lo parts)
-  int x3;            // AB_MATH_TF32X3: every k-chunk runs three passes (a_hi*w_hi, a_lo*w_hi, a_hi*w_lo)
+  int x3;            // AB_MATH_TF32X3: every k-step issues a second, kind::f16 MMA on a bf16 operand
+                     // pair ([a_lo | a_hi] x [w ; w_lo]) that adds the two cross terms of the split
+  int corr_off;      // x3: byte offset of the correction planes inside an activation stage
 };
 
 struct __align__(8) SharedCtl {
@@ -97,12 +99,15 @@ __device__ __forceinline__ void mma_issue_loop(const ConvTcParams& p, SharedCtl*
   const uint32_t dx16 = p.dil, dy16 = (uint32_t)p.dil * p.TWp;     // tap steps of A (16 B units)
   const int th = p.taps_h, tw = p.taps_w, taps = th * tw;
   // resident weights: piece index = (chunk*KSTEPS + ks)*taps + t
-  // (x3: the blob interleaves a hi and a lo piece set per k-step, see pack_weights_tc_kernel)
-  const uint32_t wmult = p.x3 ? 2u : 1u;
-  const uint32_t b_ks16 = RESIDENT ? wmult * (uint32_t)taps * piece16 : piece16;
+  // (x3: the blob interleaves a main and a correction piece per k-step, see
+  //  pack_weights_tc_kernel; a streamed weight stage holds [k-step][main, corr] pieces)
+  const bool x3 = p.x3 != 0;
+  const uint32_t wmult = x3 ? 2u : 1u;
+  const uint32_t b_ks16 = RESIDENT ? wmult * (uint32_t)taps * piece16 : wmult * piece16;
   const uint32_t chunk_w16 = wmult * (uint32_t)(KSTEPS * taps) * piece16;
-  const uint32_t lo_w16 = (uint32_t)taps * piece16;                // lo piece set of a k-step
-  const uint32_t n_pass = p.x3 ? 3u : 1u;
+  const uint32_t corr_w16 = RESIDENT ? (uint32_t)taps * piece16 : piece16;   // main -> corr piece
+  const uint32_t corr_a16 = (uint32_t)p.corr_off >> 4;                       // main -> corr planes
+  const uint32_t idesc_c = umma_idesc_bf16(128, p.Cout, 0, 0);
   uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
   const uint32_t bar_full_a = smem_u32(&ctl->full_a[0]), bar_empty_a = smem_u32(&ctl->empty_a[0]);
   const uint32_t bar_full_b = smem_u32(&ctl->full_b[0]), bar_empty_b = smem_u32(&ctl->empty_b[0]);
@@ -134,12 +139,11 @@ __device__ __forceinline__ void mma_issue_loop(const ConvTcParams& p, SharedCtl*
     const uint32_t d_tmem = tmem_base + a_ * SUB * cout;
     uint32_t accum = 0u;
     uint32_t b_tap = b_lo0;                                        // resident: running piece
-    for (uint32_t ch = 0; ch < n_chunks; ++ch)
-     for (uint32_t ps = 0; ps < n_pass; ++ps) {
+    for (uint32_t ch = 0; ch < n_chunks; ++ch) {
       mbar_wait(bar_full_a + (ring0 + sa) * 8, pa);
       tc_fence_after();
       uint32_t a_row = a_lo0 + (ring0 + sa) * a_stage16;
-      if (RESIDENT) b_tap = b_lo0 + ch * chunk_w16 + (ps == 2 ? lo_w16 : 0u);
+      if (RESIDENT) b_tap = b_lo0 + ch * chunk_w16;
       for (int ty = 0; ty < th; ++ty, a_row += dy16) {
         uint32_t a_tap = a_row;
         for (int tx = 0; tx < tw; ++tx, a_tap += dx16, b_tap += piece16) {
@@ -155,6 +159,12 @@ __device__ __forceinline__ void mma_issue_loop(const ConvTcParams& p, SharedCtl*
             umma_tf32_lh(d_tmem, ad, a_hi, bd, b_hi, idesc, accum);
             if (SUB > 1) umma_tf32_lh(d_tmem + cout, ad + (kTileW * 16 >> 4), a_hi, bd, b_hi, idesc, accum);
             accum = 1u;
+            if (x3) {   // + a_lo*w + a_hi*w_lo: one bf16 MMA (K = 16) on the correction planes
+              umma_bf16_lh(d_tmem, ad + corr_a16, a_hi, bd + corr_w16, b_hi, idesc_c, 1u);
+              if (SUB > 1)
+                umma_bf16_lh(d_tmem + cout, ad + corr_a16 + (kTileW * 16 >> 4), a_hi, bd + corr_w16,
+                             b_hi, idesc_c, 1u);
+            }
           }
           if (!RESIDENT) {
             umma_commit(bar_empty_b + (b_ring0 + sb) * 8);
@@ -216,18 +226,19 @@ __device__ __forceinline__ void loader_loop(const ConvTcParams& p, SharedCtl* ct
   const uint32_t ring_n = dual ? n_a / 2 : n_a;
   const uint32_t ring0 = dual ? grp * ring_n : 0u;
   int tile = dual ? blockIdx.x + grp * gridDim.x : blockIdx.x;
-  // x3: chunk counter `ch` runs over (real chunk, pass) pairs; pass 1 stages the low part
-  // a - rn_tf32(a) of the activations (exact in fp32), passes 0 and 2 the high part.
-  const int n_pass = p.x3 ? 3 : 1;
-  const int n_chunks_eff = n_chunks * n_pass;
+  const int n_chunks_eff = n_chunks;
+  // x3: besides the TF32 planes every element also goes, as bf16, into the correction planes of
+  // its k-step: plane 2*ks holds the low parts a - rn_tf32(a) of the 8 channels, plane 2*ks + 1
+  // the high parts (one 16-byte row per pixel each = one K-major core-matrix row of a K = 16 MMA).
+  const bool x3 = p.x3 != 0;
+  const uint32_t corr_dst0 = a_base + p.corr_off + (j >> 1) * 2 * p.plane_bytes + q0 * 16 + (j & 1) * 8;
   int ch = dual ? 0 : grp;
   uint32_t st = dual ? 0u : grp % n_a;
   uint32_t ph = dual ? 1u : ((grp / n_a) & 1) ^ 1;   // stage / empty-phase of the current chunk
   for (;;) {
     while (ch >= n_chunks_eff) { ch -= n_chunks_eff; tile += tile_step; }
     if (tile >= p.num_tiles) break;
-    const int ch_real = p.x3 ? ch / 3 : ch;
-    const bool lo_pass = p.x3 && (ch - 3 * ch_real) == 1;
+    const int ch_real = ch;
     // tile -> (n, th_i, tw_i) without integer division
     int n = __float2int_rz((float)tile * inv_tpi);
     n += ((n + 1) * tpi <= tile) - (n * tpi > tile);
@@ -312,17 +323,29 @@ __device__ __forceinline__ void loader_loop(const ConvTcParams& p, SharedCtl* ct
         v[u] = make_float4(ok ? mx : 0.f, ok ? my : 0.f, ok ? mz : 0.f, ok ? mw : 0.f);
       }
     }
-    if (lo_pass) {
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        v[u].x -= __uint_as_float(tf32_bits(v[u].x) & 0xFFFFE000u);
-        v[u].y -= __uint_as_float(tf32_bits(v[u].y) & 0xFFFFE000u);
-        v[u].z -= __uint_as_float(tf32_bits(v[u].z) & 0xFFFFE000u);
-        v[u].w -= __uint_as_float(tf32_bits(v[u].w) & 0xFFFFE000u);
-      }
-    }
     mbar_wait(bar_empty_a + (ring0 + st) * 8, ph);
     const uint32_t dst = dst0 + (ring0 + st) * p.a_stage_bytes;
+    if (x3) {
+      const uint32_t cdst = corr_dst0 + (ring0 + st) * p.a_stage_bytes;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const float hx = __uint_as_float(tf32_bits(v[u].x) & 0xFFFFE000u);
+        const float hy = __uint_as_float(tf32_bits(v[u].y) & 0xFFFFE000u);
+        const float hz = __uint_as_float(tf32_bits(v[u].z) & 0xFFFFE000u);
+        const float hw_ = __uint_as_float(tf32_bits(v[u].w) & 0xFFFFE000u);
+        const uint32_t l01 = pack_bf16x2(v[u].x - hx, v[u].y - hy);
+        const uint32_t l23 = pack_bf16x2(v[u].z - hz, v[u].w - hw_);
+        const uint32_t h01 = pack_bf16x2(hx, hy), h23 = pack_bf16x2(hz, hw_);
+        const uint32_t ok = u == U - 1 ? last_valid : 1u;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %5, 0;\n\t"
+            "@p st.shared.v2.b32 [%0], {%1, %2};\n\t"
+            "@p st.shared.v2.b32 [%6], {%3, %4};\n\t}" ::"r"(cdst + u * qs16),
+            "r"(l01), "r"(l23), "r"(h01), "r"(h23), "r"(ok),
+            "r"(cdst + u * qs16 + (uint32_t)p.plane_bytes)
+            : "memory");
+      }
+    }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       asm volatile(
@@ -561,22 +584,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
         const uint32_t b_stage = p.b_stage_bytes;
         const uint32_t bar_full_b = smem_u32(&ctl->full_b[0]), bar_empty_b = smem_u32(&ctl->empty_b[0]);
         for (int tile = blockIdx.x + pipe * gridDim.x; tile < p.num_tiles; tile += 2 * gridDim.x) {
-          const int wmult = p.x3 ? 2 : 1, n_pass = p.x3 ? 3 : 1;
+          const int wmult = p.x3 ? 2 : 1;
           for (int ch = 0; ch < p.n_chunks; ++ch) {
-           for (int ps = 0; ps < n_pass; ++ps) {
             for (int t = 0; t < taps; ++t) {
               mbar_wait(bar_empty_b + (ring0 + st) * 8, ph);
               const uint32_t bar = bar_full_b + (ring0 + st) * 8;
               mbar_arrive_expect_tx(bar, b_stage);
-              // piece (k-step s, kind, tap) of the blob lives at ((s*wmult + kind)*taps + tap)
-              const float* src = p.wblob +
-                  (((size_t)ch * ksteps * wmult + (ps == 2 ? 1 : 0)) * taps + t) * (piece >> 2);
+              // piece (k-step s, kind, tap) of the blob lives at ((s*wmult + kind)*taps + tap);
+              // the stage holds [k-step][kind] pieces
               for (int ks = 0; ks < ksteps; ++ks)
-                bulk_g2s(b_base + (ring0 + st) * b_stage + ks * piece,
-                         src + (size_t)ks * wmult * taps * (piece >> 2), piece, bar);
+                for (int kd = 0; kd < wmult; ++kd)
+                  bulk_g2s(b_base + (ring0 + st) * b_stage + (ks * wmult + kd) * piece,
+                           p.wblob + ((((size_t)ch * ksteps + ks) * wmult + kd) * taps + t) * (piece >> 2),
+                           piece, bar);
               if (++st == nb2) { st = 0; ph ^= 1; }
             }
-           }
           }
         }
       }
@@ -630,8 +652,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
 // piece is a ready-made UMMA K-major B operand for one tcgen05.mma (N rows x 8 k).
 //   FWD  : B[n = co][k = ci]            = W[co][ci][ty][tx]
 //   DGRAD: B[n = ci][k = co] (roles swap) = W[co][ci][Th-1-ty][Tw-1-tx]
-// x3 (AB_MATH_TF32X3): blob[k-step][kind (hi, lo)][tap][plane][n][4] with hi = rn_tf32(W) and
-// lo = rn_tf32(W - hi), so that a_hi*w_hi + a_lo*w_hi + a_hi*w_lo carries ~2^-21 relative error.
+// x3 (AB_MATH_TF32X3): blob[k-step][kind (main, corr)][tap][plane][n][4 words]: the main piece as
+// above (hi = rn_tf32(W)); the correction piece is the K-major bf16 B operand of a K = 16 MMA,
+// plane 0 = bf16(W) of the k-step's 8 channels (meets the activations' low parts), plane 1 =
+// bf16(W - hi) (meets their high parts): a_hi*w_hi + (a_lo*w + a_hi*w_lo) ~ 2^-20 relative.
 __global__ void pack_weights_tc_kernel(const float* __restrict__ w, int Cout, int Cin, int th,
                                        int tw, int mode, int x3, float* __restrict__ out,
                                        int64_t total) {
@@ -648,18 +672,20 @@ __global__ void pack_weights_tc_kernel(const float* __restrict__ w, int Cout, in
     int kind = 0;
     if (x3) { kind = r % 2; r /= 2; }
     const int ks = (int)r;
-    const int k = ks * 8 + j * 4 + e;
-    float v = 0.f;
-    if (k < Kk) {
-      const int ty = t / tw, tx = t % tw;
-      if (mode == AB_WMODE_FWD) {
-        v = w[(((int64_t)nn * Cin + k) * th + ty) * tw + tx];
-      } else {
-        v = w[(((int64_t)k * Cin + nn) * th + (th - 1 - ty)) * tw + (tw - 1 - tx)];
-      }
+    const int ty = t / tw, tx = t % tw;
+    auto wv = [&](int k) -> float {
+      if (k >= Kk) return 0.f;
+      return mode == AB_WMODE_FWD
+                 ? w[(((int64_t)nn * Cin + k) * th + ty) * tw + tx]
+                 : w[(((int64_t)k * Cin + nn) * th + (th - 1 - ty)) * tw + (tw - 1 - tx)];
+    };
+    if (!kind) {
+      out[i] = to_tf32(wv(ks * 8 + j * 4 + e));
+    } else {   // word e of plane j holds channels ks*8 + 2e, 2e + 1 as bf16 (j: 0 = W, 1 = W - hi)
+      const float v0 = wv(ks * 8 + 2 * e), v1 = wv(ks * 8 + 2 * e + 1);
+      const float a0 = j ? v0 - to_tf32(v0) : v0, a1 = j ? v1 - to_tf32(v1) : v1;
+      out[i] = __uint_as_float(pack_bf16x2(a0, a1));
     }
-    const float hi = to_tf32(v);
-    out[i] = kind ? to_tf32(v - hi) : hi;
   }
 }
 
@@ -737,9 +763,9 @@ static int conv_tc_plan(const ab_conv_t* d, ConvTcParams* p, int* smem_bytes) {
       int plane = p->HP * 16;
       const int want = (128 / P) % 128;  // plane stride mod 128 spreading the P planes over banks
       plane += ((want - plane % 128) + 128) % 128;
-      const int a_stage = P * plane;
+      const int a_stage = P * plane * (p->x3 ? 2 : 1);    // x3: + the bf16 correction planes
       int avail = budget - stats_bytes;
-      int n_b = 0, b_stage = KC * d->Cout * 4;
+      int n_b = 0, b_stage = KC * d->Cout * 4 * (p->x3 ? 2 : 1);
       if (resident) {
         avail -= (p->w_bytes + 127) & ~127;
       } else {
@@ -752,6 +778,7 @@ static int conv_tc_plan(const ab_conv_t* d, ConvTcParams* p, int* smem_bytes) {
       int na = avail / a_stage;
       if (na < 2) continue;
       p->KC = KC; p->plane_bytes = plane; p->a_stage_bytes = a_stage; p->b_stage_bytes = b_stage;
+      p->corr_off = P * plane;
       p->n_a = na > kMaxAStages ? kMaxAStages : na;
       p->n_a &= ~1;   // two rings of n_a/2 stages
       p->n_b = n_b; p->sub = sub; p->w_resident = resident;

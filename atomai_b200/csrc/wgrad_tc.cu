@@ -56,7 +56,11 @@ struct WgradTcParams {
   int fs;                // "fully stacked": Cout <= 32, the kernel rows ride on N (one MMA / halo row)
   int dpad;              // fs: zero rows in front of / behind the dy tile = (taps_h - 1) * dil
   int tmem_cols;
-  int x3;                // AB_MATH_TF32X3: every tile runs three passes (x_hi*dy_hi, x_lo*dy_hi, x_hi*dy_lo)
+  int x3;                // AB_MATH_TF32X3: a stage holds [x_hi][x_lo][dy_hi][dy_lo] (each value split into
+                         // rn_tf32(v) and the exact remainder) and every MMA is issued for the three
+                         // pairs (x_hi, dy_hi), (x_lo, dy_hi), (x_hi, dy_lo)
+  int dy_bytes;          // bytes of one dy tile inside a stage
+  int cob;               // output channels per CTA (128, or 64 when two stages would not fit)
 };
 
 struct __align__(8) Ctl {
@@ -114,17 +118,13 @@ __device__ __forceinline__ void wgrad_loader(const WgradTcParams& p, Ctl* ctl, u
   const bool any_pool = p.S.s[0].pool || (p.S.nsrc > 1 && p.S.s[1].pool);
   const bool has_aff = p.S.s[0].scale != nullptr || (p.S.nsrc > 1 && p.S.s[1].scale != nullptr);
   // this thread's halo pixels (up to 5 slots of 128: dilated kernels), row/col within the halo
-  const uint32_t d_rel = p.x_bytes + (p.fs ? p.dpad * 1024 : 0);   // dy tile within a stage
+  const uint32_t d_rel = p.x_bytes * (p.x3 ? 2 : 1) + (p.fs ? p.dpad * 1024 : 0);   // dy tile within a stage
   const uint32_t d_row = d_rel + gt * 128, d_sw = (uint32_t)(gt & 3) << 5;
   const int d_r = gt >> 3, d_c = gt & 7;
   uint32_t st = grp % S, ph = ((grp / S) & 1) ^ 1;     // ring slot / empty-phase of this tile
-  const int n_pass = p.x3 ? 3 : 1;
-  const uint32_t mul3 = fdiv_mul(3);
-  for (int vt = t_begin * n_pass + grp; vt < t_end * n_pass; vt += n_groups) {
-    // x3: virtual tile vt = 3 * tile + pass; pass 1 stages the low part of x, pass 2 of dy
-    const int tile = p.x3 ? (int)fdiv(vt, 3, mul3) : vt;
-    const int pass = vt - tile * n_pass;
-    const bool x_lo = pass == 1, d_lo = pass == 2;
+  const bool x3 = p.x3 != 0;
+  const uint32_t xlo_off = p.x_bytes, dlo_off = p.dy_bytes;    // hi tile -> lo tile (x3)
+  for (int tile = t_begin + grp; tile < t_end; tile += n_groups) {
     const uint32_t x0 = base + st * p.stage_bytes;
     const int n = (int)fdiv(tile, tpi, mulTpi);
     const int rem = tile - n * tpi;
@@ -166,10 +166,14 @@ __device__ __forceinline__ void wgrad_loader(const WgradTcParams& p, Ctl* ctl, u
                 x.x = fmaf(x.x, sc.x, sh.x); x.y = fmaf(x.y, sc.y, sh.y);
                 x.z = fmaf(x.z, sc.z, sh.z); x.w = fmaf(x.w, sc.w, sh.w);
               }
-              x = part4(x, x_lo);
               const uint32_t dst = (stacked ? row : row + (j >> 3) * p.x_chunk) +
                                    (((uint32_t)(j & 7) << 4) ^ sw);
               sts128u(dst, tf32b(x.x) & msk, tf32b(x.y) & msk, tf32b(x.z) & msk, tf32b(x.w) & msk);
+              if (x3) {
+                const float4 l = part4(x, true);
+                sts128u(dst + xlo_off, tf32b(l.x) & msk, tf32b(l.y) & msk, tf32b(l.z) & msk,
+                        tf32b(l.w) & msk);
+              }
             }
           }
         }
@@ -179,7 +183,7 @@ __device__ __forceinline__ void wgrad_loader(const WgradTcParams& p, Ctl* ctl, u
           float4 v[4];
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            if (jb + k < PX) v[k] = part4(load_src4(p.S, n, gh, gw, H, W, ci0 + (jb + k) * 4), x_lo);
+            if (jb + k < PX) v[k] = load_src4(p.S, n, gh, gw, H, W, ci0 + (jb + k) * 4);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const int j = jb + k;
@@ -187,6 +191,10 @@ __device__ __forceinline__ void wgrad_loader(const WgradTcParams& p, Ctl* ctl, u
               const uint32_t dst = (stacked ? row : row + (j >> 3) * p.x_chunk) +
                                    (((uint32_t)(j & 7) << 4) ^ sw);
               sts128u(dst, tf32b(v[k].x), tf32b(v[k].y), tf32b(v[k].z), tf32b(v[k].w));
+              if (x3) {
+                const float4 l = part4(v[k], true);
+                sts128u(dst + xlo_off, tf32b(l.x), tf32b(l.y), tf32b(l.z), tf32b(l.w));
+              }
             }
           }
         }
@@ -202,14 +210,20 @@ __device__ __forceinline__ void wgrad_loader(const WgradTcParams& p, Ctl* ctl, u
         float4 v[kJB];
 #pragma unroll
         for (int k = 0; k < kJB; ++k)
-          if (jb + k < PD) v[k] = part4(__ldg(reinterpret_cast<const float4*>(db + (jb + k) * 4)), d_lo);
+          if (jb + k < PD) v[k] = __ldg(reinterpret_cast<const float4*>(db + (jb + k) * 4));
 #pragma unroll
         for (int k = 0; k < kJB; ++k) {
           const int j = jb + k;
-          if (j < PD)
-            sts128u(x0 + d_row + (j >> 3) * kChunk + (((uint32_t)(j & 7) << 4) ^ d_sw),
-                    tf32b(v[k].x) & msk, tf32b(v[k].y) & msk, tf32b(v[k].z) & msk,
+          if (j < PD) {
+            const uint32_t dst = x0 + d_row + (j >> 3) * kChunk + (((uint32_t)(j & 7) << 4) ^ d_sw);
+            sts128u(dst, tf32b(v[k].x) & msk, tf32b(v[k].y) & msk, tf32b(v[k].z) & msk,
                     tf32b(v[k].w) & msk);
+            if (x3) {
+              const float4 l = part4(v[k], true);
+              sts128u(dst + dlo_off, tf32b(l.x) & msk, tf32b(l.y) & msk, tf32b(l.z) & msk,
+                      tf32b(l.w) & msk);
+            }
+          }
         }
       }
     }
@@ -237,8 +251,8 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const WgradTcPara
   const int per = (p.num_tiles + p.ranges - 1) / p.ranges;
   const int t_begin = r * per;
   const int t_end = min(p.num_tiles, t_begin + per);
-  const int co0 = cb * 128;
-  const int co_n = min(128, p.Cout - co0);          // valid output channels in this block
+  const int co0 = cb * p.cob;
+  const int co_n = min(p.cob, p.Cout - co0);        // valid output channels in this block
   const int ci0 = cc * p.cib;
   const int ci_n = min(p.cib, p.Cin - ci0);         // valid input channels in this block
   const int PD = co_n >> 2, PX = ci_n >> 2;         // 16 B pieces per pixel
@@ -324,13 +338,17 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const WgradTcPara
       const uint32_t a_hi = (uint32_t)(a_tmpl >> 32), b_hi = (uint32_t)(b_tmpl >> 32);
       uint32_t st = 0, ph = 0;
       const int n_pass = p.x3 ? 3 : 1;
-      for (int tile = t_begin * n_pass; tile < t_end * n_pass; ++tile) {
+      const uint32_t xmul = p.x3 ? 2u : 1u;
+      for (int tile = t_begin; tile < t_end; ++tile) {
         mbar_wait(smem_u32(&ctl->full[st]), ph);
         tc_fence_after();
-        const uint32_t x0 = base + st * p.stage_bytes, d0 = x0 + p.x_bytes;
+       for (int ps = 0; ps < n_pass; ++ps) {
+        // pass 0: x_hi * dy_hi, 1: x_lo * dy_hi, 2: x_hi * dy_lo
+        const uint32_t x0 = base + st * p.stage_bytes + (ps == 1 ? p.x_bytes : 0);
+        const uint32_t d0 = base + st * p.stage_bytes + xmul * p.x_bytes + (ps == 2 ? p.dy_bytes : 0);
         const uint32_t a0 = (uint32_t)a_tmpl + (x0 >> 4);
         const uint32_t b0 = (uint32_t)b_tmpl + (d0 >> 4);
-        uint32_t accum = tile > t_begin * n_pass ? 1u : 0u;
+        uint32_t accum = (tile > t_begin || ps > 0) ? 1u : 0u;
         if (p.fs) {
           // one MMA per halo row r: A = x row r (tx on M), B = dy rows r-(th-1-c)*dil (ty on N)
           uint32_t ad = a0, bd = b0;
@@ -357,6 +375,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const WgradTcPara
             }
           }
         }
+       }
         umma_commit(smem_u32(&ctl->empty[st]));
         if (++st == S) { st = 0; ph ^= 1; }
       }
@@ -390,32 +409,42 @@ int wgrad_plan(const ab_conv_t* d, WgradTcParams* p, int* smem_bytes) {
   p->TWp = kTileW + d->dil * (d->ks_w - 1);
   p->HP = p->THp * p->TWp;
   const bool stacked = d->ks_w > 1;
-  p->co_blocks = (d->Cout + 127) / 128;
-  const int co_max = d->Cout < 128 ? d->Cout : 128;
-  const int npad = (co_max + 31) & ~31;
-  const int d_bytes = (npad / 32) * kChunk;
-  // A stage is [x tile][dy tile]: the don't-care rows of the M = 128 operand (chunk 3 of a 3-wide
-  // kernel, chunks >= cib/32 of a 1x1 kernel) then alias the dy tile — finite and in bounds.
+  // A stage is [x tile][dy tile] (x3: [x_hi][x_lo][dy_hi][dy_lo]): the don't-care rows of the
+  // M = 128 operand (chunk 3 of a 3-wide kernel, chunks >= cib/32 of a 1x1 kernel) then alias
+  // whatever follows the x tile — finite and in bounds.  Search the widest (output-channel block,
+  // input-channel block) for which two stages fit.
   p->fs = stacked && d->Cout <= 32 && d->ks_h > 1;
   p->dpad = p->fs ? (d->ks_h - 1) * d->dil : 0;
-  int dy_bytes = d_bytes;
-  if (p->fs) dy_bytes = (kTileH + 2 * p->dpad + (d->ks_h - 1) * d->dil) * 1024;   // + chunk over-read
-  if (stacked) {
-    p->cib = 32;
-    p->x_chunk = 0;
-    p->x_bytes = (p->HP * 128 + 1023) & ~1023;
-    AB_CHECK(3 * d->dil * 128 + 1024 <= dy_bytes, "wgrad_tc: dilation %d too large", d->dil);
-  } else {
-    p->x_chunk = (p->HP * 128 + 1023) & ~1023;
-    p->cib = 128;
-    if (2 * (4 * p->x_chunk + d_bytes) + 3072 > 225 * 1024) p->cib = 64;
-    p->x_bytes = (p->cib / 32) * p->x_chunk;
-    AB_CHECK(p->cib == 128 || 2 * p->x_chunk <= d_bytes, "wgrad_tc: no shared-memory plan");
+  const int mult = p->x3 ? 2 : 1;
+  const int smem_cap = 225 * 1024 - 128 - 2048;
+  bool ok = false;
+  int npad = 0;
+  for (int cob = 128; cob >= 64 && !ok; cob >>= 1) {
+    const int co_max = d->Cout < cob ? d->Cout : cob;
+    npad = (co_max + 31) & ~31;
+    int dy_bytes = (npad / 32) * kChunk;
+    if (p->fs) dy_bytes = (kTileH + 2 * p->dpad + (d->ks_h - 1) * d->dil) * 1024;   // + chunk over-read
+    for (int cib = stacked ? 32 : 128; cib >= 32 && !ok; cib >>= 1) {
+      int x_chunk = 0, x_bytes;
+      if (stacked) {
+        x_bytes = (p->HP * 128 + 1023) & ~1023;
+        if (3 * d->dil * 128 + 1024 > dy_bytes) continue;
+      } else {
+        x_chunk = (p->HP * 128 + 1023) & ~1023;
+        x_bytes = (cib / 32) * x_chunk;
+      }
+      const int stage = mult * (x_bytes + dy_bytes);
+      if (2 * stage > smem_cap) continue;
+      if (!stacked && (p->x3 ? x_bytes : 0) + 4 * x_chunk > stage) continue;   // aliased chunks in bounds
+      p->cob = cob; p->cib = cib; p->x_chunk = x_chunk; p->x_bytes = x_bytes;
+      p->dy_bytes = dy_bytes; p->stage_bytes = stage;
+      ok = true;
+    }
   }
-  p->stage_bytes = p->x_bytes + dy_bytes;
-  int ns = (225 * 1024 - 128 - 2048) / p->stage_bytes;
+  AB_CHECK(ok, "wgrad_tc: no shared-memory plan (Cin=%d Cout=%d dil=%d)", p->Cin, d->Cout, d->dil);
+  p->co_blocks = (d->Cout + p->cob - 1) / p->cob;
+  int ns = smem_cap / p->stage_bytes;
   if (ns > kMaxStages) ns = kMaxStages;
-  AB_CHECK(ns >= 2, "wgrad_tc: halo tile too large for shared memory (dil=%d)", d->dil);
   p->n_stages = ns;
   *smem_bytes = ns * p->stage_bytes + 128 + 2048;
   p->n_cc = (p->Cin + p->cib - 1) / p->cib;
