@@ -95,7 +95,7 @@ def _dense(g: torch.Tensor) -> torch.Tensor:
 
 class _ConvRec:
     __slots__ = ("srcs", "out", "conv", "bn", "ks", "dil", "act", "slope", "math", "mean",
-                 "invstd", "scale", "count", "needs_in_grad")
+                 "invstd", "scale", "count", "needs_in_grad", "drop")
 
 
 class _PointwiseAdapter:
@@ -142,7 +142,8 @@ class Tape:
 
     # ------------------------------------------------------------------ convolution layer
     def conv(self, srcs: Union[Act, Sequence[Act]], conv_mod, bn_mod=None, slope: float = 1.0,
-             act: int = ACT_LRELU, out_nchw: bool = False, out_t: Optional[torch.Tensor] = None) -> Act:
+             act: int = ACT_LRELU, out_nchw: bool = False, out_t: Optional[torch.Tensor] = None,
+             p_drop: float = 0.0) -> Act:
         """conv (+bias) -> activation -> [BatchNorm as a pending affine].
         conv_mod: nn.Conv2d / nn.Conv1d (k in {1,3}, stride 1, padding = dilation*(k//2));
         bn_mod: nn.BatchNorm2d/1d or None.  Reference: atomai/nets/blocks.py:61-76, 302-319."""
@@ -177,7 +178,17 @@ class Tape:
         use_batch_stats = bn_mod is not None and (self.training or bn_mod.running_mean is None)
         stats = torch.zeros(2 * cout, device=dev, dtype=torch.float64) if use_batch_stats else None
         bias = conv_mod.bias
-        ops.conv_fwd(d, wp, None if bias is None else bias.detach(), out_t, stats)
+        # nn.Dropout sits between the convolution and the LeakyReLU (blocks.py:68-70); inverted
+        # dropout scales by 1/(1-p) > 0 or zeroes, so it commutes with the fused LeakyReLU and is
+        # applied to the kernel's output, with the BatchNorm statistics taken after it.
+        drop = None
+        if p_drop > 0 and self.training:
+            assert not out_nchw and act == ACT_LRELU
+            drop = (float(p_drop), int(torch.randint(0, 2 ** 62, (1,)).item()))
+        ops.conv_fwd(d, wp, None if bias is None else bias.detach(), out_t,
+                     None if drop is not None else stats)
+        if drop is not None:
+            ops.dropout_(out_t, drop[0], drop[1], stats)
         self.widths.append(w)
         scale = shift = mean = invstd = None
         count = n * h * w
@@ -208,6 +219,7 @@ class Tape:
             r.act, r.slope, r.math, r.mean, r.invstd, r.scale, r.count = \
                 act, slope, math, mean, invstd, scale, count
             r.needs_in_grad = any(s.needs_grad for s in srcs)
+            r.drop = drop
             assert not (bn_mod is not None and not use_batch_stats), \
                 "backward through eval-mode BatchNorm is not supported"
             assert not out_nchw or True
@@ -238,7 +250,12 @@ class Tape:
         dpre = torch.empty((n, h, w, cout), device=dev, dtype=torch.float32)
         dbias = torch.zeros(cout, device=dev, dtype=torch.float64) if r.conv.bias is not None else None
         ops.bn_act_bwd(dy, a, r.mean, r.invstd, r.scale if r.bn is not None else None, sums,
-                       r.count, out.extra, r.act, r.slope, dpre, dbias)
+                       r.count, out.extra, r.act, r.slope, dpre, None if r.drop else dbias)
+        if r.drop:            # same (seed, index) mask on the gradient; bias gradient after it
+            dsum = torch.zeros(2 * cout, device=dev, dtype=torch.float64)
+            ops.dropout_(dpre, r.drop[0], r.drop[1], dsum)
+            if dbias is not None:
+                dbias = dsum[:cout]
         out.grad = None
         out.extra = None
         if dbias is not None:

@@ -79,6 +79,50 @@ class BaseVAE(viBaseTrainer):
     def encode(self, x_new, **kwargs: int) -> Tuple[np.ndarray]:
         return self.encode_(x_new, **kwargs)
 
+    def encode_image_(self, img: np.ndarray, **kwargs: int) -> Tuple[np.ndarray, np.ndarray]:
+        """Crops and encodes a sub-image around each pixel of a 2-D image (vae.py:300-344); the
+        window size is the VAE's input size.  The reference extracts the windows coordinate by
+        coordinate on the CPU; here the image lives on the GPU, every batch of windows is one
+        gather kernel and goes straight into the encoder.  Returns the cropped original image
+        and the (h', w', z_dim) encoded array (cropping is due to the finite window size)."""
+        from ...utils.img import crop_borders, extract_subimages_cuda, get_coord_grid
+        num_batches = kwargs.get("num_batches", 10)
+        inf = int(1e5)
+        img_to_encode = np.array(img, dtype=np.float64, copy=True)
+        dev_img = torch.from_numpy(img_to_encode.astype(np.float32))[None, ..., None].to(self.device)
+        coordinates = get_coord_grid(img_to_encode, 1, return_dict=False)
+        batch_size = max(coordinates.shape[0] // num_batches, 1)
+        encoded_img = -inf * np.ones((*img_to_encode.shape, self.z_dim))
+        self.encoder_net.eval()
+        for i in range(0, coordinates.shape[0], batch_size):
+            coord_i = coordinates[i:i + batch_size]
+            subimgs_i, com_i, _ = extract_subimages_cuda(dev_img, coord_i, self.in_dim[0])
+            if len(subimgs_i) == 0:
+                continue
+            if len(self.in_dim) == 2:
+                subimgs_i = subimgs_i[..., 0]
+            zs = []
+            with torch.no_grad():
+                for j in range(0, len(subimgs_i), 2048):
+                    zs.append(self.encoder_net(subimgs_i[j:j + 2048])[0])
+            z_mean = torch.cat(zs).cpu().numpy()
+            encoded_img[com_i[:, 0].astype(int), com_i[:, 1].astype(int)] = z_mean
+        img_to_encode[encoded_img[..., 0] == -inf] = 0
+        img_to_encode = crop_borders(img_to_encode[..., None], 0)
+        encoded_img = crop_borders(encoded_img, -inf)
+        return img_to_encode[..., 0], encoded_img
+
+    def encode_images(self, imgdata: np.ndarray, **kwargs: int) -> Tuple[np.ndarray, np.ndarray]:
+        """encode_image_ for every image of a stack (vae.py:267-298)."""
+        if (imgdata.ndim == len(self.in_dim) == 2 or imgdata.ndim == len(self.in_dim) == 3):
+            imgdata = np.expand_dims(imgdata, axis=0)
+        imgdata_encoded, imgdata_ = [], []
+        for i, img in enumerate(imgdata):
+            img_, img_encoded = self.encode_image_(img, **kwargs)
+            imgdata_encoded.append(img_encoded)
+            imgdata_.append(img_)
+        return np.array(imgdata_), np.array(imgdata_encoded)
+
     def decode(self, z_sample: Union[np.ndarray, torch.Tensor], y=None) -> np.ndarray:
         """Decodes latent vector(s) into images (vae.py:178-221).  For coord > 0 the decoder is
         evaluated on the untransformed pixel grid, as in the reference."""

@@ -38,12 +38,6 @@ def _parse_layers(seq: nn.Sequential) -> List[Tuple[nn.Module, float, nn.Module,
     return layers
 
 
-def _check_dropout(p: float, training: bool) -> None:
-    if p > 0 and training:
-        raise NotImplementedError(
-            "dropout in training mode is not implemented by the native sm_100a path yet "
-            "(SURVEY.md §8: dropout is off on the benchmarked path); use dropout=False")
-
 
 class ConvBlock(nn.Module):
     """
@@ -80,8 +74,7 @@ class ConvBlock(nn.Module):
 
     def _emit(self, tape: Tape, x: Union[Act, Sequence[Act]]) -> Act:
         for conv, slope, bn, p_drop in _parse_layers(self.block):
-            _check_dropout(p_drop, self.training)
-            x = tape.conv(x, conv, bn, slope)
+            x = tape.conv(x, conv, bn, slope, p_drop=p_drop)
         return x
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
@@ -157,9 +150,10 @@ class DilatedBlock(nn.Module):
     def _emit(self, tape: Tape, x: Act) -> Act:
         outs, slope0 = [], None
         for conv, slope, bn, p_drop in _parse_layers(self.atrous_module):
-            _check_dropout(p_drop, self.training)
-            if p_drop > 0:
-                raise NotImplementedError("DilatedBlock with dropout changes the summed terms")
+            if p_drop > 0 and self.training:
+                raise NotImplementedError(
+                    "DilatedBlock with training-mode dropout: the reference sums the outputs of "
+                    "every sub-module including the Dropout's (blocks.py:321-329); not implemented")
             x = tape.conv(x, conv, bn, slope)
             outs.append(x)
             slope0 = slope if slope0 is None else slope0

@@ -286,6 +286,31 @@ def gram(x1, x2, inv_ls, outputscale, kind, out, math=MATH_TF32X3) -> None:
                                  stream_ptr()))
 
 
+def prob_mask(logits_nhwc, mode: int, thresh: float, prob, mask=None) -> None:
+    """prob = softmax (mode 0) / sigmoid (1) / exp (2) / identity (3) of NHWC logits; mask (uint8,
+    optional) = prob > thresh."""
+    N, H, W, Cc = logits_nhwc.shape
+    assert prob.is_contiguous() and prob.shape == logits_nhwc.shape
+    assert mask is None or (mask.dtype == torch.uint8 and mask.is_contiguous())
+    check(lib().atomai_b200_prob_mask(ptr(logits_nhwc), _ld(logits_nhwc), N * H * W, Cc, mode,
+                                      float(thresh), ptr(prob), Cc, ptr(mask), stream_ptr()))
+
+
+def gather_windows(img_nhwc, table, r: int, out, nanflag=None) -> None:
+    """out[k] = img[f, sx:sx+r, sy:sy+r, :] for the int32 rows (f, sx, sy) of `table`."""
+    n, h, w, c = img_nhwc.shape
+    assert img_nhwc.is_contiguous() and table.dtype == torch.int32 and table.is_contiguous()
+    check(lib().atomai_b200_gather_windows(ptr(img_nhwc), n, h, w, c, ptr(table), table.shape[0], r,
+                                           ptr(out), ptr(nanflag), stream_ptr()))
+
+
+def dropout_(a, p: float, seed: int, stats=None) -> None:
+    """In-place inverted dropout of an NHWC tensor (or gradient) from (seed, element index)."""
+    N, H, W, Cc = a.shape
+    check(lib().atomai_b200_dropout(ptr(a), _ld(a), N * H * W, Cc, float(p), int(seed) & (2**64 - 1),
+                                    ptr(stats), stream_ptr()))
+
+
 def selftest_tma(x, c0, w0, h0, n0, TWp, THp, swizzle_mode, smem_offset, out) -> None:
     N, H, W, Cc = x.shape
     check(lib().atomai_b200_selftest_tma(ptr(x), N, H, W, Cc, c0, w0, h0, n0, TWp, THp, swizzle_mode,

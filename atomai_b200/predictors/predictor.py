@@ -1,16 +1,17 @@
 """
 Inference wrappers and NN-output -> atom coordinates, with the reference's interface
-(atomai/predictors/predictor.py:23-298, 531-639).  The network forward and the softmax run on the
-GPU (native sm_100a graph); the Locator post-processing (threshold -> connected components ->
-centre of mass -> edge filter) is the reference's CPU algorithm and is bit-exact with it
-(tests/golden/locator_crop.npz).
+(atomai/predictors/predictor.py:23-298, 531-639).  The network forward runs on the GPU (native
+sm_100a graph) and so does the Locator's front end: one kernel turns the NHWC logits into class
+probabilities AND the thresholded binary masks (atomai_b200_prob_mask), batches are copied to
+pinned host buffers asynchronously and synchronised once.  Connected components -> centre of mass
+-> edge filter stay the reference's CPU algorithm (scipy.ndimage) on those masks, bit-exact with
+the reference (tests/golden/locator_crop.npz, bfo_1024.npz).
 """
 import time
 from typing import Dict, List, Tuple, Type, Union
 
 import numpy as np
 import torch
-import torch.nn.functional as F
 
 from ..utils.coords import find_com
 from ..utils.img import cv_thresh, img_pad, img_resize
@@ -114,17 +115,57 @@ class SegPredictor(BasePredictor):
         image_data = img_pad(image_data, self.downsampling)
         return torch_format_image(image_data, norm)
 
-    def forward_(self, images: torch.Tensor) -> torch.Tensor:
-        """Per-pixel class 'probabilities', channel-last, on the CPU (predictor.py:209-231)."""
-        images = images.to(self.device)
+    def _prob_mode(self) -> int:
+        """softmax / sigmoid for raw logits, exp for log-probabilities (predictor.py:219-228)."""
+        if self.logits:
+            return 0 if self.nb_classes > 1 else 1
+        return 2 if self.nb_classes > 1 else 3
+
+    def forward_device(self, images: torch.Tensor, with_mask: bool = True):
+        """Network forward + fused probability / threshold kernel; returns channel-last device
+        tensors (prob fp32 (n,h,w,c), mask uint8 (n,h,w,c) or None)."""
+        from .. import ops
+        images = images.to(self.device, non_blocking=True)
         self.model.eval()
         with torch.no_grad():
-            prob = self.model(images)
-        if self.logits:
-            prob = F.softmax(prob, dim=1) if self.nb_classes > 1 else torch.sigmoid(prob)
-        elif self.nb_classes > 1:
-            prob = torch.exp(prob)
-        return prob.permute(0, 2, 3, 1).cpu()
+            logits = self.model(images)
+        lg = logits.permute(0, 2, 3, 1)
+        if not lg.is_contiguous():
+            lg = lg.contiguous()
+        prob = torch.empty(lg.shape, device=lg.device, dtype=torch.float32)
+        mask = torch.empty(lg.shape, device=lg.device, dtype=torch.uint8) if with_mask else None
+        ops.prob_mask(lg, self._prob_mode(), self.thresh, prob, mask)
+        return prob, mask
+
+    def forward_(self, images: torch.Tensor) -> torch.Tensor:
+        """Per-pixel class 'probabilities', channel-last, on the CPU (predictor.py:209-231)."""
+        return self.forward_device(images, with_mask=False)[0].cpu()
+
+    def batch_predict(self, data: torch.Tensor, out_shape: Tuple[int],
+                      num_batches: int) -> torch.Tensor:
+        """Batch-by-batch prediction (predictor.py:82-106) without a host sync per batch: every
+        batch's probabilities and masks are copied into pinned host buffers on the compute stream
+        and the host waits once at the end.  The masks are kept in `self.masks_`."""
+        if self.device == "cpu" or not torch.cuda.is_available():
+            raise RuntimeError("atomai_b200 predicts on CUDA (sm_100a) only; there is no CPU path")
+        batch_size = len(data) // num_batches
+        if batch_size < 1:
+            num_batches = batch_size = 1
+        prediction_all = torch.zeros(out_shape).pin_memory()
+        masks_all = torch.zeros(out_shape, dtype=torch.uint8).pin_memory()
+        stop = num_batches * batch_size
+        bounds = [(i * batch_size, (i + 1) * batch_size) for i in range(num_batches)]
+        if len(data) > stop:
+            bounds.append((stop, len(data)))
+        for i, (b0, b1) in enumerate(bounds):
+            if self.verbose:
+                print("\rBatch {}/{}".format(min(i + 1, num_batches), num_batches), end="")
+            prob, mask = self.forward_device(data[b0:b1])
+            prediction_all[b0:b1].copy_(prob, non_blocking=True)
+            masks_all[b0:b1].copy_(mask, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        self.masks_ = masks_all.numpy()
+        return prediction_all
 
     def predict(self, image_data: np.ndarray, return_image: bool = False,
                 **kwargs: int) -> Tuple[np.ndarray]:
@@ -146,9 +187,11 @@ class SegPredictor(BasePredictor):
         start_time = time.time()
         if not compute_coords:
             return self.predict(image_data, **kwargs)
+        if "thresh" in kwargs:
+            self.thresh = kwargs["thresh"]
         images, decoded_imgs = self.predict(image_data, return_image=True, **kwargs)
-        loc = Locator(kwargs.get("thresh", self.thresh), refine=self.refine, d=self.d)
-        coordinates = loc.run(decoded_imgs, images)
+        loc = Locator(self.thresh, refine=self.refine, d=self.d)
+        coordinates = loc.run(decoded_imgs, images, masks=getattr(self, "masks_", None))
         if self.verbose:
             n_images_str = " image was " if decoded_imgs.shape[0] == 1 else " images were "
             print("\n" + str(decoded_imgs.shape[0]) + n_images_str +
@@ -243,14 +286,23 @@ class Locator:
                                       'or "channel_last" (e.g. tensorflow)')
         return nn_output
 
-    def run(self, nn_output: np.ndarray, *args: np.ndarray) -> Dict[int, np.ndarray]:
+    def run(self, nn_output: np.ndarray, *args: np.ndarray,
+            masks: np.ndarray = None) -> Dict[int, np.ndarray]:
+        """`masks` (optional, uint8 (n,h,w,c), channel-last): the binary images `nn_output >
+        threshold` already computed on the GPU by SegPredictor; otherwise thresholded here."""
         nn_output = self.preprocess(nn_output)
         h, w = nn_output.shape[1:3]
+        if masks is not None and (self.dim_order != 'channel_last' or
+                                  masks.shape[:3] != nn_output.shape[:3]):
+            masks = None
         d_coord = {}
         for i, decoded_img in enumerate(nn_output):
             per_class = []
             for ch in range(decoded_img.shape[2] - 1):   # background is always the last class
-                blobs = cv_thresh(decoded_img[:, :, ch], self.threshold)
+                if masks is not None and ch < masks.shape[3]:
+                    blobs = masks[i, :, :, ch].astype(decoded_img.dtype)
+                else:
+                    blobs = cv_thresh(decoded_img[:, :, ch], self.threshold)
                 coord_ch = self.rem_edge_coord(find_com(blobs), h, w)
                 per_class.append(np.concatenate(
                     (coord_ch, np.zeros((coord_ch.shape[0], 1)) + ch), axis=1))

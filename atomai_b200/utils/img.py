@@ -88,10 +88,62 @@ def get_imgstack(imgdata: np.ndarray, coord: np.ndarray, r: int):
     return np.ascontiguousarray(stack), coord[idx]
 
 
+def extract_subimages_cuda(imgdata, coordinates, window_size: int, coord_class: int = 0):
+    """extract_subimages for a CUDA image stack (n, h, w, c) fp32: the window bookkeeping (centre
+    rounding, which windows fit, numpy's negative-index wrap) is the same host code as the numpy
+    path, the crops themselves are ONE gather kernel over all frames
+    (atomai_b200_gather_windows) that also flags windows containing NaN.  Returns
+    (CUDA tensor (K, r, r, c), centres (K, 2) numpy, frame index (K,) numpy), or three empty
+    lists when nothing fits (like the reference)."""
+    import torch
+    from .. import ops
+    assert imgdata.is_cuda and imgdata.dim() == 4 and imgdata.dtype == torch.float32
+    if isinstance(coordinates, np.ndarray):
+        coordinates = {0: np.concatenate((coordinates, np.zeros((coordinates.shape[0], 1))), axis=-1)}
+    n, h, w, c = imgdata.shape
+    r = int(window_size)
+    rows, coms, frames = [], [], []
+    for i, coord in zip(range(n), coordinates.values()):
+        coord_i = np.asarray(coord)
+        coord_i = coord_i[coord_i[:, 2] == coord_class][:, :2]
+        if len(coord_i) == 0:
+            continue
+        cx = np.around(coord_i[:, 0]).astype(np.int64)
+        cy = np.around(coord_i[:, 1]).astype(np.int64)
+        sx, okx = _window_starts(cx, r, h)
+        sy, oky = _window_starts(cy, r, w)
+        idx = np.nonzero(okx & oky)[0]
+        if len(idx) == 0:
+            continue
+        rows.append(np.stack([np.full(len(idx), i), sx[idx], sy[idx]], 1))
+        coms.append(coord_i[idx])
+        frames.append(np.ones(len(idx), int) * i)
+    if not rows:
+        return [], [], []
+    table = torch.from_numpy(np.concatenate(rows).astype(np.int32)).to(imgdata.device)
+    K = table.shape[0]
+    out = torch.empty((K, r, r, c), device=imgdata.device, dtype=torch.float32)
+    nanflag = torch.zeros(K, device=imgdata.device, dtype=torch.int32)
+    ops.gather_windows(imgdata.contiguous(), table, r, out, nanflag)
+    keep = (nanflag == 0).cpu().numpy()
+    coms, frames = np.concatenate(coms), np.concatenate(frames)
+    if not keep.all():
+        if not keep.any():
+            return [], [], []
+        out = out[torch.from_numpy(keep).to(out.device)]
+        coms, frames = coms[keep], frames[keep]
+    return out, coms, frames
+
+
 def extract_subimages(imgdata: np.ndarray, coordinates, window_size: int, coord_class: int = 0):
     """(sub-images, centres, frame index) around the atoms of class `coord_class` in a stack
     (n, h, w, c) with Locator-style coordinates {i: (N, 3)} — atomai/utils/img.py:298-350.
-    Images are paired with the dictionary's VALUES in insertion order, like the reference."""
+    Images are paired with the dictionary's VALUES in insertion order, like the reference.
+    A CUDA tensor stack takes the gather-kernel path (extract_subimages_cuda)."""
+    if hasattr(imgdata, "is_cuda") and imgdata.is_cuda:
+        if imgdata.dim() == 2:
+            imgdata = imgdata[None, ..., None]
+        return extract_subimages_cuda(imgdata, coordinates, window_size, coord_class)
     if isinstance(coordinates, np.ndarray):
         coordinates = {0: np.concatenate((coordinates, np.zeros((coordinates.shape[0], 1))), axis=-1)}
     if np.ndim(imgdata) == 2:

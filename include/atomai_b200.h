@@ -229,6 +229,24 @@ int atomai_b200_gram(const float* x1, const float* x2, const float* inv_ls, floa
                      int n1, int n2, int d, int kind, int math, float* K, int64_t ldk,
                      void* workspace, int64_t workspace_bytes, void* stream);
 
+/* ---- prediction front-end / data path -----------------------------
+ * prob[p][c] = softmax_c(logits[p][:]) (mode 0) | sigmoid (1) | exp (2) | identity (3) over NHWC
+ * pixels, and mask[p][c] = prob > thresh (uint8, nullable): SegPredictor.forward_ +
+ * cv_thresh in one pass (atomai/predictors/predictor.py:209-231, atomai/utils/img.py:554-564). */
+int atomai_b200_prob_mask(const float* logits, int ld, int64_t npix, int C, int mode, float thresh,
+                          float* prob, int ld_p, uint8_t* mask, void* stream);
+/* out[k] = img[f_k, sx_k:sx_k+r, sy_k:sy_k+r, :] for the K rows {f, sx, sy} of `table` (int32,
+ * device); nanflag[k] = 1 if the window holds a NaN (nullable; caller zeroes).  Sub-image
+ * extraction of atomai/utils/img.py:138-180, 298-350 as one gather. */
+int atomai_b200_gather_windows(const float* img, int n, int h, int w, int c, const int32_t* table,
+                               int K, int r, float* out, int32_t* nanflag, void* stream);
+/* In-place inverted dropout a <- a * m / (1 - p), m = [hash(seed, element index) >= p]
+ * (nn.Dropout of ConvBlock, atomai/nets/blocks.py:68-69; the same call with the same seed applies
+ * the mask to a gradient).  stats (nullable, double[2C], caller zeroes) receives the per-channel
+ * sum and sum of squares of the result. */
+int atomai_b200_dropout(float* a, int ld, int64_t npix, int C, float p, uint64_t seed,
+                        double* stats, void* stream);
+
 /* ---- self-test hooks (tests only) ------------------------------------------------
  * Raw tcgen05 GEMM D[128][N] = A[128][K] B[N][K]^T on core-matrix ("interleave")
  * operands, used by tests to pin descriptor conventions. */
