@@ -111,7 +111,10 @@ class BaseTrainer:
         return self.comm.world if self.comm is not None else 1
 
     def _is_main(self) -> bool:
-        return self.comm is None or self.comm.rank == 0
+        if self.comm is not None:
+            return self.comm.rank == 0
+        d = torch.distributed
+        return not (d.is_available() and d.is_initialized()) or d.get_rank() == 0
 
     # ------------------------------------------------------------------ data / model
     def set_data(self, X_train, y_train, X_test, y_test, **kwargs: float) -> None:
@@ -399,7 +402,7 @@ class BaseTrainer:
         alloc = kwargs.get("memory_alloc", 4)
 
         if torch.distributed.is_available() and torch.distributed.is_initialized() \
-                and torch.distributed.get_world_size() > 1:
+                and torch.distributed.get_world_size() > 1 and not getattr(self, "_no_dp", False):
             self.comm = Comm(sync_bn=kwargs.get("sync_bn", True))
             if batch_size % self.comm.world != 0:
                 raise ValueError(f"batch_size={batch_size} must be divisible by the number of "

@@ -33,6 +33,23 @@ def average_weights(ensemble: Dict[int, Dict[str, torch.Tensor]]) -> Dict[str, t
     return out
 
 
+def sample_weights(ensemble: Dict[int, Dict[str, torch.Tensor]],
+                   n_samples: int = 30) -> Dict[int, Dict[str, torch.Tensor]]:
+    """theta_i ~ N(mu_i, sigma_i) per trainable parameter, with mean / std taken over the given
+    state_dicts (SWAG-like sampling, atomai/utils/nn.py:84-117); BatchNorm statistics are copied
+    from member 0."""
+    first = ensemble[min(ensemble.keys())]
+    out = {i: copy.deepcopy(first) for i in range(n_samples)}
+    for name, ref in first.items():
+        if name.split('_')[-1] in ("mean", "var", "tracked") or ref.dtype != torch.float32:
+            continue
+        w_all = torch.stack([m[name] for m in ensemble.values() if name in m], 0)
+        ndist = torch.distributions.Normal(w_all.mean(0), w_all.std(0))
+        for i in range(n_samples):
+            out[i][name].copy_(ndist.sample())
+    return out
+
+
 def gpu_usage_map(cuda_device: int):
     """[memory.used, memory.total] in MiB (atomai/utils/nn.py:120-133 shells out to nvidia-smi;
     so does this, falling back to torch's own counters when nvidia-smi is unavailable)."""

@@ -160,6 +160,10 @@ def run_reference(args):
     from baseline.ref_loader import import_reference
     cores = host_cores()
     torch.set_num_threads(cores)
+    if args.workload in ("rvae", "imspec", "gram"):
+        from tools.bench_workloads import run_other_reference
+        print(json.dumps(run_other_reference(args, cores)), flush=True)
+        return
     hw = seg_hw(args.workload)
     batch = args.ref_batch
     try:

@@ -116,3 +116,35 @@ def test_dropout_training_mode(cuda):
     m.fit(X, yl, X[:4], yl[:4], training_cycles=4, batch_size=4, plot_training_history=False,
           filename="/tmp/drop_model")
     assert all(np.isfinite(m.loss_acc["train_loss"]))
+
+
+def test_ensemble_trainer_and_predictor(cuda, tmp_path):
+    """EnsembleTrainer (from_scratch / from_baseline / swag) and EnsemblePredictor with the
+    reference's call patterns (test/trainers/test_etrainer.py, test/predictors/test_epredictor.py):
+    members differ, mean/var shapes, mean/var equal numpy over the member outputs."""
+    import atomai_b200 as ab
+    from atomai_b200.predictors import EnsemblePredictor
+    from atomai_b200.trainers import EnsembleTrainer
+    ab.set_math("tf32x3")
+    X = gu.images(1, 16, 32, 32)[:, None]
+    y = gu.labels(2, 16, 32, 32, 3)
+    Xt, yt = X[:8], y[:8]
+    et = EnsembleTrainer("Unet", nb_classes=3, nb_filters=8)
+    et.compile_ensemble_trainer(training_cycles=3, batch_size=4, filename=str(tmp_path / "ens"),
+                                plot_training_history=False)
+    net, ens = et.train_ensemble_from_scratch(X, y, Xt, yt, n_models=3)
+    assert sorted(ens) == [0, 1, 2]
+    w0, w1 = ens[0]["c1.block.0.weight"], ens[1]["c1.block.0.weight"]
+    assert not torch.equal(w0, w1)
+    ck = torch.load(str(tmp_path / "ens_ensemble_metadict.tar"), weights_only=False)
+    assert sorted(ck["weights"]) == [0, 1, 2] and ck["model_type"] == "seg"
+    net2, ens2 = et.train_ensemble_from_baseline(X, y, Xt, yt, n_models=2, training_cycles_base=3,
+                                                 training_cycles_ensemble=2)
+    assert sorted(ens2)[:2] == [0, 1]
+    p = EnsemblePredictor(net, ens, nb_classes=3, verbose=0)
+    mean, var = p.predict(X[:5, 0], num_batches=2)
+    assert mean.shape == (5, 32, 32, 3) and var.shape == mean.shape
+    allp = p.ensemble_forward(p.preprocess(X[:5, 0]))
+    np.testing.assert_allclose(mean, allp.mean(0).transpose(0, 2, 3, 1), rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(var, allp.var(0).transpose(0, 2, 3, 1), rtol=1e-4, atol=1e-9)
+    assert np.all(var >= 0) and float(var.max()) > 0

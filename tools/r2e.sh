@@ -1,0 +1,3 @@
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/r2e_pytest.log 2>&1
+grep -E "^E   .*(assert|Error)|passed|failed|^FAILED|^ERROR" gpurun_out/r2e_pytest.log | head -40
