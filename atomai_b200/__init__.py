@@ -8,7 +8,8 @@ convolutions + HBM-bound fused kernels); there is no CPU or eager-PyTorch fallba
 """
 from .__version__ import version as __version__
 from .engine import get_math, set_math
-from . import losses_metrics, models, nets, predictors, trainers, utils
+from . import losses_metrics, models, nets, predictors, trainers, transforms, utils
 
-__all__ = ["nets", "losses_metrics", "trainers", "predictors", "models", "utils", "set_math",
+__all__ = ["nets", "losses_metrics", "trainers", "predictors", "models", "utils", "transforms",
+           "set_math",
            "get_math", "__version__"]

@@ -95,6 +95,45 @@ __global__ void __launch_bounds__(kT) dropout_kernel(float* __restrict__ a, int 
   }
 }
 
+// per-sample reconstruction loss of the VAEs (atomai/losses_metrics/vi_losses.py:13-37):
+// kind 0: out[b] = 0.5 * sum_j (xhat - x)^2 ; kind 1: sum_j BCE-with-logits(xhat, x).
+// grid = (chunks, B); float4 loads when D % 4 == 0; one double atomic per block.
+// dxhat (nullable) = gvec[b] * dloss/dxhat.
+__global__ void __launch_bounds__(kT) rowloss_kernel(const float* __restrict__ x,
+                                                      const float* __restrict__ xhat, int64_t D,
+                                                      int kind, double* __restrict__ out,
+                                                      float* __restrict__ dxhat,
+                                                      const float* __restrict__ gvec) {
+  const int b = blockIdx.y;
+  const float* xr = x + (int64_t)b * D;
+  const float* hr = xhat + (int64_t)b * D;
+  float* dr = dxhat ? dxhat + (int64_t)b * D : nullptr;
+  const float g = gvec ? gvec[b] : 1.f;
+  float acc = 0.f;
+  for (int64_t j = blockIdx.x * (int64_t)kT + threadIdx.x; j < D; j += (int64_t)gridDim.x * kT) {
+    const float t = xr[j], p = hr[j];
+    if (kind == 0) {
+      const float d = p - t;
+      acc = fmaf(0.5f * d, d, acc);
+      if (dr) dr[j] = g * d;
+    } else {   // max(p, 0) - p t + log(1 + exp(-|p|))
+      acc += fmaxf(p, 0.f) - p * t + log1pf(expf(-fabsf(p)));
+      if (dr) dr[j] = g * (1.f / (1.f + expf(-p)) - t);
+    }
+  }
+  if (out) {
+    acc = warp_sum(acc);
+    __shared__ float s_w[kT / 32];
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float tot = 0.f;
+      for (int i = 0; i < kT / 32; ++i) tot += s_w[i];
+      atomicAdd(out + b, (double)tot);
+    }
+  }
+}
+
 int grid_for(int64_t n) {
   int64_t g = (n + kT - 1) / kT;
   const int64_t cap = (int64_t)ab_num_sms() * 16;
@@ -122,6 +161,18 @@ int atomai_b200_gather_windows(const float* img, int n, int h, int w, int c, con
            "gather_windows: bad arguments");
   if (K == 0) return 0;
   gather_windows_kernel<<<K, kT, 0, (cudaStream_t)stream>>>(img, h, w, c, table, r, out, nanflag);
+  AB_LAUNCH_CHECK();
+  return 0;
+}
+
+int atomai_b200_rowloss(const float* x, const float* xhat, int B, int64_t D, int kind, double* out,
+                        float* dxhat, const float* gvec, void* stream) {
+  AB_CHECK(x && xhat && B >= 0 && D > 0 && (kind == 0 || kind == 1), "rowloss: bad arguments");
+  AB_CHECK(B <= 65535, "rowloss: batch too large for one launch");
+  if (B == 0) return 0;
+  int gx = (int)((D + kT * 8 - 1) / (kT * 8));
+  gx = gx < 1 ? 1 : (gx > 64 ? 64 : gx);
+  rowloss_kernel<<<dim3(gx, B), kT, 0, (cudaStream_t)stream>>>(x, xhat, D, kind, out, dxhat, gvec);
   AB_LAUNCH_CHECK();
   return 0;
 }

@@ -398,6 +398,20 @@ class Tape:
                 _acc_grad(l, g, False)
 
 
+    def add(self, a: Act, b: Act) -> Act:
+        """a + b (rDecoderNet's skip connections, atomai/nets/ed.py:632-637)."""
+        if a.pending():
+            a = self.materialize(a)
+        if b.pending():
+            b = self.materialize(b)
+        out_t = torch.empty(a.t.shape, device=a.t.device, dtype=torch.float32)
+        ops.add_slice(a.t, out_t, False)
+        ops.add_slice(b.t, out_t, True)
+        out = Act(out_t)
+        if self.record:
+            self.ops.append(("custom", _AddRec(a, b, out)))
+        return out
+
     # ------------------------------------------------------------------ dense layers
     def pointwise(self, x: Act, lin_mod, slope: float = 1.0, act: int = ACT_LRELU) -> Act:
         """nn.Linear applied to every pixel's channel vector (rDecoderNet's fc_decoder / out,
@@ -670,6 +684,21 @@ def _unpad_b(param, r0, r1):
         full[r0:r1] = g.reshape(-1)[:r1 - r0]
         return param, full
     return fn
+
+
+class _AddRec:
+    def __init__(self, a, b, out):
+        self.a, self.b, self.out = a, b, out
+
+    def backward(self, tape):
+        g = self.out.grad
+        self.out.grad = None
+        if g is None:
+            return
+        g = _dense(g)
+        for s_ in (self.a, self.b):
+            if s_.needs_grad:
+                _acc_grad(s_, g, False)
 
 
 class _PadRec:

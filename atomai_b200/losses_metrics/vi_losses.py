@@ -1,7 +1,7 @@
 """
 ELBO terms for the VAEs with the reference's function names and maths
 (atomai/losses_metrics/vi_losses.py:13-137).  The reconstruction term — the only part that touches
-image-sized tensors (2*B*H*W*4 bytes) — is one fused, vectorised reduction kernel that also emits
+image-sized tensors (2*B*H*W*4 bytes) — is one fused per-sample reduction kernel that also emits
 d/dx_hat for the backward pass; the KL terms act on (B, latent) tensors and stay in torch.
 """
 from typing import List, Optional, Tuple, Union
@@ -12,41 +12,49 @@ import torch
 from .. import ops
 
 
-class _HalfSqErrFn(torch.autograd.Function):
-    """sum_b 0.5 * sum_px (x_hat - x)^2  (a scalar); gradient only w.r.t. x_hat."""
+class _RowLossFn(torch.autograd.Function):
+    """Per-sample reconstruction loss (B,) from the fused row-reduction kernel; gradient only
+    w.r.t. x_hat.  kind 0: 0.5 * sum_px (x_hat - x)^2, kind 1: sum_px BCE-with-logits."""
 
     @staticmethod
-    def forward(ctx, x, x_hat):
+    def forward(ctx, x, x_hat, kind):
         if not x_hat.is_cuda:
             raise RuntimeError("atomai_b200 losses run on CUDA (sm_100a) only")
         xc = x.detach().float().contiguous()
         xh = x_hat.detach().float().contiguous()
         assert xc.numel() == xh.numel(), "input and reconstruction differ in size"
-        acc = torch.zeros(1, device=xh.device, dtype=torch.float64)
-        ops.sqerr_reduce(xc, xh, acc)
+        acc = torch.zeros(xc.shape[0], device=xh.device, dtype=torch.float64)
+        ops.rowloss(xc, xh, kind, acc)
         ctx.save_for_backward(xc, xh)
-        ctx.shape = x_hat.shape
-        return acc.float().reshape(())
+        ctx.shape, ctx.kind = x_hat.shape, kind
+        return acc.float()
 
     @staticmethod
     def backward(ctx, g):
         xc, xh = ctx.saved_tensors
         d = torch.empty_like(xh)
-        ops.sqerr_reduce(xc, xh, None, d, 1.0, g.detach().float().reshape(1).contiguous())
-        return None, d.reshape(ctx.shape)
+        ops.rowloss(xc, xh, ctx.kind, None, d, g.detach().float().contiguous())
+        return None, d.reshape(ctx.shape), None
 
 
 def reconstruction_loss(loss_type: str, in_dim: Tuple[int], x: torch.Tensor,
                         x_reconstr: torch.Tensor, logits: bool = True) -> torch.Tensor:
     """
-    Batch-summed reconstruction loss.  NOTE: the reference returns the per-sample vector
-    (vi_losses.py:13-37) and every caller immediately takes `.mean()`; here the fused kernel
-    returns the scalar SUM over the batch, and `vae_loss`/`rvae_loss` divide by B.
+    Reconstruction loss (mse or cross-entropy) without mean reduction, one value per sample
+    (vi_losses.py:13-37), as ONE fused reduction kernel that also yields d/dx_hat.  For
+    multi-channel 'ce' the reference sums over the channel axis only and leaves (B, H*W); every
+    caller takes `.mean()` of the result, so the per-sample sums are divided by H*W here.
     """
-    if loss_type != "mse":
-        raise NotImplementedError("the native path implements the 'mse' reconstruction loss "
-                                  "(the reference's 'ce' branch needs numpy<2, SURVEY.md §0.10)")
-    return _HalfSqErrFn.apply(x, x_reconstr)
+    if loss_type == "mse":
+        return _RowLossFn.apply(x, x_reconstr, 0)
+    if loss_type == "ce":
+        if not logits:
+            raise NotImplementedError("'ce' reconstruction loss expects decoder logits")
+        per = _RowLossFn.apply(x, x_reconstr, 1)
+        if len(in_dim) == 3:
+            per = per / float(int(in_dim[0]) * int(in_dim[1]))
+        return per
+    raise NotImplementedError("Reconstruction loss must be 'mse' or 'ce'")
 
 
 def kld_normal(q_param: Tuple[torch.Tensor],
@@ -84,7 +92,7 @@ def vae_loss(recon_loss: str, in_dim: Tuple[int], x: torch.Tensor, x_reconstr: t
     if len(args) != 2:
         raise ValueError("Pass mean and SD values of encoded distribution as args")
     capacity = kwargs.get("capacity")
-    likelihood = -reconstruction_loss(recon_loss, in_dim, x, x_reconstr) / x.size(0)
+    likelihood = -reconstruction_loss(recon_loss, in_dim, x, x_reconstr).mean()
     kl_div = kld_normal(args).mean()
     if capacity is not None:
         kl_div = infocapacity(kl_div, capacity, num_iter=kwargs.get("num_iter", 0))
@@ -102,7 +110,7 @@ def rvae_loss(recon_loss: str, in_dim: Tuple[int], x: torch.Tensor, x_reconstr: 
     capacity = kwargs.get("capacity")
     phi_logsd = z_logsd[:, 0]
     z_mean, z_logsd = z_mean[:, 1:], z_logsd[:, 1:]
-    likelihood = -reconstruction_loss(recon_loss, in_dim, x, x_reconstr) / x.size(0)
+    likelihood = -reconstruction_loss(recon_loss, in_dim, x, x_reconstr).mean()
     kl_div = kld_normal([z_mean, z_logsd]).mean() + kld_rot(phi_prior, phi_logsd).mean()
     if capacity is not None:
         kl_div = infocapacity(kl_div, capacity, num_iter=kwargs.get("num_iter", 0))

@@ -13,18 +13,11 @@ from ..utils.nn import get_downsample_factor
 
 
 def _seg_augmentor(nb_classes: int, **kwargs):
-    """The reference builds an on-the-fly numpy/cv2 augmentor when augmentation kwargs are given
-    (atomai/transforms/imaug.py:406-432) and returns None otherwise.  CPU augmentation is outside
-    the accelerated hot path: reject those kwargs loudly instead of
-    silently training without them."""
-    aug_keys = {"custom_transform", "rotation", "zoom", "gauss_noise", "jitter", "poisson_noise",
-                "salt_and_pepper", "blur", "contrast", "background", "resize"}
-    used = sorted(aug_keys.intersection(kwargs))
-    if used:
-        raise NotImplementedError(
-            f"on-the-fly augmentation kwargs {used} are not part of the atomai_b200 hot path; "
-            "augment the data up front or pass a torch-based function to data_augmentation()")
-    return None
+    """On-the-fly augmentor when augmentation kwargs are given, None otherwise
+    (atomai/transforms/imaug.py:406-432) — here the GPU implementation of
+    atomai_b200.transforms."""
+    from ..transforms import seg_augmentor
+    return seg_augmentor(nb_classes, **kwargs)
 
 
 class Segmentor(SegTrainer):

@@ -320,8 +320,6 @@ class rDecoderNet(nn.Module):
             c = out_dim[-1]
             self.reshape_ = (out_dim[0], out_dim[1], c)
         self.skip = skip
-        if skip:
-            raise NotImplementedError("rDecoderNet(skip=True) is not on the native path")
         self.coord_latent = coord_latent(latent_dim, hidden_dim, not skip)
         fc_decoder = []
         for i in range(num_layers):
@@ -333,9 +331,12 @@ class rDecoderNet(nn.Module):
     def _emit(self, tape: Tape, z: Act, phi: Optional[Act] = None, dx: Optional[Act] = None) -> Act:
         h = tape.coord_latent(self.coord_latent, self.reshape_[:2], z, phi, dx,
                               self.coord_latent.activation is not None)
+        residual = h
         for m in self.fc_decoder:
             if isinstance(m, nn.Linear):
                 h = tape.pointwise(h, m, 1.0, ACT_TANH)
+                if self.skip:          # h.add(residual) after every (Linear, Tanh) pair
+                    h = tape.add(h, residual)
         return tape.pointwise(h, self.out, 1.0, ACT_LRELU)
 
     def decode(self, z: torch.Tensor, phi: Optional[torch.Tensor] = None,

@@ -304,11 +304,27 @@ def gather_windows(img_nhwc, table, r: int, out, nanflag=None) -> None:
                                            ptr(out), ptr(nanflag), stream_ptr()))
 
 
+def rowloss(x, xhat, kind: int, out=None, dxhat=None, gvec=None) -> None:
+    """Per-sample reconstruction loss over (B, D) rows (kind 0: 0.5*sum sq. err., 1: BCE logits)."""
+    B = x.shape[0]
+    D = x.numel() // max(B, 1)
+    check(lib().atomai_b200_rowloss(ptr(x), ptr(xhat), B, D, kind, ptr(out), ptr(dxhat), ptr(gvec),
+                                    stream_ptr()))
+
+
 def dropout_(a, p: float, seed: int, stats=None) -> None:
     """In-place inverted dropout of an NHWC tensor (or gradient) from (seed, element index)."""
     N, H, W, Cc = a.shape
     check(lib().atomai_b200_dropout(ptr(a), _ld(a), N * H * W, Cc, float(p), int(seed) & (2**64 - 1),
                                     ptr(stats), stream_ptr()))
+
+
+def augment(x, y, scratch, lab_in, lab_out, params, row_shift, in_min, in_max, seed, minmax) -> None:
+    n, h, w = x.shape
+    check(lib().atomai_b200_augment(ptr(x), ptr(y), ptr(scratch), ptr(lab_in), ptr(lab_out),
+                                    ptr(params), ptr(row_shift), n, h, w, float(in_min),
+                                    float(in_max), int(seed) & (2**64 - 1), ptr(minmax),
+                                    stream_ptr()))
 
 
 def selftest_tma(x, c0, w0, h0, n0, TWp, THp, swizzle_mode, smem_offset, out) -> None:

@@ -240,12 +240,27 @@ int atomai_b200_prob_mask(const float* logits, int ld, int64_t npix, int C, int 
  * extraction of atomai/utils/img.py:138-180, 298-350 as one gather. */
 int atomai_b200_gather_windows(const float* img, int n, int h, int w, int c, const int32_t* table,
                                int K, int r, float* out, int32_t* nanflag, void* stream);
+/* Per-sample VAE reconstruction loss (atomai/losses_metrics/vi_losses.py:13-37) over B rows of D
+ * elements: kind 0 out[b] += 0.5*sum (xhat-x)^2, kind 1 out[b] += sum BCE-with-logits(xhat, x)
+ * (double, nullable, caller zeroes); dxhat (nullable) = gvec[b] * d loss_b / d xhat. */
+int atomai_b200_rowloss(const float* x, const float* xhat, int B, int64_t D, int kind, double* out,
+                        float* dxhat, const float* gvec, void* stream);
 /* In-place inverted dropout a <- a * m / (1 - p), m = [hash(seed, element index) >= p]
  * (nn.Dropout of ConvBlock, atomai/nets/blocks.py:68-69; the same call with the same seed applies
  * the mask to a gradient).  stats (nullable, double[2C], caller zeroes) receives the per-channel
  * sum and sum of squares of the result. */
 int atomai_b200_dropout(float* a, int ld, int64_t npix, int C, float p, uint64_t seed,
                         double* stats, void* stream);
+
+/* On-the-fly augmentation of a batch of (n, h, w) images (+ int64 label maps, nullable) entirely in
+ * HBM: the reference's datatransform sequence (atomai/transforms/imaug.py:109-358) as three passes.
+ * params: n x 16 floats per image {flip code, gauss var, poisson vals, s&p amount, blur sigma,
+ * gamma, background amp, x0, y0, a*ln2/fwhm^2, b*ln2/fwhm^2, ...} drawn by the caller; row_shift
+ * (nullable): n x h jitter roll amounts; scratch: n*h*w floats; minmax: 2 floats (device). */
+int atomai_b200_augment(const float* x, float* y, float* scratch, const int64_t* lab_in,
+                        int64_t* lab_out, const float* params, const int32_t* row_shift, int n,
+                        int h, int w, float in_min, float in_max, uint64_t seed, float* minmax,
+                        void* stream);
 
 /* ---- self-test hooks (tests only) ------------------------------------------------
  * Raw tcgen05 GEMM D[128][N] = A[128][K] B[N][K]^T on core-matrix ("interleave")

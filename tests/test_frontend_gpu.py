@@ -148,3 +148,59 @@ def test_ensemble_trainer_and_predictor(cuda, tmp_path):
     np.testing.assert_allclose(mean, allp.mean(0).transpose(0, 2, 3, 1), rtol=1e-6, atol=1e-7)
     np.testing.assert_allclose(var, allp.var(0).transpose(0, 2, 3, 1), rtol=1e-4, atol=1e-9)
     assert np.all(var >= 0) and float(var.max()) > 0
+
+
+def test_gpu_augmentation(cuda, tmp_path):
+    """GPU datatransform against the reference's semantics
+    (atomai/transforms/imaug.py:109-358): flips act on image and labels alike, blur equals
+    scipy.ndimage.gaussian_filter, gamma equals skimage's adjust_gamma formula, noise levels
+    follow skimage.util.random_noise, output is min-max normalised; Segmentor.fit accepts the
+    augmentation kwargs."""
+    from scipy import ndimage
+    from atomai_b200.transforms import datatransform
+    X = torch.from_numpy(gu.images(7, 6, 48, 48)).to(cuda)
+    y = torch.from_numpy(gu.labels(8, 6, 48, 48, 3)).to(cuda)
+    Xn = ((X - X.min()) / (X.max() - X.min())).cpu().numpy()
+    # rotation only: every output is one of the five flips / turns of its input, labels follow
+    out, lab = datatransform(3, seed=3, rotation=True).run(X, y)
+    for i in range(6):
+        cands = {"v": lambda a: a[::-1], "h": lambda a: a[:, ::-1], "hv": lambda a: a[::-1, ::-1],
+                 "ccw": lambda a: np.rot90(a, 1), "id": lambda a: a}
+        hit = [k for k, f in cands.items()
+               if np.allclose(out[i].cpu().numpy(), f(Xn[i]), atol=1e-6)
+               and np.array_equal(lab[i].cpu().numpy(), f(y[i].cpu().numpy()))]
+        assert hit, i
+    # blur only (same parameter draw as the reference: np.random.seed(seed); randint per image)
+    out, _ = datatransform(3, seed=5, blur=[20, 21]).run(X, None)
+    ref = np.stack([ndimage.gaussian_filter(im.astype(np.float64), 20 * 5e-2) for im in Xn])
+    ref = (ref - ref.min()) / np.ptp(ref)
+    assert np.abs(out.cpu().numpy() - ref).max() < 2e-5
+    # gamma only
+    out, _ = datatransform(3, seed=5, contrast=[15, 16]).run(X, None)
+    ref = Xn.astype(np.float64) ** 1.5
+    ref = (ref - ref.min()) / np.ptp(ref)
+    assert np.abs(out.cpu().numpy() - ref).max() < 2e-5
+    # gaussian noise: variance 1e-4 * 40, clipped to [0, 1] before the final normalisation
+    out, _ = datatransform(3, seed=5, gauss_noise=[40, 41]).run(X, None)
+    d = out.cpu().numpy() - Xn
+    inner = (Xn > 0.2) & (Xn < 0.8)
+    assert abs(d[inner].std() / np.sqrt(40e-4) - 1) < 0.15 and abs(d[inner].mean()) < 0.02
+    # salt & pepper: amount = 30e-3 of the pixels become 0 or 1
+    out, _ = datatransform(3, seed=5, salt_and_pepper=[30, 31]).run(X, None)
+    o = out.cpu().numpy()
+    changed = np.abs(o - Xn) > 1e-6
+    assert abs(changed.mean() - 0.03) < 0.008 and set(np.unique(o[changed])) <= {0.0, 1.0}
+    # poisson + jitter + background run and stay finite / normalised
+    out, lab = datatransform(3, seed=9, rotation=True, poisson_noise=True, jitter=[10, 20],
+                             background=True, gauss_noise=True).run(X, y)
+    o = out.cpu().numpy()
+    assert np.isfinite(o).all() and abs(o.min()) < 1e-6 and abs(o.max() - 1) < 1e-6
+    assert sorted(np.unique(lab.cpu().numpy())) == [0, 1, 2]
+    with pytest.raises(NotImplementedError):
+        datatransform(3, zoom=True)
+    from atomai_b200.models import Segmentor
+    Xs, ys = gu.images(3, 8, 32, 32), gu.labels(4, 8, 32, 32, 3)
+    m = Segmentor("Unet", nb_classes=3, nb_filters=8)
+    m.fit(Xs, ys, Xs[:4], ys[:4], training_cycles=3, batch_size=4, plot_training_history=False,
+          filename=str(tmp_path / "aug"), rotation=True, gauss_noise=True, contrast=True)
+    assert all(np.isfinite(m.loss_acc["train_loss"])) and m.augment_fn is not None

@@ -112,3 +112,64 @@ def test_rvae_fit_runs_and_improves(cuda, tmp_path):
     assert m.decode(zm[:, 3:]).shape == (10, 32, 32)
     ck = torch.load(str(tmp_path / "rvae.tar"), weights_only=False)
     assert "encoder" in ck and "decoder" in ck and ck["coord"] == 3
+
+
+def test_rdecoder_skip_and_ce_loss(cuda):
+    """rDecoderNet(skip=True) (atomai/nets/ed.py:626-637) and the 'ce' reconstruction loss
+    (atomai/losses_metrics/vi_losses.py:27-34) against a float64 torch restatement on the CPU,
+    forward and backward; reconstruction_loss returns one value per sample like the reference."""
+    import atomai_b200 as ab
+    from atomai_b200.losses_metrics.vi_losses import reconstruction_loss
+    from atomai_b200.models import rVAE
+    from atomai_b200.utils import imcoordgrid
+    ab.set_math("fp32")
+    torch.manual_seed(0)
+    m = rVAE((16, 16), latent_dim=2, skip=True, seed=1)
+    dec = m.decoder_net.to(cuda)
+    assert dec.skip and dec.coord_latent.activation is None
+    z = torch.randn(5, 2, device=cuda, requires_grad=True)
+    phi = torch.randn(5, device=cuda) * 0.3
+    dx = torch.randn(5, 2, device=cuda) * 0.1
+    out = dec.decode(z, phi, dx)
+    g = torch.randn_like(out)
+    out.backward(g)
+    # float64 restatement
+    sd = {k: v.detach().cpu().double() for k, v in dec.state_dict().items()}
+    zc = z.detach().cpu().double().requires_grad_(True)
+    grid = imcoordgrid((16, 16)).double()                                   # (HW, 2)
+    c, s = torch.cos(phi.cpu().double()), torch.sin(phi.cpu().double())
+    R = torch.stack([torch.stack([c, s], 1), torch.stack([-s, c], 1)], 1)    # (B, 2, 2)
+    xc = torch.bmm(grid[None].expand(5, -1, -1), R) + dx.cpu().double()[:, None]
+    h = xc @ sd["coord_latent.fc_coord.weight"].T + sd["coord_latent.fc_coord.bias"] + \
+        (zc @ sd["coord_latent.fc_latent.weight"].T)[:, None]
+    res = h
+    for i in range(0, len(dec.fc_decoder), 2):
+        h = torch.tanh(h @ sd[f"fc_decoder.{i}.weight"].T + sd[f"fc_decoder.{i}.bias"]) + res
+    ref = (h @ sd["out.weight"].T + sd["out.bias"]).reshape(5, 16, 16)
+    assert rel(out.detach().cpu().numpy(), ref.detach().numpy()) <= 1e-5
+    (ref * g.cpu().double()).sum().backward()
+    assert rel(z.grad.cpu().numpy(), zc.grad.numpy()) <= 1e-4
+    # reconstruction losses: per-sample vectors, values and gradients
+    x = torch.rand(6, 16, 16, device=cuda)
+    xh = torch.randn(6, 16, 16, device=cuda, requires_grad=True)
+    for kind in ("mse", "ce"):
+        xh.grad = None
+        per = reconstruction_loss(kind, (16, 16), x, xh)
+        assert per.shape == (6,)
+        w = torch.arange(1, 7, device=cuda, dtype=torch.float32)
+        (per * w).sum().backward()
+        xr = xh.detach().cpu().double().requires_grad_(True)
+        if kind == "mse":
+            pr = 0.5 * ((xr - x.cpu().double()) ** 2).reshape(6, -1).sum(1)
+        else:
+            pr = torch.nn.functional.binary_cross_entropy_with_logits(
+                xr.reshape(6, -1), x.cpu().double().reshape(6, -1), reduction="none").sum(-1)
+        (pr * w.cpu().double()).sum().backward()
+        assert rel(per.detach().cpu().numpy(), pr.detach().numpy()) <= 1e-5
+        assert rel(xh.grad.cpu().numpy(), xr.grad.numpy()) <= 1e-5
+    # VAE.fit(loss='ce') trains
+    from atomai_b200.models import VAE
+    X = (gu.images(3, 64, 16, 16) > 0.5).astype(np.float32)
+    v = VAE((16, 16), latent_dim=2, seed=1)
+    v.fit(X, training_cycles=2, batch_size=16, loss="ce", filename="/tmp/vae_ce")
+    assert len(v.loss_history["train_loss"]) == 2 and np.isfinite(v.loss_history["train_loss"]).all()
