@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libatomai_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 SOURCES = ["api.cu", "conv_tc.cu", "conv_simt.cu", "wgrad_tc.cu", "elementwise.cu",
-           "selftest.cu", "selftest_tma.cu", "vae.cu", "gram.cu", "frontend.cu", "augment.cu"]
+           "selftest.cu", "selftest_tma.cu", "vae.cu", "gram.cu", "frontend.cu", "augment.cu", "p2p.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo",
               "-std=c++17", "-Xcompiler", "-fPIC", "-shared"]
 
@@ -112,6 +112,13 @@ SIGNATURES = {
     "atomai_b200_dropout": (_i, [_vp, _i, _i64, _i, _f, C.c_uint64, _vp, _vp]),
     "atomai_b200_augment": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _f, C.c_uint64,
                                  _vp, _vp]),
+    "atomai_b200_ipc_export": (_i, [_vp, _vp, C.POINTER(_i64)]),
+    "atomai_b200_ipc_import": (_i, [_vp, _i64, C.POINTER(_vp)]),
+    "atomai_b200_p2p_data_bytes": (_i64, [_i]),
+    "atomai_b200_p2p_flag_bytes": (_i64, [_i]),
+    "atomai_b200_p2p_allreduce": (_i, [_vp, _vp, _i, _i, C.c_uint64, _vp, _i, _vp]),
+    "atomai_b200_p2p_bn_finalize": (_i, [_vp, _vp, _i, _i, C.c_uint64, _vp, _i, _d, _vp, _vp, _vp,
+                                         _vp, _f, _f, _vp, _vp, _vp, _vp, _vp]),
     "atomai_b200_umma_rate": (_i, [_i, _i, _i, _i, _vp, _vp]),
     "atomai_b200_selftest_tma": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "atomai_b200_selftest_sw128": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),

@@ -18,6 +18,8 @@
 // Replaces nn.Conv2d(+bias) -> nn.LeakyReLU -> (batch statistics of) nn.BatchNorm2d of
 // atomai/nets/blocks.py:61-76,302-319, the preceding BatchNorm2d/max_pool2d/cat passes
 // (normalise-on-load, atomai/nets/fcnn.py:123-138) and, with flipped weights, autograd's dgrad.
+#include <cuda.h>
+
 #include <cstdio>
 #include <cstdlib>
 #include "common.cuh"
@@ -26,19 +28,27 @@ namespace {
 
 constexpr int kTileH = 16;
 constexpr int kTileW = 8;
-constexpr int kNumEpiWarps = 4;
+constexpr int kNumEpiWarps = 4;     // per epilogue group (one warp per TMEM lane quadrant)
+constexpr int kEpiGroups = 1;       // 2: group e drains the accumulators of pipeline e (warps 0-3, 16-19)
+constexpr int kEpiBWarp = 16;       // first warp of epilogue group 1
 constexpr int kMmaWarp = 4;
 constexpr int kWgtWarp = 5;
 constexpr int kMmaWarp2 = 6;          // second issuing thread
 constexpr int kWgtWarp2 = 7;          // second weight producer (streamed weights)
 constexpr int kFirstLoadWarp = 8;   // warps 6,7 idle: roles are aligned to 4-warp groups (setmaxnreg)
 constexpr int kNumLoadWarps = 8;
-constexpr int kThreads = (kFirstLoadWarp + kNumLoadWarps) * 32;  // 512 -> 128 regs/thread at launch
-// register re-balancing between the warpgroups (sum * 128 threads = 64K registers)
-constexpr int kRegsEpi = 112, kRegsMma = 72, kRegsLoad = 160;
-static_assert(kRegsEpi + kRegsMma + 2 * kRegsLoad <= 512, "register budget");
+constexpr int kThreads = (kFirstLoadWarp + kNumLoadWarps + (kEpiGroups - 1) * kNumEpiWarps) * 32;
+// register re-balancing between the warpgroups (sum * 128 threads = 64K registers).  A second
+// epilogue group (kEpiGroups = 2, 640 threads) was tried in round 2 — the ncu source view shows
+// the epilogue warps never waiting while loaders and the MMA thread do — but ptxas allocates for
+// the launch bound (96 registers at 640 threads) whatever setmaxnreg says, and the spills cost
+// more than the second group gains.
+constexpr int kRegsEpi = kEpiGroups == 1 ? 112 : 128, kRegsMma = kEpiGroups == 1 ? 72 : 48,
+              kRegsLoad = kEpiGroups == 1 ? 160 : 104;
+static_assert(kEpiGroups * kRegsEpi + kRegsMma + 2 * kRegsLoad <= 512, "register budget");
 constexpr int kMaxAStages = 4;
 constexpr int kMaxBStages = 32;     // streamed weights: bytes in flight must cover the L2 latency
+constexpr int kMaxRStages = 8;      // TMA mode: raw activation tiles in flight (two rings of n_r/2)
 constexpr int kGroupThreads = 128;  // loader threads per group (2 groups of 4 warps)
 constexpr int kMaxU = 12;           // register-staged 16B elements per loader thread per chunk
 
@@ -69,12 +79,22 @@ struct ConvTcParams {
   int x3;            // AB_MATH_TF32X3: every k-step issues a second, kind::f16 MMA on a bf16 operand
                      // pair ([a_lo | a_hi] x [w ; w_lo]) that adds the two cross terms of the split
   int corr_off;      // x3: byte offset of the correction planes inside an activation stage
+  // TMA mode (resident weights, un-pooled sources): cp.async.bulk.tensor copies the raw NHWC halo
+  // tile {KC channels, TWp, THp} (out-of-image pixels zero-filled by the copy engine) into a ring
+  // of raw stages; the "loader" warps then only transform shared memory -> shared memory (affine,
+  // border mask, TF32 rounding / x3 split into the UMMA planes).  Bytes in flight are bounded by
+  // the raw ring (up to 8 stages) instead of by loader registers.
+  int tma;
+  int raw_bytes;     // HP * KC * 4
+  int n_r;           // raw stages (two rings of n_r/2)
+  int dbg;           // bring-up only (ATOMAI_B200_DBG): bit 0 skip the global stores, bit 1 skip the TMEM loads
 };
 
 struct __align__(8) SharedCtl {
   uint64_t full_a[kMaxAStages], empty_a[kMaxAStages];
   uint64_t full_b[kMaxBStages], empty_b[kMaxBStages];
   uint64_t tmem_full[4], tmem_empty[4];
+  uint64_t raw_full[kMaxRStages], raw_empty[kMaxRStages];
   uint64_t w_full;
   uint32_t tmem_base;
   uint32_t pad;
@@ -189,9 +209,25 @@ __device__ __forceinline__ uint32_t tf32_bits(float x) { return __float_as_uint(
 // chunk.  Element u of a thread is halo pixel q0 + u*QS of plane j for every chunk, so its pixel
 // offset relative to the tile origin and its smem slot are loop constants; only element U-1 can be
 // absent (HP is not a multiple of QS), every other load/store is unconditional.
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, int c0, int c1,
+                                            int c2, int c3, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
+      : "memory");
+}
+
 template <int U>
 __device__ __forceinline__ void loader_loop(const ConvTcParams& p, SharedCtl* ctl,
-                                            uint32_t a_base, int grp) {
+                                            uint32_t a_base, uint32_t raw_base, int grp) {
   const int lane = threadIdx.x & 31;
   const int gt = threadIdx.x - (kFirstLoadWarp + grp * 4) * 32;   // 0..127
   const int P = p.KC >> 2;                   // planes per chunk (2, 4 or 8)
@@ -232,6 +268,12 @@ __device__ __forceinline__ void loader_loop(const ConvTcParams& p, SharedCtl* ct
   // the high parts (one 16-byte row per pixel each = one K-major core-matrix row of a K = 16 MMA).
   const bool x3 = p.x3 != 0;
   const uint32_t corr_dst0 = a_base + p.corr_off + (j >> 1) * 2 * p.plane_bytes + q0 * 16 + (j & 1) * 8;
+  // TMA mode: this group's half of the raw ring, and this thread's first row inside a raw tile
+  const uint32_t rn = (uint32_t)p.n_r / 2, rr0 = grp * rn;
+  const uint32_t rowb = (uint32_t)p.KC * 4;
+  const uint32_t raw_src0 = raw_base + q0 * rowb + j * 16;
+  const uint32_t bar_raw_full = smem_u32(&ctl->raw_full[0]), bar_raw_empty = smem_u32(&ctl->raw_empty[0]);
+  uint32_t rst = 0, rph = 0;
   int ch = dual ? 0 : grp;
   uint32_t st = dual ? 0u : grp % n_a;
   uint32_t ph = dual ? 1u : ((grp / n_a) & 1) ^ 1;   // stage / empty-phase of the current chunk
@@ -265,7 +307,36 @@ __device__ __forceinline__ void loader_loop(const ConvTcParams& p, SharedCtl* ct
     const float* base = sp->ptr + c;
     float4 v[U];
     const bool interior = h_org >= 0 && w_org >= 0 && h_org + p.THp <= H && w_org + p.TWp <= W;
-    if (!pool && interior) {
+    if (p.tma) {
+      // the copy engine has staged the raw tile (zero-filled outside the image): registers <-
+      // shared memory, then hand the raw stage straight back to the producer
+      mbar_wait(bar_raw_full + (rr0 + rst) * 8, rph);
+      const uint32_t rsrc = raw_src0 + (rr0 + rst) * p.raw_bytes;
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        v[u] = (u < U - 1 || last_valid) ? lds128(rsrc + u * QS * rowb) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (has_aff) {
+        if (interior) {
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            v[u].x = fmaf(v[u].x, sc.x, sh.x);
+            v[u].y = fmaf(v[u].y, sc.y, sh.y);
+            v[u].z = fmaf(v[u].z, sc.z, sh.z);
+            v[u].w = fmaf(v[u].w, sc.w, sh.w);
+          }
+        } else {      // zero padding applies AFTER the affine: mask the out-of-image pixels
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int gh = h_org + (int)(hw[u] >> 16), gw = w_org + (int)(hw[u] & 0xFFFFu);
+            const bool ok = (unsigned)gh < (unsigned)H && (unsigned)gw < (unsigned)W;
+            v[u].x = ok ? fmaf(v[u].x, sc.x, sh.x) : 0.f;
+            v[u].y = ok ? fmaf(v[u].y, sc.y, sh.y) : 0.f;
+            v[u].z = ok ? fmaf(v[u].z, sc.z, sh.z) : 0.f;
+            v[u].w = ok ? fmaf(v[u].w, sc.w, sh.w) : 0.f;
+          }
+        }
+      }
+    } else if (!pool && interior) {
       // fast path (~90 % of the tiles of a 512^2 image): one IMAD.WIDE + LDG.128 per element
       const float* tb = base + ((size_t)(n * H + h_org) * W + w_org) * ld;
 #pragma unroll
@@ -358,6 +429,10 @@ __device__ __forceinline__ void loader_loop(const ConvTcParams& p, SharedCtl* ct
     fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0) mbar_arrive(bar_full_a + (ring0 + st) * 8);
+    if (p.tma) {   // the raw tile has been consumed (the stores above depend on every load of it)
+      if (lane == 0) mbar_arrive(bar_raw_empty + (rr0 + rst) * 8);
+      if (++rst == rn) { rst = 0; rph ^= 1; }
+    }
     // advance to this group's next chunk
     ch += ch_step;
     st += ch_step;
@@ -385,15 +460,16 @@ __device__ __forceinline__ float warp_transpose_sum32(float (&w)[32], int lane) 
 // NG > 0 (Cout = 16*NG <= 32, the HBM-bound thin layers): per-thread running sums live in
 // registers for the whole kernel (2 instructions per value) and are reduced once at the end;
 // NG == 0: per-tile transposing butterfly into per-warp shared-memory partials.
-// FAST: LeakyReLU with 0 <= slope <= 1 as max(x, slope*x).
-template <int NG, bool FAST>
+// FAST 1: LeakyReLU with 0 <= slope <= 1 as max(x, slope*x); FAST 2: the Gram kernel's RBF
+// epilogue alpha * exp(-x/2) as one FMUL + EX2 (the epilogue, not the MMA, bounds that kernel).
+template <int NG, int FAST>
 __device__ __forceinline__ void epilogue_loop(const ConvTcParams& p, SharedCtl* ctl,
                                               uint32_t tmem_base, float* s_stats,
-                                              const float* s_bias) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+                                              const float* s_bias, int eg) {
+  const int warp = (threadIdx.x >> 5) & 3, lane = threadIdx.x & 31;   // warp within the group
   const uint32_t n_acc = p.n_acc;
-  uint32_t tl = 0;                                       // local tile counter -> accumulator buffer
-  float* my_stats = s_stats + warp * 2 * p.Cout;
+  uint32_t tl = eg;                  // this group's local tile counter (= the issuing thread's)
+  float* my_stats = s_stats + (eg * kNumEpiWarps + warp) * 2 * p.Cout;
   const int row = warp * 32 + lane;
   const int r_h = row >> 3, r_w = row & 7;
   const int tpi = p.tiles_w * p.tiles_h;
@@ -404,7 +480,7 @@ __device__ __forceinline__ void epilogue_loop(const ConvTcParams& p, SharedCtl* 
 #pragma unroll
   for (int i = 0; i < NA; ++i) rs[i] = rq[i] = 0.f;
   const bool do_stats = p.stats != nullptr;
-  for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+  for (int tile = blockIdx.x + eg * gridDim.x; tile < p.num_tiles; tile += kEpiGroups * gridDim.x) {
     int n = __float2int_rz((float)tile * inv_tpi);
     n += ((n + 1) * tpi <= tile) - (n * tpi > tile);
     const int rem = tile - n * tpi;
@@ -423,7 +499,12 @@ __device__ __forceinline__ void epilogue_loop(const ConvTcParams& p, SharedCtl* 
       auto group = [&](const int g, const int gi) {
         const int c0 = g * 16;
         float v[16];
-        tmem_ld16(t_addr + c0, v);
+        if (p.dbg & 2) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = (float)i;
+        } else {
+          tmem_ld16(t_addr + c0, v);
+        }
         const float4* b4 = reinterpret_cast<const float4*>(s_bias + c0);
 #pragma unroll
         for (int i4 = 0; i4 < 4; ++i4) {
@@ -432,11 +513,13 @@ __device__ __forceinline__ void epilogue_loop(const ConvTcParams& p, SharedCtl* 
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const float x = v[i4 * 4 + k] + bv[k];
-            const float y = FAST ? fmaxf(x, x * alpha) : act_f(x, p.act, alpha);
+            const float y = FAST == 1 ? fmaxf(x, x * alpha)
+                            : (FAST == 2 ? alpha * exp2f(-0.72134752f * fmaxf(x, 0.f))
+                                         : act_f(x, p.act, alpha));
             v[i4 * 4 + k] = valid ? y : 0.f;
           }
         }
-        if (valid) {
+        if (valid && !(p.dbg & 1)) {
           if (!p.out_nchw) {
             float4* o = reinterpret_cast<float4*>(p.out + pix * p.ld_out + c0);
             o[0] = make_float4(v[0], v[1], v[2], v[3]);
@@ -479,7 +562,7 @@ __device__ __forceinline__ void epilogue_loop(const ConvTcParams& p, SharedCtl* 
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(smem_u32(&ctl->tmem_empty[acc]));
-    ++tl;
+    tl += kEpiGroups;
   }
   if (do_stats) {
     if (NG > 0) {
@@ -503,14 +586,17 @@ __device__ __forceinline__ void epilogue_loop(const ConvTcParams& p, SharedCtl* 
 constexpr int kCtlBytes = 1024;     // SharedCtl, then the statistics / bias block
 static_assert(sizeof(SharedCtl) <= kCtlBytes, "SharedCtl must fit below the statistics block");
 
-__global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams p) {
+__global__ void __launch_bounds__(kThreads, 1)
+    conv_tc_kernel(const ConvTcParams p, const __grid_constant__ CUtensorMap tm0,
+                   const __grid_constant__ CUtensorMap tm1) {
   extern __shared__ __align__(1024) uint8_t smem[];
   SharedCtl* ctl = reinterpret_cast<SharedCtl*>(smem);
   float* s_stats = reinterpret_cast<float*>(smem + kCtlBytes);  // [4 warps][2][Cout]
-  const uint32_t stats_bytes = (kNumEpiWarps * 2 + 1) * p.Cout * sizeof(float);   // + bias copy
-  float* s_bias = s_stats + kNumEpiWarps * 2 * p.Cout;
+  const uint32_t stats_bytes = (kEpiGroups * kNumEpiWarps * 2 + 1) * p.Cout * sizeof(float);   // + bias copy
+  float* s_bias = s_stats + kEpiGroups * kNumEpiWarps * 2 * p.Cout;
   const uint32_t a_base = smem_u32(smem) + ((kCtlBytes + stats_bytes + 127) & ~127u);
   const uint32_t b_base = a_base + p.n_a * p.a_stage_bytes;
+  const uint32_t raw_base = (b_base + p.w_bytes + 127) & ~127u;      // TMA mode (resident weights)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -529,12 +615,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
       mbar_init(smem_u32(&ctl->tmem_full[i]), 1);
       mbar_init(smem_u32(&ctl->tmem_empty[i]), kNumEpiWarps);
     }
+    for (int i = 0; i < kMaxRStages; ++i) {
+      mbar_init(smem_u32(&ctl->raw_full[i]), 1);
+      mbar_init(smem_u32(&ctl->raw_empty[i]), kNumLoadWarps / 2);
+    }
     mbar_init(smem_u32(&ctl->w_full), 1);
     fence_barrier_init();
   }
   if (warp == kWgtWarp) tmem_alloc(smem_u32(&ctl->tmem_base), p.tmem_cols);
-  if (warp < kNumEpiWarps) {
-    for (int i = lane; i < 2 * p.Cout; i += 32) s_stats[warp * 2 * p.Cout + i] = 0.f;
+  if (warp < kNumEpiWarps || warp >= kEpiBWarp) {
+    const int ew = warp < kNumEpiWarps ? warp : kNumEpiWarps + (warp - kEpiBWarp);
+    for (int i = lane; i < 2 * p.Cout; i += 32) s_stats[ew * 2 * p.Cout + i] = 0.f;
     if (warp == 0)
       for (int i = lane; i < p.Cout; i += 32) s_bias[i] = p.bias ? __ldg(p.bias + i) : 0.f;
   }
@@ -543,7 +634,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
   tc_fence_after();
   const uint32_t tmem_base = ctl->tmem_base;
 
-  if (warp >= kFirstLoadWarp) {
+  if (warp >= kFirstLoadWarp && warp < kEpiBWarp) {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsLoad));
     // ===================== activation loaders =====================
     // Two groups of 4 warps; group g stages the k-chunks with (global chunk counter & 1) == g, so
@@ -554,25 +645,53 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
     const int grp = (warp - kFirstLoadWarp) >> 2;
     const int U = (p.HP * (p.KC >> 2) + kGroupThreads - 1) / kGroupThreads;   // <= kMaxU (plan)
     switch (U) {
-#define AB_LOAD_CASE(K) case K: loader_loop<K>(p, ctl, a_base, grp); break;
+#define AB_LOAD_CASE(K) case K: loader_loop<K>(p, ctl, a_base, raw_base, grp); break;
       AB_LOAD_CASE(1) AB_LOAD_CASE(2) AB_LOAD_CASE(3) AB_LOAD_CASE(4) AB_LOAD_CASE(5) AB_LOAD_CASE(6)
       AB_LOAD_CASE(7) AB_LOAD_CASE(8) AB_LOAD_CASE(9) AB_LOAD_CASE(10) AB_LOAD_CASE(11)
       AB_LOAD_CASE(12)
 #undef AB_LOAD_CASE
       default: __trap();
     }
-  } else if (warp >= kNumEpiWarps) {
+  } else if (warp >= kNumEpiWarps && warp < kFirstLoadWarp) {
    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsMma));
-   if (warp == kWgtWarp || (warp == kWgtWarp2 && !p.w_resident)) {
-    // ===================== weight producer(s) =====================
+   if (warp == kWgtWarp || (warp == kWgtWarp2 && (!p.w_resident || p.tma))) {
+    // ===================== weight producer(s) / TMA activation producers =====================
     if (elect_one()) {
       if (p.w_resident) {
-        // the packed blob is already in shared-memory order: copy it once, in 16 KB pieces
-        const uint32_t bar = smem_u32(&ctl->w_full);
-        mbar_arrive_expect_tx(bar, p.w_bytes);
-        for (int off = 0; off < p.w_bytes; off += 16384) {
-          const int n = min(16384, p.w_bytes - off);
-          bulk_g2s(b_base + off, reinterpret_cast<const char*>(p.wblob) + off, n, bar);
+        if (warp == kWgtWarp) {
+          // the packed blob is already in shared-memory order: copy it once, in 16 KB pieces
+          const uint32_t bar = smem_u32(&ctl->w_full);
+          mbar_arrive_expect_tx(bar, p.w_bytes);
+          for (int off = 0; off < p.w_bytes; off += 16384) {
+            const int n = min(16384, p.w_bytes - off);
+            bulk_g2s(b_base + off, reinterpret_cast<const char*>(p.wblob) + off, n, bar);
+          }
+        }
+        if (p.tma) {
+          // warp 5 feeds pipeline 0's raw ring, warp 7 pipeline 1's: one cp.async.bulk.tensor per
+          // (tile, k-chunk): box {KC channels, TWp, THp} at (c, w_org, h_org, n); coordinates
+          // outside the image are zero-filled by the copy engine
+          const int pipe = warp == kWgtWarp ? 0 : 1;
+          const uint32_t rn = (uint32_t)p.n_r / 2, rr0 = pipe * rn;
+          const uint32_t bar_full = smem_u32(&ctl->raw_full[0]), bar_empty = smem_u32(&ctl->raw_empty[0]);
+          const int tpi = p.tiles_w * p.tiles_h;
+          const int c_split = p.S.nsrc > 1 ? p.S.s[0].C : (1 << 30);
+          uint32_t rs = 0, rph = 1;
+          for (int tile = blockIdx.x + pipe * gridDim.x; tile < p.num_tiles; tile += 2 * gridDim.x) {
+            const int n = tile / tpi, rem = tile - n * tpi;
+            const int th_i = rem / p.tiles_w, tw_i = rem - th_i * p.tiles_w;
+            const int h_org = th_i * kTileH - p.dil * (p.taps_h >> 1);
+            const int w_org = tw_i * kTileW * p.sub - p.dil * (p.taps_w >> 1);
+            for (int ch = 0; ch < p.n_chunks; ++ch) {
+              mbar_wait(bar_empty + (rr0 + rs) * 8, rph);
+              const uint32_t bar = bar_full + (rr0 + rs) * 8;
+              mbar_arrive_expect_tx(bar, p.raw_bytes);
+              const int c = ch * p.KC;
+              tma_load_4d(raw_base + (rr0 + rs) * p.raw_bytes, c < c_split ? &tm0 : &tm1,
+                          c < c_split ? c : c - c_split, w_org, h_org, n, bar);
+              if (++rs == rn) { rs = 0; rph ^= 1; }
+            }
+          }
         }
       } else {
         // streamed: producer i (warp 5 / warp 7) feeds pipeline i's weight ring for its tiles
@@ -626,16 +745,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const ConvTcParams
     __syncwarp();
    }
   } else {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsEpi));
-    // ===================== epilogue =====================
+    if (kEpiGroups == 1) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsEpi));
+    else asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsEpi));
+    // ===================== epilogue (kEpiGroups groups, group e <-> tiles e mod kEpiGroups) =====
+    const int eg = warp < kNumEpiWarps ? 0 : 1;
     const bool fast = p.act == AB_ACT_LRELU && p.alpha >= 0.f && p.alpha <= 1.f;
     const int ng = p.stats ? p.Cout >> 4 : 0;
     if (fast) {
-      if (ng == 1) epilogue_loop<1, true>(p, ctl, tmem_base, s_stats, s_bias);
-      else if (ng == 2) epilogue_loop<2, true>(p, ctl, tmem_base, s_stats, s_bias);
-      else epilogue_loop<0, true>(p, ctl, tmem_base, s_stats, s_bias);
+      if (ng == 1) epilogue_loop<1, 1>(p, ctl, tmem_base, s_stats, s_bias, eg);
+      else if (ng == 2) epilogue_loop<2, 1>(p, ctl, tmem_base, s_stats, s_bias, eg);
+      else epilogue_loop<0, 1>(p, ctl, tmem_base, s_stats, s_bias, eg);
+    } else if (p.act == AB_ACT_RBF) {
+      epilogue_loop<0, 2>(p, ctl, tmem_base, s_stats, s_bias, eg);
     } else {
-      epilogue_loop<0, false>(p, ctl, tmem_base, s_stats, s_bias);
+      epilogue_loop<0, 0>(p, ctl, tmem_base, s_stats, s_bias, eg);
     }
   }
 
@@ -738,12 +861,16 @@ static int conv_tc_plan(const ab_conv_t* d, ConvTcParams* p, int* smem_bytes) {
   p->x3 = d->math == AB_MATH_TF32X3 ? 1 : 0;
   p->w_bytes = taps * S.Ctot * d->Cout * 4 * (p->x3 ? 2 : 1);
   const int budget = 212 * 1024;
-  const int stats_bytes = (((kNumEpiWarps * 2 + 1) * d->Cout * 4 + 127) & ~127) + kCtlBytes + 128;
+  const int stats_bytes = (((kEpiGroups * kNumEpiWarps * 2 + 1) * d->Cout * 4 + 127) & ~127) + kCtlBytes + 128;
   // Try, in order of preference: (resident weights, 1 sub-tile), (streamed weights, 2 sub-tiles
   // so that every weight stage feeds M = 256), (streamed, 1 sub-tile).
   // tuning hooks (bring-up only): ATOMAI_B200_PLAN="<attempt>,<KC>" pins the plan search
   int force_attempt = -1, force_kc = 0;
   if (const char* e = getenv("ATOMAI_B200_PLAN")) sscanf(e, "%d,%d", &force_attempt, &force_kc);
+  p->dbg = 0;
+  if (const char* e = getenv("ATOMAI_B200_DBG")) p->dbg = atoi(e);
+  const char* e_tma = getenv("ATOMAI_B200_TMA");      // "0" pins the register-staged loaders
+  const bool use_tma = !(e_tma && e_tma[0] == '0');
   bool ok = false;
   for (int attempt = 0; attempt < 3 && !ok; ++attempt) {
     if (force_attempt >= 0 && attempt != force_attempt) continue;
@@ -782,7 +909,38 @@ static int conv_tc_plan(const ab_conv_t* d, ConvTcParams* p, int* smem_bytes) {
       p->n_a = na > kMaxAStages ? kMaxAStages : na;
       p->n_a &= ~1;   // two rings of n_a/2 stages
       p->n_b = n_b; p->sub = sub; p->w_resident = resident;
+      p->tma = 0; p->n_r = 0; p->raw_bytes = 0;
       ok = true;
+    }
+    // TMA mode (resident weights, un-pooled sources, sources split on a chunk boundary): choose
+    // the (KC, operand stages, raw stages) with the most raw bytes in flight
+    if (ok && resident && use_tma && !S.s[0].pool && !(S.nsrc > 1 && S.s[1].pool)) {
+      int best_bytes = 0;
+      for (int KC = pick_kc(S.Ctot); KC >= 16; KC >>= 1) {
+        if (S.Ctot % KC != 0 || (S.nsrc > 1 && S.s[0].C % KC != 0)) continue;
+        if (force_kc > 0 && KC != force_kc) continue;
+        const int P = KC / 4;
+        if (p->HP * P > kMaxU * kGroupThreads) continue;
+        int plane = p->HP * 16;
+        const int want = (128 / P) % 128;
+        plane += ((want - plane % 128) + 128) % 128;
+        const int a_stage = P * plane * (p->x3 ? 2 : 1);
+        const int raw = p->HP * KC * 4;
+        if (raw % 128 != 0) continue;
+        const int avail = budget - stats_bytes - ((p->w_bytes + 127) & ~127);
+        for (int na = 4; na >= 2; na -= 2) {
+          int nr = ((avail - na * a_stage) / raw) & ~1;
+          if (nr > kMaxRStages) nr = kMaxRStages;
+          if (nr < 2) continue;
+          const int score = nr * raw + (na == 4 ? 1 : 0);
+          if (score > best_bytes) {
+            best_bytes = score;
+            p->KC = KC; p->plane_bytes = plane; p->a_stage_bytes = a_stage;
+            p->b_stage_bytes = KC * d->Cout * 4 * (p->x3 ? 2 : 1);
+            p->corr_off = P * plane; p->n_a = na; p->n_r = nr; p->raw_bytes = raw; p->tma = 1;
+          }
+        }
+      }
     }
   }
   AB_CHECK(ok, "conv_tc: no shared-memory plan (Cin=%d Cout=%d dil=%d)", S.Ctot, d->Cout, d->dil);
@@ -794,7 +952,36 @@ static int conv_tc_plan(const ab_conv_t* d, ConvTcParams* p, int* smem_bytes) {
   while (cols < p->n_acc * p->sub * d->Cout) cols <<= 1;
   p->tmem_cols = cols;
   *smem_bytes = stats_bytes + p->n_a * p->a_stage_bytes +
-                (p->w_resident ? ((p->w_bytes + 127) & ~127) : p->n_b * p->b_stage_bytes);
+                (p->w_resident ? ((p->w_bytes + 127) & ~127) : p->n_b * p->b_stage_bytes) +
+                p->n_r * p->raw_bytes + (p->tma ? 128 : 0);
+  return 0;
+}
+
+// 4-D tensor map {C, W, H, N} of one NHWC source (pixel stride ld) with box {KC, TWp, THp, 1}
+static int make_src_tmap(const SrcDev& s, int N, int H, int W, int KC, int TWp, int THp,
+                         CUtensorMap* out) {
+  typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeTiledFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    AB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    AB_CHECK(fn != nullptr && q == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available");
+    encode = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  const cuuint64_t dims[4] = {(cuuint64_t)s.C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  const cuuint64_t strides[3] = {(cuuint64_t)s.ld * 4, (cuuint64_t)W * s.ld * 4,
+                                 (cuuint64_t)H * W * s.ld * 4};
+  const cuuint32_t box[4] = {(cuuint32_t)KC, (cuuint32_t)TWp, (cuuint32_t)THp, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(s.ptr), dims,
+                            strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  AB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d)", (int)r);
   return 0;
 }
 
@@ -824,7 +1011,14 @@ int ab_conv_tc_fwd(const ab_conv_t* d, const float* wblob, const float* bias, fl
   const int sms = ab_num_sms();
   const int grid = p.num_tiles < sms ? p.num_tiles : sms;
   if (grid == 0) return 0;
-  conv_tc_kernel<<<grid, kThreads, smem_bytes, stream>>>(p);
+  CUtensorMap tm0, tm1;
+  memset(&tm0, 0, sizeof(tm0));
+  memset(&tm1, 0, sizeof(tm1));
+  if (p.tma) {
+    if (make_src_tmap(p.S.s[0], p.N, p.H, p.W, p.KC, p.TWp, p.THp, &tm0)) return 1;
+    if (p.S.nsrc > 1 && make_src_tmap(p.S.s[1], p.N, p.H, p.W, p.KC, p.TWp, p.THp, &tm1)) return 1;
+  }
+  conv_tc_kernel<<<grid, kThreads, smem_bytes, stream>>>(p, tm0, tm1);
   AB_LAUNCH_CHECK();
   return 0;
 }

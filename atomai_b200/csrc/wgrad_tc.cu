@@ -235,6 +235,123 @@ __device__ __forceinline__ void wgrad_loader(const WgradTcParams& p, Ctl* ctl, u
   }
 }
 
+// Fast loader for un-pooled sources with <= 8 input pieces (one 32-channel block) and <= ND dy
+// pieces per pixel and a halo of <= 256 pixels: a thread owns the dy pixel `gt` and the halo
+// pixels gt and gt + 128, and issues EVERY load of the tile (up to 8 + 8 + ND float4) before it
+// waits for the shared-memory slot — one memory round trip per tile, overlapped with the MMAs of
+// the tiles in front of it, instead of three serialised ones behind the slot wait.
+template <int ND>
+__device__ __forceinline__ void wgrad_loader_fast(const WgradTcParams& p, Ctl* ctl, uint32_t base,
+                                                  const float4* s_aff, int grp, int gt, int t_begin,
+                                                  int t_end, int co0, int ci0, int PD, int PX) {
+  constexpr int NX = 8;
+  const int lane = threadIdx.x & 31;
+  const int H = p.H, W = p.W, HP = p.HP;
+  const int tpi = p.tiles_w * p.tiles_h;
+  const uint32_t mulTpi = fdiv_mul(tpi), mulTw = fdiv_mul(p.tiles_w), mulT = fdiv_mul(p.TWp);
+  const uint32_t S = p.n_stages;
+  const int n_groups = S >= (uint32_t)kGroups ? kGroups : 2;
+  if (grp >= n_groups) return;
+  const int c_split = p.S.nsrc > 1 ? p.S.s[0].C : (1 << 30);
+  const bool has_aff = p.S.s[0].scale != nullptr || (p.S.nsrc > 1 && p.S.s[1].scale != nullptr);
+  const bool x3 = p.x3 != 0;
+  const uint32_t xlo_off = p.x_bytes, dlo_off = p.dy_bytes;
+  const uint32_t d_rel = p.x_bytes * (p.x3 ? 2 : 1) + (p.fs ? p.dpad * 1024 : 0);
+  const uint32_t d_row = d_rel + gt * 128, d_sw = (uint32_t)(gt & 3) << 5;
+  const int d_r = gt >> 3, d_c = gt & 7;
+  const int q1 = gt + kGroupThreads;
+  const bool has_q1 = q1 < HP;
+  const uint32_t hh0 = fdiv(gt, p.TWp, mulT), ww0 = gt - hh0 * p.TWp;
+  const uint32_t hh1 = has_q1 ? fdiv(q1, p.TWp, mulT) : 0u, ww1 = has_q1 ? q1 - hh1 * p.TWp : 0u;
+  const uint32_t sw0 = (uint32_t)(gt & 3) << 5, sw1 = (uint32_t)(q1 & 3) << 5;
+  uint32_t st = grp % S, ph = ((grp / S) & 1) ^ 1;
+  for (int tile = t_begin + grp; tile < t_end; tile += n_groups) {
+    const uint32_t x0 = base + st * p.stage_bytes;
+    const int n = (int)fdiv(tile, tpi, mulTpi);
+    const int rem = tile - n * tpi;
+    const int th_i = (int)fdiv(rem, p.tiles_w, mulTw);
+    const int tw_i = rem - th_i * p.tiles_w;
+    const int h0 = th_i * kTileH, w0 = tw_i * kTileW;
+    const int h_org = h0 - p.dil * (p.taps_h >> 1), w_org = w0 - p.dil * (p.taps_w >> 1);
+    const size_t img = (size_t)n * H;
+    // ---- issue every load of this tile
+    float4 xa[NX], xb[NX], dv[ND];
+    const int gha = h_org + (int)hh0, gwa = w_org + (int)ww0;
+    const int ghb = h_org + (int)hh1, gwb = w_org + (int)ww1;
+    const bool oka = (unsigned)gha < (unsigned)H && (unsigned)gwa < (unsigned)W;
+    const bool okb = has_q1 && (unsigned)ghb < (unsigned)H && (unsigned)gwb < (unsigned)W;
+    {
+      const size_t pa = (img + min(max(gha, 0), H - 1)) * W + min(max(gwa, 0), W - 1);
+      const size_t pb = (img + min(max(ghb, 0), H - 1)) * W + min(max(gwb, 0), W - 1);
+      const float* a0 = p.S.s[0].ptr + pa * p.S.s[0].ld + ci0;
+      const float* a1 = p.S.nsrc > 1 ? p.S.s[1].ptr + pa * p.S.s[1].ld + (ci0 - c_split) : a0;
+      const float* b0 = p.S.s[0].ptr + pb * p.S.s[0].ld + ci0;
+      const float* b1 = p.S.nsrc > 1 ? p.S.s[1].ptr + pb * p.S.s[1].ld + (ci0 - c_split) : b0;
+#pragma unroll
+      for (int j = 0; j < NX; ++j)
+        if (j < PX) xa[j] = __ldg(reinterpret_cast<const float4*>(((ci0 + j * 4 < c_split) ? a0 : a1) + j * 4));
+      if (has_q1) {
+#pragma unroll
+        for (int j = 0; j < NX; ++j)
+          if (j < PX) xb[j] = __ldg(reinterpret_cast<const float4*>(((ci0 + j * 4 < c_split) ? b0 : b1) + j * 4));
+      }
+    }
+    const int ghd = h0 + d_r, gwd = w0 + d_c;
+    const bool okd = ghd < H && gwd < W;
+    {
+      const float* db = p.dy + ((img + min(ghd, H - 1)) * W + min(gwd, W - 1)) * p.ld_dy + co0;
+#pragma unroll
+      for (int j = 0; j < ND; ++j)
+        if (j < PD) dv[j] = __ldg(reinterpret_cast<const float4*>(db + j * 4));
+    }
+    // ---- wait for the slot, transform, store
+    mbar_wait(smem_u32(&ctl->empty[st]), ph);
+    auto put_x = [&](float4 x, int j, uint32_t row, uint32_t sw, uint32_t msk) {
+      if (has_aff) {
+        const float4 sc = s_aff[2 * j], sh = s_aff[2 * j + 1];
+        x.x = fmaf(x.x, sc.x, sh.x); x.y = fmaf(x.y, sc.y, sh.y);
+        x.z = fmaf(x.z, sc.z, sh.z); x.w = fmaf(x.w, sc.w, sh.w);
+      }
+      const uint32_t dst = row + (((uint32_t)(j & 7) << 4) ^ sw);
+      sts128u(dst, tf32b(x.x) & msk, tf32b(x.y) & msk, tf32b(x.z) & msk, tf32b(x.w) & msk);
+      if (x3) {
+        const float4 l = part4(x, true);
+        sts128u(dst + xlo_off, tf32b(l.x) & msk, tf32b(l.y) & msk, tf32b(l.z) & msk, tf32b(l.w) & msk);
+      }
+    };
+    {
+      const uint32_t ma = oka ? 0xFFFFFFFFu : 0u, mb = okb ? 0xFFFFFFFFu : 0u;
+#pragma unroll
+      for (int j = 0; j < NX; ++j)
+        if (j < PX) put_x(xa[j], j, x0 + gt * 128, sw0, ma);
+      if (has_q1) {
+#pragma unroll
+        for (int j = 0; j < NX; ++j)
+          if (j < PX) put_x(xb[j], j, x0 + q1 * 128, sw1, mb);
+      }
+    }
+    {
+      const uint32_t msk = okd ? 0xFFFFFFFFu : 0u;
+#pragma unroll
+      for (int j = 0; j < ND; ++j) {
+        if (j < PD) {
+          const uint32_t dst = x0 + d_row + (j >> 3) * kChunk + (((uint32_t)(j & 7) << 4) ^ d_sw);
+          sts128u(dst, tf32b(dv[j].x) & msk, tf32b(dv[j].y) & msk, tf32b(dv[j].z) & msk, tf32b(dv[j].w) & msk);
+          if (x3) {
+            const float4 l = part4(dv[j], true);
+            sts128u(dst + dlo_off, tf32b(l.x) & msk, tf32b(l.y) & msk, tf32b(l.z) & msk, tf32b(l.w) & msk);
+          }
+        }
+      }
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(smem_u32(&ctl->full[st]));
+    st += n_groups;
+    while (st >= S) { st -= S; ph ^= 1; }
+  }
+}
+
 __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const WgradTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   Ctl* ctl = reinterpret_cast<Ctl*>(smem);
@@ -297,7 +414,14 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const WgradTcPara
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsLoad));
     const int grp = warp >= kFirstLoadWarp ? (warp - kFirstLoadWarp) >> 2 : 2;
     const int gt = threadIdx.x & (kGroupThreads - 1);   // warps 0-3, 8-11, 12-15 -> 0..127
-    wgrad_loader(p, ctl, base, s_aff, grp, gt, t_begin, t_end, co0, ci0, PD, PX);
+    const bool pooled = p.S.s[0].pool || (p.S.nsrc > 1 && p.S.s[1].pool);
+    if (!pooled && p.HP <= 2 * kGroupThreads && PX <= 8 && PD <= 16) {
+      if (PD <= 4) wgrad_loader_fast<4>(p, ctl, base, s_aff, grp, gt, t_begin, t_end, co0, ci0, PD, PX);
+      else if (PD <= 8) wgrad_loader_fast<8>(p, ctl, base, s_aff, grp, gt, t_begin, t_end, co0, ci0, PD, PX);
+      else wgrad_loader_fast<16>(p, ctl, base, s_aff, grp, gt, t_begin, t_end, co0, ci0, PD, PX);
+    } else {
+      wgrad_loader(p, ctl, base, s_aff, grp, gt, t_begin, t_end, co0, ci0, PD, PX);
+    }
     if (warp < kNumEpiWarps && t_end > t_begin) {
       // ===================== epilogue: TMEM -> atomics into dW (OIHW) =====================
       // accumulator row m = chunk * 32 + lane: chunk = warp = horizontal tap (stacked) or

@@ -197,15 +197,22 @@ class Tape:
             scale = torch.empty(cout, device=dev, dtype=torch.float32)
             shift = torch.empty(cout, device=dev, dtype=torch.float32)
             if use_batch_stats:
-                if self.comm is not None:
-                    count = self.comm.allreduce_count(count)
-                    self.comm.allreduce_sum_(stats)
                 mean = torch.empty(cout, device=dev, dtype=torch.float32)
                 invstd = torch.empty(cout, device=dev, dtype=torch.float32)
                 mom = bn_mod.momentum if bn_mod.momentum is not None else 0.1
-                ops.bn_finalize(stats, count, _d(bn_mod.weight), _d(bn_mod.bias),
-                                bn_mod.running_mean, bn_mod.running_var, mom, bn_mod.eps, True,
-                                scale, shift, mean, invstd)
+                fused = False
+                if self.comm is not None:
+                    count = self.comm.allreduce_count(count)
+                    # one kernel: exchange of the statistics over NVLink peer memory + finalise
+                    fused = getattr(self.comm, "bn_finalize_fused", lambda *a: False)(
+                        stats, count, _d(bn_mod.weight), _d(bn_mod.bias), bn_mod.running_mean,
+                        bn_mod.running_var, mom, bn_mod.eps, scale, shift, mean, invstd)
+                    if not fused:
+                        self.comm.allreduce_sum_(stats)
+                if not fused:
+                    ops.bn_finalize(stats, count, _d(bn_mod.weight), _d(bn_mod.bias),
+                                    bn_mod.running_mean, bn_mod.running_var, mom, bn_mod.eps, True,
+                                    scale, shift, mean, invstd)
                 if bn_mod.num_batches_tracked is not None:
                     bn_mod.num_batches_tracked.add_(1)
             else:

@@ -262,6 +262,27 @@ int atomai_b200_augment(const float* x, float* y, float* scratch, const int64_t*
                         int h, int w, float in_min, float in_max, uint64_t seed, float* minmax,
                         void* stream);
 
+/* ---- multi-GPU: small all-reduce over NVLink peer memory (csrc/p2p.cu) -----------------
+ * Every rank exposes a zero-initialised mailbox (atomai_b200_p2p_data_bytes) and flag buffer
+ * (atomai_b200_p2p_flag_bytes) to its peers (CUDA IPC: atomai_b200_ipc_export gives the 64-byte
+ * handle of the enclosing allocation + the offset inside it, atomai_b200_ipc_import maps it for the
+ * current device with peer access); data_ptrs / flag_ptrs are HOST arrays of
+ * the `world` mapped device pointers in rank order.  All ranks call with the same, strictly
+ * increasing `epoch`.  allreduce: vals[0:n] <- sum over ranks (n <= 1024 doubles).
+ * bn_finalize: the same exchange fused with atomai_b200_bn_finalize(training = 1) —
+ * synchronised BatchNorm statistics without an NCCL launch per layer. */
+int atomai_b200_ipc_export(const void* ptr, unsigned char* handle64, int64_t* offset);
+int atomai_b200_ipc_import(const unsigned char* handle64, int64_t offset, void** ptr_out);
+int64_t atomai_b200_p2p_data_bytes(int world);
+int64_t atomai_b200_p2p_flag_bytes(int world);
+int atomai_b200_p2p_allreduce(void* const* data_ptrs_host, void* const* flag_ptrs_host, int world,
+                              int rank, uint64_t epoch, double* vals, int n, void* stream);
+int atomai_b200_p2p_bn_finalize(void* const* data_ptrs_host, void* const* flag_ptrs_host, int world,
+                                int rank, uint64_t epoch, double* stats, int C, double count,
+                                const float* gamma, const float* beta, float* running_mean,
+                                float* running_var, float momentum, float eps, float* scale,
+                                float* shift, float* mean, float* invstd, void* stream);
+
 /* ---- self-test hooks (tests only) ------------------------------------------------
  * Raw tcgen05 GEMM D[128][N] = A[128][K] B[N][K]^T on core-matrix ("interleave")
  * operands, used by tests to pin descriptor conventions. */

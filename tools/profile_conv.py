@@ -5,7 +5,7 @@ sys.path.insert(0, ROOT)
 import torch
 from atomai_b200 import ops
 from atomai_b200.ops import Source
-shapes = {"c40": (32, 128, 128, 64), "c1": (32, 512, 1, 16), "c61": (32, 512, 16, 16), "c6": (32, 512, 32, 16), "bn3": (32, 64, 128, 128), "c5": (32, 256, 64, 32)}
+shapes = {"c40": (32, 128, 128, 64), "c1": (32, 512, 1, 16), "c61": (32, 512, 16, 16), "c6": (32, 512, 32, 16), "bn3": (32, 64, 128, 128), "c5": (32, 256, 64, 32), "c51": (32, 256, 32, 32)}
 which = [a for a in sys.argv[1:] if a != "wgrad"] or ["c6", "bn3"]
 do_wgrad = "wgrad" in sys.argv[1:]
 for tag in which:
