@@ -32,6 +32,18 @@ void ab_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+int ab_optin_smem(const void* func, int bytes, unsigned char* done) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = -1;
+  if (dev >= 0 && done[dev]) return 0;
+  if (cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) {
+    ab_set_error("cudaFuncSetAttribute(MaxDynamicSharedMemorySize=%d) failed", bytes);
+    return 1;
+  }
+  if (dev >= 0) done[dev] = 1;
+  return 0;
+}
+
 int ab_num_sms() {
   static int sms[64] = {0};
   int dev = 0;

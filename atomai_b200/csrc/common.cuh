@@ -28,6 +28,9 @@ void ab_set_error(const char* fmt, ...);
 #define AB_LAUNCH_CHECK() AB_CUDA(cudaGetLastError())
 
 int ab_num_sms();  // cached SM count of the current device
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: `done` is a per-kernel table
+// indexed by the current device (set once per device, benign if two threads race)
+int ab_optin_smem(const void* func, int bytes, unsigned char* done);
 
 // ---------------------------------------------------------------- device utils
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -94,13 +97,25 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
   return ok;
 }
 // Bounded wait: a protocol bug must surface as a trapped launch, never a hung GPU.
+__device__ __forceinline__ uint64_t global_timer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
+  uint64_t t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 15)) {     // x up to 0.2 ms per try: a few seconds
-      printf("atomai_b200: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n",
-             blockIdx.x, threadIdx.x, bar, parity);
-      __trap();
+    // wall-clock bound (20 s), not a spin count: under a profiler's instrumented replay a healthy
+    // kernel can run two orders of magnitude slower, and the suspend hint is only an upper limit
+    if ((++spins & 255u) == 0) {
+      const uint64_t now = global_timer_ns();
+      if (t0 == 0) t0 = now;
+      if (now - t0 > 20000000000ull) {
+        printf("atomai_b200: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n",
+               blockIdx.x, threadIdx.x, bar, parity);
+        __trap();
+      }
     }
   }
 }

@@ -694,12 +694,10 @@ int ab_conv_simt_fwd(const ab_conv_t* d, const float* w, const float* bias, floa
   const int smem = (F_CIT * (F_TH + 2 * ph) * (F_TW + 2 * pw) + d->ks_h * d->ks_w * F_CIT * F_COT) *
                    (int)sizeof(float);
   AB_CHECK(smem <= 200 * 1024, "conv_simt: dilation %d too large", d->dil);
-  static int configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    AB_CUDA(cudaFuncSetAttribute(conv_simt_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 200 * 1024));
-    configured = 200 * 1024;
-  }
+  static unsigned char optin[64];
+  if (smem > 48 * 1024 &&
+      ab_optin_smem(reinterpret_cast<const void*>(conv_simt_fwd_kernel), 200 * 1024, optin))
+    return 1;
   const int64_t tiles = (int64_t)d->N * p.tiles_h * p.tiles_w;
   AB_CHECK(tiles < (1ll << 31), "conv_simt: too many tiles");
   if (tiles == 0) return 0;

@@ -1002,12 +1002,8 @@ int ab_conv_tc_fwd(const ab_conv_t* d, const float* wblob, const float* bias, fl
   AB_CHECK(((uintptr_t)wblob & 15) == 0 && ((uintptr_t)y & 15) == 0 && ld_y % 4 == 0,
            "conv_tc: unaligned weight blob / output");
   p.wblob = wblob; p.bias = bias; p.out = y; p.ld_out = ld_y; p.stats = stats;
-  static int configured_smem = 0;
-  if (smem_bytes > configured_smem) {
-    AB_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 226 * 1024));
-    configured_smem = 226 * 1024;
-  }
+  static unsigned char optin[64];
+  if (ab_optin_smem(reinterpret_cast<const void*>(conv_tc_kernel), 226 * 1024, optin)) return 1;
   const int sms = ab_num_sms();
   const int grid = p.num_tiles < sms ? p.num_tiles : sms;
   if (grid == 0) return 0;

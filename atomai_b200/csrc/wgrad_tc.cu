@@ -607,12 +607,8 @@ int ab_conv_tc_wgrad(const ab_conv_t* d, const float* dy, int ld_dy, float* dw,
   AB_CHECK(((uintptr_t)dy & 15) == 0 && ld_dy % 4 == 0, "wgrad_tc: unaligned dy");
   p.dy = dy; p.ld_dy = ld_dy; p.dw = dw;
   if (p.num_tiles == 0) return 0;
-  static int configured = 0;
-  if (!configured) {
-    AB_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 226 * 1024));
-    configured = 1;
-  }
+  static unsigned char optin[64];
+  if (ab_optin_smem(reinterpret_cast<const void*>(wgrad_tc_kernel), 226 * 1024, optin)) return 1;
   const int grid = p.ranges * p.n_cc * p.co_blocks;
   wgrad_tc_kernel<<<grid, kThreads, smem, stream>>>(p);
   AB_LAUNCH_CHECK();

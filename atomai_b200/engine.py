@@ -18,27 +18,45 @@ import torch
 from . import ops
 from .ops import ACT_LRELU, ACT_TANH, MATH_FP32, MATH_TF32, MATH_TF32X3, Source
 
-_MATH = {"mode": MATH_TF32X3, "wgrad_tc": True}   # default: the mode that meets the fp32 tolerances
+_MATH = {"mode": MATH_TF32X3, "wgrad_tc": True,   # default: the mode that meets the fp32 tolerances
+         "wgrad": MATH_TF32}                        # weight-gradient contraction (None: same mode)
 
 
 _MODES = {"fp32": MATH_FP32, "tf32": MATH_TF32, "tf32x3": MATH_TF32X3}
 
 
-def set_math(mode: str = "tf32x3", wgrad_tc: Optional[bool] = None) -> None:
+def set_math(mode: str = "tf32x3", wgrad_tc: Optional[bool] = None,
+             wgrad_math: Optional[str] = "auto") -> None:
     """Arithmetic of the convolution family:
       'tf32'   tcgen05 tensor cores, operands RN-rounded to TF32 (what stock PyTorch/cuDNN does by
                default on CUDA); ~1e-3 relative on the logits of a 17-layer Unet;
       'tf32x3' the same kernels with every operand split into a TF32 high and low part (three MMAs
                per product, fp32 accumulate): matches the reference's fp32 CPU results to ~1e-6;
-      'fp32'   exact FFMA (CUDA-core) kernels."""
+      'fp32'   exact FFMA (CUDA-core) kernels.
+    wgrad_math ('auto' | 'same' | 'tf32' | 'tf32x3'): arithmetic of the weight-gradient contraction
+    only.  Its reduction runs over every pixel of the batch (K = N*H*W ~ 10^4..10^7 terms), so the
+    unbiased RN operand rounding of single TF32 averages out there (relative error ~2^-12/sqrt(K)
+    per term) instead of accumulating as in the K = 9*Cin forward / dgrad contractions, whose
+    errors BatchNorm's backward then amplifies.  'auto' (default) therefore runs the weight
+    gradients of 'tf32x3' in single TF32: measured on the 17-layer Unet against the exact-fp32
+    mode, total gradient error 7.7e-4 (4x256^2) / 1.9e-4 (2x64^2) vs 7.6e-4 / 4e-6 with split
+    weight gradients ('same') — tools/debug_wgrad_mix.py, tests/test_unet_gpu.py."""
     assert mode in _MODES, f"math mode must be one of {sorted(_MODES)}"
     _MATH["mode"] = _MODES[mode]
+    assert wgrad_math in (None, "auto", "same", "tf32", "tf32x3")
+    if wgrad_math == "auto":
+        wgrad_math = "tf32" if mode == "tf32x3" else "same"
+    _MATH["wgrad"] = None if wgrad_math in (None, "same") or mode == "fp32" else _MODES[wgrad_math]
     if wgrad_tc is not None:
         _MATH["wgrad_tc"] = bool(wgrad_tc)
 
 
 def get_math() -> str:
-    return {v: k for k, v in _MODES.items()}[_MATH["mode"]]
+    inv = {v: k for k, v in _MODES.items()}
+    m = inv[_MATH["mode"]]
+    if _MATH["wgrad"] is not None and _MATH["wgrad"] != _MATH["mode"]:
+        m += "+wgrad-" + inv[_MATH["wgrad"]]
+    return m
 
 
 class Act:
@@ -272,8 +290,9 @@ class Tape:
         srcs_s = [s.source() for s in r.srcs]
         dw = torch.zeros((wt.shape[0], wt.shape[1], r.ks[0], r.ks[1]), device=dev,
                          dtype=torch.float32)
-        dsc = ops.conv_desc(srcs_s, n, h, w, cout, r.ks, r.dil, 1.0, r.math)
-        if r.math != MATH_FP32 and not (_MATH["wgrad_tc"] and ops.conv_supported(dsc, 1)):
+        wmath = r.math if (r.math == MATH_FP32 or _MATH["wgrad"] is None) else _MATH["wgrad"]
+        dsc = ops.conv_desc(srcs_s, n, h, w, cout, r.ks, r.dil, 1.0, wmath)
+        if wmath != MATH_FP32 and not (_MATH["wgrad_tc"] and ops.conv_supported(dsc, 1)):
             dsc.math = MATH_FP32
         ops.conv_wgrad(dsc, dpre, dw)
         self._add_pgrad(wt, dw)
@@ -417,6 +436,56 @@ class Tape:
         out = Act(out_t)
         if self.record:
             self.ops.append(("custom", _AddRec(a, b, out)))
+        return out
+
+    def cat(self, xs: Sequence[Act]) -> Act:
+        """torch.cat(xs, 1) written out (pending affines applied on the way) — for concatenations a
+        convolution cannot take as separate sources (more than two, or channel counts that are not
+        multiples of 4: ResHedNet's side outputs, atomai/nets/fcnn.py:295)."""
+        xs = [self.materialize(x) if x.pool else x for x in xs]
+        n, h, w, _ = xs[0].t.shape
+        ctot = sum(x.C for x in xs)
+        out_t = torch.empty((n, h, w, ctot), device=xs[0].t.device, dtype=torch.float32)
+        c0, parts = 0, []
+        for x in xs:
+            sl = out_t[..., c0:c0 + x.C]
+            if x.scale is not None:
+                ops.affine(x.t, x.scale, x.shift, sl)
+            else:
+                ops.add_slice(x.t, sl, False)
+            parts.append((x, c0, c0 + x.C))
+            c0 += x.C
+        out = Act(out_t)
+        if self.record:
+            self.ops.append(("custom", _CatRec(out, parts)))
+        return out
+
+    def bn_res_act(self, x: Act, res: Optional[Act], slope: float) -> Act:
+        """LeakyReLU(BatchNorm(x) [+ res]) — the tail of a ResBlock (atomai/nets/blocks.py:205-213:
+        `out = bn(out); out += residual; out = leaky_relu(out)`) as one pass: x carries the
+        BatchNorm as its pending affine."""
+        assert not x.pool and slope > 0
+        if res is not None and res.pending():
+            res = self.materialize(res)
+        out_t = torch.empty(x.t.shape, device=x.t.device, dtype=torch.float32)
+        ops.affine_res_act(x.t, x.scale, x.shift, None if res is None else res.t, slope, out_t)
+        out = Act(out_t)
+        if self.record:
+            self.ops.append(("custom", _ResActRec(x, res, out, slope)))
+        return out
+
+    def resize(self, x: Act, factor: int, mode: str = "bilinear") -> Act:
+        """F.interpolate(x, size=factor*(h, w), mode) (atomai/nets/fcnn.py:292-293)."""
+        if factor == 1:
+            return x
+        if x.pending():
+            x = self.materialize(x)
+        n, h, w, c = x.t.shape
+        out_t = torch.empty((n, factor * h, factor * w, c), device=x.t.device, dtype=torch.float32)
+        ops.resize_fwd(x.t, out_t, factor, mode == "bilinear")
+        out = Act(out_t, needs_grad=x.needs_grad)
+        if self.record:
+            self.ops.append(("custom", _ResizeRec(x, out, factor, mode == "bilinear")))
         return out
 
     # ------------------------------------------------------------------ dense layers
@@ -706,6 +775,52 @@ class _AddRec:
         for s_ in (self.a, self.b):
             if s_.needs_grad:
                 _acc_grad(s_, g, False)
+
+
+class _CatRec:
+    def __init__(self, out, parts):
+        self.out, self.parts = out, parts
+
+    def backward(self, tape):
+        g = self.out.grad
+        self.out.grad = None
+        if g is None:
+            return
+        for x, c0, c1 in self.parts:
+            if x.needs_grad:
+                _acc_grad(x, g[..., c0:c1], False)
+
+
+class _ResActRec:
+    def __init__(self, x, res, out, slope):
+        self.x, self.res, self.out, self.slope = x, res, out, slope
+
+    def backward(self, tape):
+        dy = self.out.grad
+        self.out.grad = None
+        if dy is None:
+            return
+        g = torch.empty(self.out.t.shape, device=dy.device, dtype=torch.float32)
+        ops.lrelu_mask_bwd(dy, self.out.t, self.slope, g)
+        shared = self.res is not None and self.res.needs_grad
+        if self.x.needs_grad:
+            _acc_grad(self.x, g, not shared)
+        if shared:
+            _acc_grad(self.res, g, False)
+
+
+class _ResizeRec:
+    def __init__(self, x, out, factor, bilinear):
+        self.x, self.out, self.factor, self.bilinear = x, out, factor, bilinear
+
+    def backward(self, tape):
+        g = self.out.grad
+        self.out.grad = None
+        if g is None or not self.x.needs_grad:
+            return
+        dx = torch.zeros(self.x.t.shape, device=g.device, dtype=torch.float32)
+        ops.resize_bwd(_dense(g), dx, self.factor, self.bilinear)
+        _acc_grad(self.x, dx, True)
 
 
 class _PadRec:

@@ -118,6 +118,83 @@ class UpsampleBlock(nn.Module):
         return engine.run(self, x)
 
 
+class ResBlock(nn.Module):
+    """
+    Builds a residual block: 1x1 conv -> [3x3 conv -> BN -> LeakyReLU -> 3x3 conv -> BN] + skip ->
+    LeakyReLU (atomai/nets/blocks.py:135-214; identical signature and parameter names).  Natively:
+    three tcgen05 convolutions with the BatchNorm statistics in their epilogues, and the
+    BN-affine + residual add + LeakyReLU tails as one HBM pass each (csrc/resnet.cu).
+    """
+    def __init__(self,
+                 ndim: int,
+                 input_channels: int,
+                 output_channels: int,
+                 kernel_size: Union[Tuple[int], int] = 3,
+                 stride: Union[Tuple[int], int] = 1,
+                 padding: Union[Tuple[int], int] = 1,
+                 batch_norm: bool = True,
+                 lrelu_a: float = 0.01) -> None:
+        super(ResBlock, self).__init__()
+        if not 0 < ndim < 3:
+            raise AssertionError("ndim must be equal to 1 or 2")
+        conv = nn.Conv2d if ndim == 2 else nn.Conv1d
+        self.lrelu_a = lrelu_a
+        self.batch_norm = batch_norm
+        self.c0 = conv(input_channels, output_channels, kernel_size=1, stride=1, padding=0)
+        self.c1 = conv(output_channels, output_channels, kernel_size=3, stride=1, padding=1)
+        self.c2 = conv(output_channels, output_channels, kernel_size=3, stride=1, padding=1)
+        if batch_norm:
+            bn = nn.BatchNorm2d if ndim == 2 else nn.BatchNorm1d
+            self.bn1 = bn(output_channels)
+            self.bn2 = bn(output_channels)
+        self._squeeze_h = ndim == 1
+
+    def _emit(self, tape: Tape, x: Union[Act, Sequence[Act]]) -> Act:
+        a = float(self.lrelu_a)
+        if not a > 0:
+            raise NotImplementedError("native ResBlock needs a LeakyReLU slope > 0")
+        x0 = tape.conv(x, self.c0, None, 1.0)                       # residual
+        if self.batch_norm:
+            h = tape.bn_res_act(tape.conv(x0, self.c1, self.bn1, 1.0), None, a)
+            return tape.bn_res_act(tape.conv(h, self.c2, self.bn2, 1.0), x0, a)
+        h = tape.conv(x0, self.c1, None, a)                          # fused LeakyReLU epilogue
+        return tape.bn_res_act(tape.conv(h, self.c2, None, 1.0), x0, a)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return engine.run(self, x)
+
+
+class ResModule(nn.Module):
+    """
+    Stitches multiple convolutional blocks with residual connections together
+    (atomai/nets/blocks.py:217-254).
+    """
+    def __init__(self,
+                 ndim: int,
+                 res_depth: int,
+                 input_channels: int,
+                 output_channels: int,
+                 batch_norm: bool = True,
+                 lrelu_a: float = 0.01) -> None:
+        super(ResModule, self).__init__()
+        res_module = []
+        for i in range(res_depth):
+            input_channels = output_channels if i > 0 else input_channels
+            res_module.append(
+                ResBlock(ndim, input_channels, output_channels,
+                         lrelu_a=lrelu_a, batch_norm=batch_norm))
+        self.res_module = nn.Sequential(*res_module)
+        self._squeeze_h = ndim == 1
+
+    def _emit(self, tape: Tape, x: Union[Act, Sequence[Act]]) -> Act:
+        for blk in self.res_module:
+            x = blk._emit(tape, x)
+        return x
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return engine.run(self, x)
+
+
 class DilatedBlock(nn.Module):
     """
     Creates a "cascade" with dilated convolutional layers (aka atrous convolutions);

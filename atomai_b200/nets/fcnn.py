@@ -3,8 +3,7 @@ Fully convolutional neural networks — Unet and dilnet with the reference's con
 signatures, module names and checkpoint layout (atomai/nets/fcnn.py:18-226, 379-442), executed
 as one native sm_100a graph per call (see atomai_b200/engine.py).
 
-ResHedNet / SegResNet (ResBlock based) are outside the hot-path scope of this build
- and raise NotImplementedError.
+ResHedNet / SegResNet (ResBlock based, atomai/nets/fcnn.py:229-376) run on the same native tape.
 """
 from typing import List, Type, Union
 
@@ -13,7 +12,7 @@ import torch.nn as nn
 
 from .. import engine
 from ..engine import Act, Tape
-from .blocks import ConvBlock, DilatedBlock, UpsampleBlock
+from .blocks import ConvBlock, DilatedBlock, ResModule, UpsampleBlock
 
 
 class Unet(nn.Module):
@@ -120,6 +119,93 @@ class dilnet(nn.Module):
         return engine.run(self, x)
 
 
+class ResHedNet(nn.Module):
+    """
+    Holistically nested edge detector with residual connections in each block
+    (arguments, module names and state_dict keys as in atomai/nets/fcnn.py:229-296).
+    """
+    def __init__(self,
+                 nb_classes: int = 1,
+                 nb_filters: int = 64,
+                 upsampling_mode: str = "bilinear",
+                 **kwargs: List[int]) -> None:
+        super(ResHedNet, self).__init__()
+        nbl = kwargs.get("layers", [3, 4, 5])
+        self.upsample = upsampling_mode
+        self.net1 = ResModule(2, nbl[0], 1, nb_filters, True)
+        self.net2 = nn.Sequential(
+            nn.MaxPool2d(2, 2),
+            ResModule(2, nbl[1], nb_filters, 2*nb_filters, True)
+        )
+        self.net3 = nn.Sequential(
+            nn.MaxPool2d(2, 2),
+            ResModule(2, nbl[2], 2*nb_filters, 4*nb_filters, True)
+        )
+        self.net1score = nn.Sequential(
+            nn.Conv2d(nb_filters, nb_classes, 1, 1, 0),
+            nn.BatchNorm2d(nb_classes)
+        )
+        self.net2score = nn.Sequential(
+            nn.Conv2d(2*nb_filters, nb_classes, 1, 1, 0),
+            nn.BatchNorm2d(nb_classes)
+        )
+        self.net3score = nn.Sequential(
+            nn.Conv2d(4*nb_filters, nb_classes, 1, 1, 0),
+            nn.BatchNorm2d(nb_classes)
+        )
+        self.out = torch.nn.Conv2d(3*nb_classes, nb_classes, 1, 1, 0)
+
+    def _emit(self, tape: Tape, x: Act) -> Act:
+        n1 = self.net1._emit(tape, x)
+        n2 = self.net2[1]._emit(tape, tape.pool(n1))
+        n3 = self.net3[1]._emit(tape, tape.pool(n2))
+        # side outputs: 1x1 conv -> BatchNorm (no activation), brought to the input size
+        s1 = tape.conv(n1, self.net1score[0], self.net1score[1], 1.0)
+        s2 = tape.resize(tape.conv(n2, self.net2score[0], self.net2score[1], 1.0), 2, self.upsample)
+        s3 = tape.resize(tape.conv(n3, self.net3score[0], self.net3score[1], 1.0), 4, self.upsample)
+        return tape.conv(tape.cat([s1, s2, s3]), self.out, None, 1.0)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return engine.run(self, x)
+
+
+class SegResNet(nn.Module):
+    """
+    Builds a fully convolutional neural network based on SegNet architecture
+    with residual blocks for semantic segmentation
+    (arguments, module names and state_dict keys as in atomai/nets/fcnn.py:299-376).
+    """
+    def __init__(self,
+                 nb_classes: int = 1,
+                 nb_filters: int = 32,
+                 batch_norm: bool = True,
+                 upsampling_mode: str = "bilinear",
+                 **kwargs: List[int]) -> None:
+        super(SegResNet, self).__init__()
+        nbl = kwargs.get("layers", [2, 2, 2])
+        self.c1 = ConvBlock(2, 1, 1, nb_filters, batch_norm=batch_norm)
+        self.c2 = ResModule(2, nbl[0], nb_filters, nb_filters*2, batch_norm=batch_norm)
+        self.bn = ResModule(2, nbl[1], nb_filters*2, nb_filters*4, batch_norm=batch_norm)
+        self.upsample_block1 = UpsampleBlock(2, nb_filters*4, nb_filters*2, 2, upsampling_mode)
+        self.c3 = ResModule(2, nbl[2], nb_filters*4, nb_filters*2, batch_norm=batch_norm)
+        self.upsample_block2 = UpsampleBlock(2, nb_filters*2, nb_filters, 2, upsampling_mode)
+        self.c4 = ConvBlock(2, 1, nb_filters*2, nb_filters, batch_norm=batch_norm)
+        self.px = nn.Conv2d(nb_filters, nb_classes, 1, 1, 0)
+
+    def _emit(self, tape: Tape, x: Act) -> Act:
+        c1 = self.c1._emit(tape, x)
+        c2 = self.c2._emit(tape, tape.pool(c1))
+        bn = self.bn._emit(tape, tape.pool(c2))
+        u2 = self.upsample_block1._emit(tape, bn)
+        u2 = self.c3._emit(tape, [c2, u2])
+        u1 = self.upsample_block2._emit(tape, u2)
+        u1 = self.c4._emit(tape, [c1, u1])
+        return tape.conv(u1, self.px, None, 1.0)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return engine.run(self, x)
+
+
 def init_fcnn_model(model: Union[Type[nn.Module], str],
                     nb_classes: int, **kwargs: [bool, int, List]
                     ) -> Type[nn.Module]:
@@ -153,14 +239,20 @@ def init_fcnn_model(model: Union[Type[nn.Module], str],
         nb_filters = kwargs.get('nb_filters', 25)
         layers = kwargs.get("layers", [1, 3, 3, 1])
         net = dilnet(nb_classes, nb_filters, dropout, batch_norm, upsampling, layers=layers)
-    elif isinstance(model, str) and model in ('SegResNet', 'ResHedNet'):
-        raise NotImplementedError(
-            f"'{model}' (ResBlock-based) is outside the accelerated hot path of atomai_b200; "
-            "implemented models are 'Unet' and 'dilnet'")
+    elif isinstance(model, str) and model == 'SegResNet':
+        nb_filters = kwargs.get('nb_filters', 32)
+        layers = kwargs.get("layers", [2, 2, 2])
+        net = SegResNet(nb_classes, nb_filters, batch_norm, upsampling, layers=layers)
+    elif isinstance(model, str) and model == 'ResHedNet':
+        nb_filters = kwargs.get('nb_filters', 64)
+        layers = kwargs.get("layers", [3, 4, 5])
+        net = ResHedNet(nb_classes, nb_filters, upsampling, layers=layers)
     else:
         raise NotImplementedError(
             "Currently implemented models are 'Unet', 'dilnet', SegResNet', and 'ResHedNet'"
         )
+    if model in ["ResHedNet", "SegResNet"]:
+        meta_state_dict["dropout"] = None          # (atomai/nets/fcnn.py:436-439, quirk kept)
     meta_state_dict["nb_filters"] = nb_filters
     meta_state_dict["layers"] = layers
     return net, meta_state_dict

@@ -190,6 +190,32 @@ def upsample_bwd(dy, dx, bilinear=True) -> None:
                                            1 if bilinear else 0, stream_ptr()))
 
 
+def affine_res_act(a, scale, shift, res, slope, out) -> None:
+    """out = LeakyReLU(a*scale + shift + res) (scale/shift/res optional)."""
+    N, H, W, Cc = a.shape
+    check(lib().atomai_b200_affine_res_act(ptr(a), _ld(a), ptr(scale), ptr(shift), ptr(res),
+                                           _ld(res) if res is not None else 0, float(slope),
+                                           ptr(out), _ld(out), N * H * W, Cc, stream_ptr()))
+
+
+def lrelu_mask_bwd(dy, y, slope, g) -> None:
+    N, H, W, Cc = y.shape
+    check(lib().atomai_b200_lrelu_mask_bwd(ptr(dy), _ld(dy), ptr(y), _ld(y), float(slope), ptr(g),
+                                           _ld(g), N * H * W, Cc, stream_ptr()))
+
+
+def resize_fwd(x, out, factor, bilinear=True) -> None:
+    N, h, w, Cc = x.shape
+    check(lib().atomai_b200_resize_fwd(ptr(x), _ld(x), ptr(out), _ld(out), N, h, w, Cc, int(factor),
+                                       1 if bilinear else 0, stream_ptr()))
+
+
+def resize_bwd(dy, dx, factor, bilinear=True) -> None:
+    N, h, w, Cc = dx.shape
+    check(lib().atomai_b200_resize_bwd(ptr(dy), _ld(dy), ptr(dx), _ld(dx), N, h, w, Cc, int(factor),
+                                       1 if bilinear else 0, stream_ptr()))
+
+
 def transpose(x, y, N, R, Cc) -> None:
     """y[n][c][r] = x[n][r][c] (both contiguous)."""
     assert x.is_contiguous() and y.is_contiguous() and x.numel() == y.numel() == N * R * Cc

@@ -145,6 +145,21 @@ int atomai_b200_upsample2x_fwd(const float* x, int ld_x, float* y, int ld_y, int
                                int C, int bilinear, void* stream);
 int atomai_b200_upsample2x_bwd(const float* dy, int ld_dy, float* dx, int ld_dx, int N, int h,
                                int w, int C, int bilinear, void* stream);
+/* ResBlock tail (atomai/nets/blocks.py:199-214): y = LeakyReLU(a*scale + shift + res) in one
+ * pass; scale/shift (the BatchNorm affine) and res (the residual) may be NULL.  Backward mask:
+ * g = dy * LeakyReLU'(y), read from sign(y) (slope > 0). */
+int atomai_b200_affine_res_act(const float* a, int ld_a, const float* scale, const float* shift,
+                               const float* res, int ld_res, float lrelu, float* y, int ld_y,
+                               int64_t npix, int C, void* stream);
+int atomai_b200_lrelu_mask_bwd(const float* dy, int ld_dy, const float* y, int ld_y, float lrelu,
+                               float* g, int ld_g, int64_t npix, int C, void* stream);
+/* F.interpolate(size = factor * (h, w), mode = bilinear (align_corners=False) | nearest) of the
+ * ResHedNet side outputs (atomai/nets/fcnn.py:292-293) and its adjoint (dx zeroed by the caller,
+ * accumulated with atomics). */
+int atomai_b200_resize_fwd(const float* x, int ld_x, float* y, int ld_y, int N, int h, int w, int C,
+                           int factor, int bilinear, void* stream);
+int atomai_b200_resize_bwd(const float* dy, int ld_dy, float* dx, int ld_dx, int N, int h, int w,
+                           int C, int factor, int bilinear, void* stream);
 /* y[n][c][r] = x[n][r][c]: NHWC <-> NCHW around `x.reshape(-1, C*H*W)` -> nn.Linear
  * (atomai/nets/ed.py:77-79, 284-287, 516-517). */
 int atomai_b200_transpose(const float* x, float* y, int N, int R, int Cc, void* stream);

@@ -77,8 +77,10 @@ def fcnn_case(tag, model, nb_classes, seed, n, h, w, logit_stride=1, **kw):
         opt.step()
         losses.append(l_.item())
     out["adam_losses"] = np.array(losses, np.float64)
-    out["adam_px_weight"] = net.px.weight.detach().numpy().copy()
-    out["adam_c1_weight"] = net.c1.block[0].weight.detach().numpy().copy()
+    last = net.px if hasattr(net, "px") else net.out
+    first = net.c1.block[0] if hasattr(net, "c1") else net.net1.res_module[0].c0
+    out["adam_px_weight"] = last.weight.detach().numpy().copy()
+    out["adam_c1_weight"] = first.weight.detach().numpy().copy()
     if logit_stride > 1:
         out["logits_absmax"] = np.float64(np.abs(out["logits_eval"]).max())
         out["logits_eval"] = gu.sample_flat(out["logits_eval"], logit_stride)
@@ -149,6 +151,12 @@ if __name__ == "__main__":
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "big":
         fcnn_case("unet_default_3c_128", "Unet", 3, 600, 4, 128, 128, logit_stride=5)
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "resnets":
+        fcnn_case("segresnet_default_3c", "SegResNet", 3, 800, 2, 64, 64)
+        fcnn_case("segresnet_nobn_1c", "SegResNet", 1, 810, 2, 32, 32, batch_norm=False, nb_filters=16,
+                  upsampling="nearest")
+        fcnn_case("reshednet_3c", "ResHedNet", 3, 820, 2, 64, 64, nb_filters=16, layers=[2, 2, 2])
         sys.exit(0)
     fcnn_case("unet_default_3c", "Unet", 3, 100, 2, 32, 48)
     fcnn_case("unet_nearest_1c", "Unet", 1, 200, 2, 32, 32, upsampling="nearest", nb_filters=8)

@@ -22,6 +22,12 @@ CASES = {
     "unet_default_3c_128": dict(model="Unet", nb_classes=3, seed=600, n=4, h=128, w=128, cfg={}),
     # BASELINE.json configs[1] geometry: default 3-class Unet on 512x512 images (N = 2)
     "unet_default_3c_512": dict(model="Unet", nb_classes=3, seed=700, n=2, h=512, w=512, cfg={}),
+    # ResBlock networks (atomai/nets/fcnn.py:229-376)
+    "segresnet_default_3c": dict(model="SegResNet", nb_classes=3, seed=800, n=2, h=64, w=64, cfg={}),
+    "segresnet_nobn_1c": dict(model="SegResNet", nb_classes=1, seed=810, n=2, h=32, w=32,
+                              cfg=dict(batch_norm=False, nb_filters=16, upsampling="nearest")),
+    "reshednet_3c": dict(model="ResHedNet", nb_classes=3, seed=820, n=2, h=64, w=64,
+                         cfg=dict(nb_filters=16, layers=[2, 2, 2])),
 }
 
 
@@ -52,7 +58,9 @@ def build_case(name):
 
 
 def oracle_forward(name, sd, cfg, x, training, new_stats=None):
-    fn = nets_ref.unet_forward if CASES[name]["model"] == "Unet" else nets_ref.dilnet_forward
+    fn = {"Unet": nets_ref.unet_forward, "dilnet": nets_ref.dilnet_forward,
+          "SegResNet": nets_ref.segresnet_forward, "ResHedNet": nets_ref.reshednet_forward}[
+              CASES[name]["model"]]
     return fn(x, sd, cfg, training=training, new_stats=new_stats)
 
 

@@ -45,7 +45,27 @@ def test_dilated_unet_and_dilnet_structure():
     net2, meta2 = init_fcnn_model("dilnet", 3)
     assert isinstance(net2, dilnet) and meta2["nb_filters"] == 25
     with pytest.raises(NotImplementedError):
-        init_fcnn_model("SegResNet", 3)
+        init_fcnn_model("SegNet", 3)
+
+
+def test_resnet_structure_and_state_dict_keys():
+    """ResBlock networks: module tree / checkpoint keys of atomai/nets/fcnn.py:229-376."""
+    net, meta = init_fcnn_model("SegResNet", 3)
+    assert meta["nb_filters"] == 32 and meta["layers"] == [2, 2, 2] and meta["dropout"] is None
+    keys = set(net.state_dict())
+    for k in ("c1.block.0.weight", "c2.res_module.0.c0.weight", "c2.res_module.1.bn2.running_var",
+              "bn.res_module.0.c1.bias", "upsample_block1.conv.weight", "c3.res_module.0.c0.weight",
+              "c4.block.2.weight", "px.bias"):
+        assert k in keys, k
+    assert net.c3.res_module[0].c0.weight.shape == (64, 128, 1, 1)
+    net2, meta2 = init_fcnn_model("ResHedNet", 1)
+    assert meta2["nb_filters"] == 64 and meta2["layers"] == [3, 4, 5]
+    keys2 = set(net2.state_dict())
+    for k in ("net1.res_module.2.c2.weight", "net2.1.res_module.3.bn1.weight",
+              "net3.1.res_module.4.c0.bias", "net1score.0.weight", "net3score.1.running_mean",
+              "out.weight"):
+        assert k in keys2, k
+    assert net2.out.weight.shape == (1, 3, 1, 1)
 
 
 def test_constructor_argument_errors_match_reference():
