@@ -75,6 +75,9 @@ int ab_make_srcset(const ab_conv_t* d, SrcSet* out) {
                a.C, a.ld);
       AB_CHECK((a.scale == nullptr) == (a.shift == nullptr), "conv: source %d scale/shift mismatch",
                i);
+      AB_CHECK(a.pool >= 0 && a.pool <= 3, "conv: source %d transform code %d", i, a.pool);
+      AB_CHECK(a.pool < 2 || (d->H % 2 == 0 && d->W % 2 == 0),
+               "conv: upsample-on-load needs even H, W (got %d x %d)", d->H, d->W);
       s.ptr = a.ptr; s.scale = a.scale; s.shift = a.shift; s.C = a.C; s.ld = a.ld; s.pool = a.pool;
       out->Ctot += a.C;
     } else {

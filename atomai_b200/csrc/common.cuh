@@ -303,6 +303,49 @@ struct SrcSet {
   int Ctot;
 };
 
+// ---- 2x upsampling on load (F.interpolate(scale_factor=2, mode), atomai/nets/blocks.py:130-131,
+// fused into the consumer convolution's loader: source code pool = AB_SRC_UP_BILINEAR / _NEAREST,
+// the source tensor is (H/2, W/2)).  For output coordinate o of an axis with n_lo low-res samples:
+// the two contributing samples and the weight of the second (align_corners = False:
+// src = (o + 0.5)/2 - 0.5 clamped at 0 -> even o = 2i: 0.25 x[i-1] + 0.75 x[i], odd: 0.75 x[i] +
+// 0.25 x[i+1], edges clamped).
+#define AB_SRC_POOL 1
+#define AB_SRC_UP_BILINEAR 2
+#define AB_SRC_UP_NEAREST 3
+__device__ __forceinline__ void up2_coord(int o, int n_lo, bool bilinear, int& i0, int& i1,
+                                          float& l1) {
+  const int i = o >> 1;
+  if (!bilinear) { i0 = i1 = i; l1 = 0.f; return; }
+  if (o & 1) { i0 = i; i1 = min(i + 1, n_lo - 1); l1 = 0.25f; }
+  else { i0 = max(i - 1, 0); i1 = i; l1 = 0.75f; }     // (o = 0: i0 = i1 = 0, any weight gives x[0])
+}
+__device__ __forceinline__ float lerp2(float v00, float v01, float v10, float v11, float lh,
+                                       float lw) {
+  // same association as ATen's upsample_bilinear2d kernel
+  return (1.f - lh) * ((1.f - lw) * v00 + lw * v01) + lh * ((1.f - lw) * v10 + lw * v11);
+}
+__device__ __forceinline__ float4 lerp2_4(float4 a, float4 b, float4 c, float4 d, float lh, float lw) {
+  return make_float4(lerp2(a.x, b.x, c.x, d.x, lh, lw), lerp2(a.y, b.y, c.y, d.y, lh, lw),
+                     lerp2(a.z, b.z, c.z, d.z, lh, lw), lerp2(a.w, b.w, c.w, d.w, lh, lw));
+}
+// upsampled value (before the affine) of 4 channels at hi-res pixel (n, h, w) of an H x W grid
+__device__ __forceinline__ float4 load_up4(const float* __restrict__ ptr_c, int ld, int mode, int n,
+                                           int h, int w, int H, int W) {
+  const int Hl = H >> 1, Wl = W >> 1;
+  int h0, h1, w0, w1;
+  float lh, lw;
+  up2_coord(h, Hl, mode == AB_SRC_UP_BILINEAR, h0, h1, lh);
+  up2_coord(w, Wl, mode == AB_SRC_UP_BILINEAR, w0, w1, lw);
+  const float* r0 = ptr_c + (size_t)(n * Hl + h0) * Wl * ld;
+  const float* r1 = ptr_c + (size_t)(n * Hl + h1) * Wl * ld;
+  const float4 a = __ldg(reinterpret_cast<const float4*>(r0 + (size_t)w0 * ld));
+  if (mode != AB_SRC_UP_BILINEAR) return a;
+  const float4 b = __ldg(reinterpret_cast<const float4*>(r0 + (size_t)w1 * ld));
+  const float4 c = __ldg(reinterpret_cast<const float4*>(r1 + (size_t)w0 * ld));
+  const float4 d = __ldg(reinterpret_cast<const float4*>(r1 + (size_t)w1 * ld));
+  return lerp2_4(a, b, c, d, lh, lw);
+}
+
 // 4 consecutive channels [c, c+4) of the logical (post-affine, post-pool, zero padded)
 // input at pixel (n, h, w) of an H x W grid.  c must be a multiple of 4 and every source's
 // C a multiple of 4 on this vector path.
@@ -320,7 +363,13 @@ __device__ __forceinline__ float4 load_src4(const SrcSet& S, int n, int h, int w
     sc = __ldg(reinterpret_cast<const float4*>(s->scale + c));
     sh = __ldg(reinterpret_cast<const float4*>(s->shift + c));
   }
-  if (!s->pool) {
+  if (s->pool >= AB_SRC_UP_BILINEAR) {
+    const float4 v = load_up4(s->ptr + c, s->ld, s->pool, n, h, w, H, W);
+    r.x = fmaf(v.x, sc.x, sh.x);
+    r.y = fmaf(v.y, sc.y, sh.y);
+    r.z = fmaf(v.z, sc.z, sh.z);
+    r.w = fmaf(v.w, sc.w, sh.w);
+  } else if (!s->pool) {
     const float4 v = __ldg(
         reinterpret_cast<const float4*>(s->ptr + ((size_t)(n * H + h) * W + w) * s->ld + c));
     r.x = fmaf(v.x, sc.x, sh.x);
@@ -359,6 +408,18 @@ __device__ __forceinline__ float load_src1(const SrcSet& S, int n, int h, int w,
   if (s->scale) {
     sc = __ldg(s->scale + c);
     sh = __ldg(s->shift + c);
+  }
+  if (s->pool >= AB_SRC_UP_BILINEAR) {
+    const int Hl = H >> 1, Wl = W >> 1;
+    int h0, h1, w0, w1;
+    float lh, lw;
+    up2_coord(h, Hl, s->pool == AB_SRC_UP_BILINEAR, h0, h1, lh);
+    up2_coord(w, Wl, s->pool == AB_SRC_UP_BILINEAR, w0, w1, lw);
+    const float* r0 = s->ptr + (size_t)(n * Hl + h0) * Wl * s->ld + c;
+    const float* r1 = s->ptr + (size_t)(n * Hl + h1) * Wl * s->ld + c;
+    const float v = lerp2(__ldg(r0 + (size_t)w0 * s->ld), __ldg(r0 + (size_t)w1 * s->ld),
+                          __ldg(r1 + (size_t)w0 * s->ld), __ldg(r1 + (size_t)w1 * s->ld), lh, lw);
+    return fmaf(v, sc, sh);
   }
   if (!s->pool) {
     return fmaf(__ldg(s->ptr + ((size_t)(n * H + h) * W + w) * s->ld + c), sc, sh);

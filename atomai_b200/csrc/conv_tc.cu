@@ -63,6 +63,7 @@ struct ConvTcParams {
   float* out;
   int ld_out;
   int out_nchw;
+  int64_t nchw_stride; // out_nchw: elements between channel planes (H*W, or the caller's row pitch)
   double* stats;
   int tiles_h, tiles_w, num_tiles;
   int KC;            // channels per k-chunk (8, 16 or 32)
@@ -297,7 +298,8 @@ __device__ __forceinline__ void loader_loop(const ConvTcParams& p, SharedCtl* ct
       c -= p.S.s[0].C;
     }
     const uint32_t ld = sp->ld;
-    const bool pool = sp->pool != 0;
+    const bool pool = sp->pool != 0;            // any on-load resampling (2x2 max or 2x upsampling)
+    const int up_mode = sp->pool >= AB_SRC_UP_BILINEAR ? sp->pool : 0;
     const bool has_aff = sp->scale != nullptr;
     float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
     if (has_aff) {
@@ -368,6 +370,19 @@ __device__ __forceinline__ void loader_loop(const ConvTcParams& p, SharedCtl* ct
         v[u].y = ok ? fmaf(v[u].y, sc.y, sh.y) : 0.f;
         v[u].z = ok ? fmaf(v[u].z, sc.z, sh.z) : 0.f;
         v[u].w = ok ? fmaf(v[u].w, sc.w, sh.w) : 0.f;
+      }
+    } else if (up_mode) {
+      // 2x upsampling on load (the decoder's second source, atomai/nets/blocks.py:130-131 +
+      // fcnn.py:131-138): the (H/2, W/2) tensor is interpolated while the halo tile is staged,
+      // so the 4x larger upsampled tensor is never written or re-read
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int gh = h_org + (int)(hw[u] >> 16), gw = w_org + (int)(hw[u] & 0xFFFFu);
+        const bool ok = (unsigned)gh < (unsigned)H && (unsigned)gw < (unsigned)W;
+        const int ghc = min(max(gh, 0), H - 1), gwc = min(max(gw, 0), W - 1);
+        const float4 a = load_up4(base, (int)ld, up_mode, n, ghc, gwc, H, W);
+        v[u] = make_float4(ok ? fmaf(a.x, sc.x, sh.x) : 0.f, ok ? fmaf(a.y, sc.y, sh.y) : 0.f,
+                           ok ? fmaf(a.z, sc.z, sh.z) : 0.f, ok ? fmaf(a.w, sc.w, sh.w) : 0.f);
       }
     } else {
       const int H2 = 2 * H, W2 = 2 * W;
@@ -527,7 +542,7 @@ __device__ __forceinline__ void epilogue_loop(const ConvTcParams& p, SharedCtl* 
             o[2] = make_float4(v[8], v[9], v[10], v[11]);
             o[3] = make_float4(v[12], v[13], v[14], v[15]);
           } else {
-            const size_t hw = (size_t)p.H * p.W;
+            const size_t hw = (size_t)p.nchw_stride;
             float* o = p.out + ((size_t)n * p.Cout + c0) * hw + (size_t)gh * p.W + gw;
 #pragma unroll
             for (int i = 0; i < 16; ++i) o[i * hw] = v[i];
@@ -999,9 +1014,12 @@ int ab_conv_tc_fwd(const ab_conv_t* d, const float* wblob, const float* bias, fl
   ConvTcParams p;
   int smem_bytes = 0;
   if (conv_tc_plan(d, &p, &smem_bytes)) return 1;
-  AB_CHECK(((uintptr_t)wblob & 15) == 0 && ((uintptr_t)y & 15) == 0 && ld_y % 4 == 0,
+  AB_CHECK(((uintptr_t)wblob & 15) == 0 && ((uintptr_t)y & 15) == 0 && (d->out_nchw || ld_y % 4 == 0),
            "conv_tc: unaligned weight blob / output");
   p.wblob = wblob; p.bias = bias; p.out = y; p.ld_out = ld_y; p.stats = stats;
+  // NCHW output: ld_y < 0 gives the pitch between channel planes (the Gram kernel writes
+  // K[row = channel][col = pixel] with the caller's leading dimension); default H*W
+  p.nchw_stride = (d->out_nchw && ld_y < 0) ? -(int64_t)ld_y : (int64_t)d->H * d->W;
   static unsigned char optin[64];
   if (ab_optin_smem(reinterpret_cast<const void*>(conv_tc_kernel), 226 * 1024, optin)) return 1;
   const int sms = ab_num_sms();

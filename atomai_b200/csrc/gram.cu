@@ -9,6 +9,7 @@
 // tile kernel below.
 // RBF / Matern-2.5 / outputscale follow gpytorch's public kernel definitions as configured at
 // atomai/nets/gp.py:41-46 and :100-111 (gpytorch itself is not vendored by the reference).
+#include <cstdlib>
 #include "common.cuh"
 
 
@@ -22,7 +23,7 @@ int ab_conv_tc_fwd(const ab_conv_t* d, const float* wblob, const float* bias, fl
 namespace {
 
 constexpr int TM = 64, TN = 64, TK = 16, GT = 256;
-constexpr int kColBlock = 256;      // output channels (columns of K) per tcgen05 launch
+constexpr int kColBlock = 256;      // max output channels (rows of K) per tcgen05 launch
 
 // one warp per row: out[row] = [x*inv_ls * fac, (side 0: |.|^2, 1) | (side 1: 1, |.|^2), 0-pad]
 __global__ void augment_kernel(const float* __restrict__ x, const float* __restrict__ inv_ls,
@@ -148,24 +149,32 @@ extern "C" int atomai_b200_gram(const float* x1, const float* x2, const float* i
   AB_LAUNCH_CHECK();
   const int act = kind == 0 ? AB_ACT_RBF : AB_ACT_MATERN25;
   int n1m = 0, n2m = 0;
-  if (math != AB_MATH_FP32 && (ldk % 4) == 0 && ((uintptr_t)K & 15) == 0) {
-    n1m = n1 & ~7;
-    n2m = n2 & ~15;
+  if (math != AB_MATH_FP32 && ldk < (1ll << 31)) {
+    n1m = n1 & ~15;
+    n2m = n2 & ~7;
   }
   if (n1m > 0 && n2m > 0) {
-    // tensor path: K[0:n1m, c0:c1] = act(a'[0:n1m] . b'[c0:c1]^T), one launch per column block
+    // tensor path: the rows of x2 are the pixels of a (1, n2m/8, 8, K') image, row blocks of <= 256
+    // rows of x1 the output channels, stored "NCHW" with the channel pitch = ldk: lane l of an
+    // epilogue warp holds K[r][c + l], so every store instruction writes 128 contiguous bytes of a
+    // row of K (the NHWC form wrote 16 B to 32 different rows per instruction: 1.1 TB/s, round 2)
     ab_conv_t cd;
     memset(&cd, 0, sizeof(cd));
-    cd.N = 1; cd.H = n1m / 8; cd.W = 8;
+    cd.N = 1; cd.H = n2m / 8; cd.W = 8;
     cd.ks_h = cd.ks_w = 1; cd.dil = 1; cd.nsrc = 1;
-    cd.src[0].ptr = a; cd.src[0].C = Kp; cd.src[0].ld = Kp;
-    cd.lrelu = outputscale; cd.math = math; cd.act = act;
+    cd.src[0].ptr = b; cd.src[0].C = Kp; cd.src[0].ld = Kp;
+    cd.lrelu = outputscale; cd.math = math; cd.act = act; cd.out_nchw = 1;
     const int x3 = math == AB_MATH_TF32X3;
-    for (int c0 = 0; c0 < n2m; c0 += kColBlock) {
-      const int cb = (n2m - c0) < kColBlock ? (n2m - c0) : kColBlock;
-      cd.Cout = cb;
-      if (ab_pack_weights_tc(b + (int64_t)c0 * Kp, cb, Kp, 1, 1, AB_WMODE_FWD, x3, blob, st)) return 1;
-      if (ab_conv_tc_fwd(&cd, blob, nullptr, K + c0, (int)ldk, nullptr, st)) return 1;
+    // rows of K per launch (measured, 50k x 50k x 128: 256 rows 1.18-1.24 TB/s, 128 rows 0.77-0.95,
+    // 64 rows 0.51-0.56 — wide N amortises the A-operand reads and the per-tile handshakes)
+    int blk = kColBlock;
+    if (const char* e = getenv("ATOMAI_B200_GRAM_BLOCK")) blk = atoi(e);
+    if (blk < 16 || blk > kColBlock || blk % 16 != 0) blk = kColBlock;
+    for (int r0 = 0; r0 < n1m; r0 += blk) {
+      const int rb = (n1m - r0) < blk ? (n1m - r0) : blk;
+      cd.Cout = rb;
+      if (ab_pack_weights_tc(a + (int64_t)r0 * Kp, rb, Kp, 1, 1, AB_WMODE_FWD, x3, blob, st)) return 1;
+      if (ab_conv_tc_fwd(&cd, blob, nullptr, K + (int64_t)r0 * ldk, -(int)ldk, nullptr, st)) return 1;
     }
   }
   // exact FFMA tiles: everything (fp32 math) or the right / bottom remainders of the tensor path

@@ -25,6 +25,7 @@
 // them); warps 0-3 also flush the accumulators at the end.
 //
 // Replaces autograd's cuDNN bwd-filter behind loss.backward(), atomai/trainers/trainer.py:206.
+#include <cstdlib>
 #include "common.cuh"
 
 namespace {
@@ -61,6 +62,8 @@ struct WgradTcParams {
                          // pairs (x_hi, dy_hi), (x_lo, dy_hi), (x_hi, dy_lo)
   int dy_bytes;          // bytes of one dy tile inside a stage
   int cob;               // output channels per CTA (128, or 64 when two stages would not fit)
+  int interleave;        // tile order (see the kernel)
+  int legacy_loader;     // bring-up only (ATOMAI_B200_WGRAD_LOADER=0): the thread = pixel loaders
 };
 
 struct __align__(8) Ctl {
@@ -102,7 +105,7 @@ constexpr int kJB = 8;                        // 16 B channel pieces per pixel p
 // with the row's swizzle phase).
 __device__ __forceinline__ void wgrad_loader(const WgradTcParams& p, Ctl* ctl, uint32_t base,
                                              const float4* s_aff, int grp, int gt, int t_begin,
-                                             int t_end, int co0, int ci0, int PD, int PX) {
+                                             int t_end, int ts, int co0, int ci0, int PD, int PX) {
   const int lane = threadIdx.x & 31;
   const bool stacked = p.taps_w > 1;
   const int H = p.H, W = p.W, HP = p.HP;
@@ -124,7 +127,7 @@ __device__ __forceinline__ void wgrad_loader(const WgradTcParams& p, Ctl* ctl, u
   uint32_t st = grp % S, ph = ((grp / S) & 1) ^ 1;     // ring slot / empty-phase of this tile
   const bool x3 = p.x3 != 0;
   const uint32_t xlo_off = p.x_bytes, dlo_off = p.dy_bytes;    // hi tile -> lo tile (x3)
-  for (int tile = t_begin + grp; tile < t_end; tile += n_groups) {
+  for (int tile = t_begin + grp * ts; tile < t_end; tile += n_groups * ts) {
     const uint32_t x0 = base + st * p.stage_bytes;
     const int n = (int)fdiv(tile, tpi, mulTpi);
     const int rem = tile - n * tpi;
@@ -243,7 +246,7 @@ __device__ __forceinline__ void wgrad_loader(const WgradTcParams& p, Ctl* ctl, u
 template <int ND>
 __device__ __forceinline__ void wgrad_loader_fast(const WgradTcParams& p, Ctl* ctl, uint32_t base,
                                                   const float4* s_aff, int grp, int gt, int t_begin,
-                                                  int t_end, int co0, int ci0, int PD, int PX) {
+                                                  int t_end, int ts, int co0, int ci0, int PD, int PX) {
   constexpr int NX = 8;
   const int lane = threadIdx.x & 31;
   const int H = p.H, W = p.W, HP = p.HP;
@@ -265,7 +268,7 @@ __device__ __forceinline__ void wgrad_loader_fast(const WgradTcParams& p, Ctl* c
   const uint32_t hh1 = has_q1 ? fdiv(q1, p.TWp, mulT) : 0u, ww1 = has_q1 ? q1 - hh1 * p.TWp : 0u;
   const uint32_t sw0 = (uint32_t)(gt & 3) << 5, sw1 = (uint32_t)(q1 & 3) << 5;
   uint32_t st = grp % S, ph = ((grp / S) & 1) ^ 1;
-  for (int tile = t_begin + grp; tile < t_end; tile += n_groups) {
+  for (int tile = t_begin + grp * ts; tile < t_end; tile += n_groups * ts) {
     const uint32_t x0 = base + st * p.stage_bytes;
     const int n = (int)fdiv(tile, tpi, mulTpi);
     const int rem = tile - n * tpi;
@@ -352,6 +355,215 @@ __device__ __forceinline__ void wgrad_loader_fast(const WgradTcParams& p, Ctl* c
   }
 }
 
+// Element-mapped loader (round 2): consecutive lanes own consecutive 16-byte channel pieces of the
+// SAME pixel (PX / PD pieces per pixel, powers of two), so a warp's LDG.128 reads whole pixels
+// (coalesced 64-512 B runs) and its ST.SHARED.128 fills whole 128-byte swizzle rows (conflict
+// free) — the thread = pixel mapping of the loaders above touches 32 different lines per
+// instruction and measured 4200 warp instructions per tile (ncu, c6.0).  A thread's piece index
+// and therefore its source tensor, its BatchNorm scale/shift (registers, not shared memory) and
+// its swizzle phase are loop constants; per element there is one address multiply-add, the
+// affine, the TF32 rounding add and one store.  Pooled sources (2x2 max of the affine'd window)
+// take four loads per element in the same mapping.  XB = elements in flight per thread.
+template <int XB>
+__device__ __forceinline__ void wgrad_loader_elem(const WgradTcParams& p, Ctl* ctl, uint32_t base,
+                                                  int grp, int gt, int t_begin, int t_end, int ts,
+                                                  int co0, int ci0, int PD, int PX) {
+  const int lane = threadIdx.x & 31;
+  const bool stacked = p.taps_w > 1;
+  const int H = p.H, W = p.W, HP = p.HP;
+  const int tpi = p.tiles_w * p.tiles_h;
+  const uint32_t mulTpi = fdiv_mul(tpi), mulTw = fdiv_mul(p.tiles_w), mulT = fdiv_mul(p.TWp);
+  const uint32_t S = p.n_stages;
+  const int n_groups = S >= (uint32_t)kGroups ? kGroups : 2;
+  if (grp >= n_groups) return;
+  const bool x3 = p.x3 != 0;
+  const uint32_t xlo_off = p.x_bytes, dlo_off = p.dy_bytes;
+  // ---- x operand: piece j of halo pixels q0, q0 + QS, ...
+  const int j = gt & (PX - 1);
+  const int lx = 31 - __clz(PX);                       // log2(PX)
+  const int QS = kGroupThreads >> lx, q0 = gt >> lx;
+  const int ux_total = (HP + QS - 1 - q0) / QS;          // this thread's halo pixels: q0 + u*QS < HP
+  int cx = ci0 + j * 4;
+  const SrcDev* sp = &p.S.s[0];
+  if (p.S.nsrc > 1 && cx >= p.S.s[0].C) { sp = &p.S.s[1]; cx -= p.S.s[0].C; }
+  const bool has_aff = sp->scale != nullptr, pool = sp->pool != 0;
+  const int up_mode = sp->pool >= AB_SRC_UP_BILINEAR ? sp->pool : 0;
+  float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (has_aff) {
+    sc = __ldg(reinterpret_cast<const float4*>(sp->scale + cx));
+    sh = __ldg(reinterpret_cast<const float4*>(sp->shift + cx));
+  }
+  const float* xsrc = sp->ptr + cx;
+  const uint32_t xld = sp->ld;
+  // (q & 3) is the same for all of a thread's pixels: QS is a multiple of 4
+  const uint32_t x_dst0 = (uint32_t)q0 * 128 + (stacked ? 0u : (uint32_t)(j >> 3) * p.x_chunk) +
+                          (((uint32_t)(j & 7) << 4) ^ ((uint32_t)(q0 & 3) << 5));
+  const uint32_t x_step = (uint32_t)QS * 128;
+  // ---- dy operand: piece jd of tile pixels pd0, pd0 + QD, ...
+  const int jd = gt & (PD - 1);
+  const int ld_ = 31 - __clz(PD);
+  const int QD = kGroupThreads >> ld_, pd0 = gt >> ld_;
+  const uint32_t d_rel = p.x_bytes * (p.x3 ? 2 : 1) + (p.fs ? p.dpad * 1024 : 0);
+  const uint32_t d_dst0 = d_rel + (uint32_t)pd0 * 128 + (uint32_t)(jd >> 3) * kChunk +
+                          (((uint32_t)(jd & 7) << 4) ^ ((uint32_t)(pd0 & 3) << 5));
+  const uint32_t d_step = (uint32_t)QD * 128;
+  const float* dsrc = p.dy + co0 + jd * 4;
+  uint32_t st = grp % S, ph = ((grp / S) & 1) ^ 1;
+  for (int tile = t_begin + grp * ts; tile < t_end; tile += n_groups * ts) {
+    const uint32_t x0 = base + st * p.stage_bytes;
+    const int n = (int)fdiv(tile, tpi, mulTpi);
+    const int rem = tile - n * tpi;
+    const int th_i = (int)fdiv(rem, p.tiles_w, mulTw);
+    const int tw_i = rem - th_i * p.tiles_w;
+    const int h0 = th_i * kTileH, w0 = tw_i * kTileW;
+    const int h_org = h0 - p.dil * (p.taps_h >> 1), w_org = w0 - p.dil * (p.taps_w >> 1);
+    const bool interior = h_org >= 0 && w_org >= 0 && h_org + p.THp <= H && w_org + p.TWp <= W;
+    bool waited = false;
+    // ---------------- x halo elements, XB at a time
+    for (int ub = 0; ub < ux_total; ub += XB) {
+      float4 v[XB];
+      uint32_t okm = 0;
+      if (!pool) {
+        const float* tb = xsrc + ((size_t)(n * H + h_org) * W + w_org) * xld;   // interior tiles only
+#pragma unroll
+        for (int k = 0; k < XB; ++k) {
+          const int u = ub + k;
+          if (u < ux_total) {
+            const uint32_t q = (uint32_t)(q0 + u * QS);
+            const uint32_t hh = fdiv(q, p.TWp, mulT), ww = q - hh * p.TWp;
+            if (interior) {
+              v[k] = __ldg(reinterpret_cast<const float4*>(tb + (size_t)(hh * W + ww) * xld));
+              okm |= 1u << k;
+            } else {
+              const int gh = h_org + (int)hh, gw = w_org + (int)ww;
+              const bool ok = (unsigned)gh < (unsigned)H && (unsigned)gw < (unsigned)W;
+              const int ghc = min(max(gh, 0), H - 1), gwc = min(max(gw, 0), W - 1);
+              v[k] = __ldg(reinterpret_cast<const float4*>(xsrc + ((size_t)(n * H + ghc) * W + gwc) * xld));
+              okm |= (ok ? 1u : 0u) << k;
+            }
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < XB; ++k) {
+          const bool ok = (okm >> k) & 1u;
+          v[k].x = ok ? fmaf(v[k].x, sc.x, sh.x) : 0.f;
+          v[k].y = ok ? fmaf(v[k].y, sc.y, sh.y) : 0.f;
+          v[k].z = ok ? fmaf(v[k].z, sc.z, sh.z) : 0.f;
+          v[k].w = ok ? fmaf(v[k].w, sc.w, sh.w) : 0.f;
+        }
+      } else if (up_mode) {
+        // 2x upsampling on load: this piece belongs to the decoder's (H/2, W/2) source
+#pragma unroll
+        for (int k = 0; k < XB; ++k) {
+          const int u = ub + k;
+          v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (u < ux_total) {
+            const uint32_t q = (uint32_t)(q0 + u * QS);
+            const uint32_t hh = fdiv(q, p.TWp, mulT), ww = q - hh * p.TWp;
+            const int gh = h_org + (int)hh, gw = w_org + (int)ww;
+            const bool ok = (unsigned)gh < (unsigned)H && (unsigned)gw < (unsigned)W;
+            const float4 a = load_up4(xsrc, (int)xld, up_mode, n, min(max(gh, 0), H - 1),
+                                      min(max(gw, 0), W - 1), H, W);
+            if (ok)
+              v[k] = make_float4(fmaf(a.x, sc.x, sh.x), fmaf(a.y, sc.y, sh.y), fmaf(a.z, sc.z, sh.z),
+                                 fmaf(a.w, sc.w, sh.w));
+            okm |= 1u << k;
+          }
+        }
+      } else {
+        const int H2 = 2 * H, W2 = 2 * W;
+        const size_t rs = (size_t)W2 * xld;
+#pragma unroll
+        for (int k = 0; k < XB; ++k) {
+          const int u = ub + k;
+          v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (u < ux_total) {
+            const uint32_t q = (uint32_t)(q0 + u * QS);
+            const uint32_t hh = fdiv(q, p.TWp, mulT), ww = q - hh * p.TWp;
+            const int gh = h_org + (int)hh, gw = w_org + (int)ww;
+            const bool ok = (unsigned)gh < (unsigned)H && (unsigned)gw < (unsigned)W;
+            const int ghc = min(max(gh, 0), H - 1), gwc = min(max(gw, 0), W - 1);
+            const float* q0p = xsrc + ((size_t)(n * H2 + 2 * ghc) * W2 + 2 * gwc) * xld;
+            const float4 a0 = __ldg(reinterpret_cast<const float4*>(q0p));
+            const float4 a1 = __ldg(reinterpret_cast<const float4*>(q0p + xld));
+            const float4 a2 = __ldg(reinterpret_cast<const float4*>(q0p + rs));
+            const float4 a3 = __ldg(reinterpret_cast<const float4*>(q0p + rs + xld));
+            if (ok) {
+              v[k].x = fmaxf(fmaxf(fmaf(a0.x, sc.x, sh.x), fmaf(a1.x, sc.x, sh.x)),
+                             fmaxf(fmaf(a2.x, sc.x, sh.x), fmaf(a3.x, sc.x, sh.x)));
+              v[k].y = fmaxf(fmaxf(fmaf(a0.y, sc.y, sh.y), fmaf(a1.y, sc.y, sh.y)),
+                             fmaxf(fmaf(a2.y, sc.y, sh.y), fmaf(a3.y, sc.y, sh.y)));
+              v[k].z = fmaxf(fmaxf(fmaf(a0.z, sc.z, sh.z), fmaf(a1.z, sc.z, sh.z)),
+                             fmaxf(fmaf(a2.z, sc.z, sh.z), fmaf(a3.z, sc.z, sh.z)));
+              v[k].w = fmaxf(fmaxf(fmaf(a0.w, sc.w, sh.w), fmaf(a1.w, sc.w, sh.w)),
+                             fmaxf(fmaf(a2.w, sc.w, sh.w), fmaf(a3.w, sc.w, sh.w)));
+            }
+            okm |= 1u << k;
+          }
+        }
+      }
+      if (!waited) {
+        mbar_wait(smem_u32(&ctl->empty[st]), ph);
+        waited = true;
+      }
+#pragma unroll
+      for (int k = 0; k < XB; ++k) {
+        const int u = ub + k;
+        if (u < ux_total) {
+          const uint32_t dst = x0 + x_dst0 + (uint32_t)u * x_step;
+          sts128u(dst, tf32b(v[k].x), tf32b(v[k].y), tf32b(v[k].z), tf32b(v[k].w));
+          if (x3) {
+            const float4 l = part4(v[k], true);
+            sts128u(dst + xlo_off, tf32b(l.x), tf32b(l.y), tf32b(l.z), tf32b(l.w));
+          }
+        }
+      }
+    }
+    // ---------------- dy elements (PD per thread), 8 at a time
+    {
+      const size_t img = (size_t)n * H;
+      for (int ub = 0; ub < PD; ub += 8) {
+        float4 v[8];
+        uint32_t okm = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int u = ub + k;
+          if (u < PD) {
+            const int pd = pd0 + u * QD;
+            const int gh = h0 + (pd >> 3), gw = w0 + (pd & 7);
+            const bool ok = gh < H && gw < W;
+            v[k] = __ldg(reinterpret_cast<const float4*>(
+                dsrc + ((img + min(gh, H - 1)) * W + min(gw, W - 1)) * p.ld_dy));
+            okm |= (ok ? 1u : 0u) << k;
+          }
+        }
+        if (!waited) {
+          mbar_wait(smem_u32(&ctl->empty[st]), ph);
+          waited = true;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int u = ub + k;
+          if (u < PD) {
+            const uint32_t msk = ((okm >> k) & 1u) ? 0xFFFFFFFFu : 0u;
+            const uint32_t dst = x0 + d_dst0 + (uint32_t)u * d_step;
+            sts128u(dst, tf32b(v[k].x) & msk, tf32b(v[k].y) & msk, tf32b(v[k].z) & msk, tf32b(v[k].w) & msk);
+            if (x3) {
+              const float4 l = part4(v[k], true);
+              sts128u(dst + dlo_off, tf32b(l.x) & msk, tf32b(l.y) & msk, tf32b(l.z) & msk, tf32b(l.w) & msk);
+            }
+          }
+        }
+      }
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(smem_u32(&ctl->full[st]));
+    st += n_groups;
+    while (st >= S) { st -= S; ph ^= 1; }
+  }
+}
+
 __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const WgradTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   Ctl* ctl = reinterpret_cast<Ctl*>(smem);
@@ -366,8 +578,13 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const WgradTcPara
   const int cb = (blockIdx.x / p.n_cc) % p.co_blocks;
   const int r = blockIdx.x / (p.n_cc * p.co_blocks);
   const int per = (p.num_tiles + p.ranges - 1) / p.ranges;
-  const int t_begin = r * per;
-  const int t_end = min(p.num_tiles, t_begin + per);
+  // interleaved (default): CTA r takes tiles r, r + ranges, ...: at any moment the CTAs work on
+  // neighbouring tiles, so their 8-pixel-wide column segments complete DRAM pages and share halo
+  // columns in L2; contiguous ranges (ATOMAI_B200_WGRAD_ORDER=0) spread 148 CTAs over 148 far-apart
+  // image regions
+  const int ts = p.interleave ? p.ranges : 1;
+  const int t_begin = p.interleave ? r : r * per;
+  const int t_end = p.interleave ? p.num_tiles : min(p.num_tiles, t_begin + per);
   const int co0 = cb * p.cob;
   const int co_n = min(p.cob, p.Cout - co0);        // valid output channels in this block
   const int ci0 = cc * p.cib;
@@ -415,12 +632,21 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const WgradTcPara
     const int grp = warp >= kFirstLoadWarp ? (warp - kFirstLoadWarp) >> 2 : 2;
     const int gt = threadIdx.x & (kGroupThreads - 1);   // warps 0-3, 8-11, 12-15 -> 0..127
     const bool pooled = p.S.s[0].pool || (p.S.nsrc > 1 && p.S.s[1].pool);
-    if (!pooled && p.HP <= 2 * kGroupThreads && PX <= 8 && PD <= 16) {
-      if (PD <= 4) wgrad_loader_fast<4>(p, ctl, base, s_aff, grp, gt, t_begin, t_end, co0, ci0, PD, PX);
-      else if (PD <= 8) wgrad_loader_fast<8>(p, ctl, base, s_aff, grp, gt, t_begin, t_end, co0, ci0, PD, PX);
-      else wgrad_loader_fast<16>(p, ctl, base, s_aff, grp, gt, t_begin, t_end, co0, ci0, PD, PX);
+    const bool pow2 = PX > 0 && PD > 0 && (PX & (PX - 1)) == 0 && (PD & (PD - 1)) == 0 && PX <= 32 &&
+                      PD <= 32;
+    if (pow2 && !p.legacy_loader) {
+      // elements per thread per tile: pooled sources keep 4 loads per element in flight
+      const int ux = (p.HP * PX + kGroupThreads - 1) / kGroupThreads;
+      if (pooled) wgrad_loader_elem<4>(p, ctl, base, grp, gt, t_begin, t_end, ts, co0, ci0, PD, PX);
+      else if (ux <= 8) wgrad_loader_elem<8>(p, ctl, base, grp, gt, t_begin, t_end, ts, co0, ci0, PD, PX);
+      else if (ux <= 12) wgrad_loader_elem<12>(p, ctl, base, grp, gt, t_begin, t_end, ts, co0, ci0, PD, PX);
+      else wgrad_loader_elem<16>(p, ctl, base, grp, gt, t_begin, t_end, ts, co0, ci0, PD, PX);
+    } else if (!pooled && p.HP <= 2 * kGroupThreads && PX <= 8 && PD <= 16) {
+      if (PD <= 4) wgrad_loader_fast<4>(p, ctl, base, s_aff, grp, gt, t_begin, t_end, ts, co0, ci0, PD, PX);
+      else if (PD <= 8) wgrad_loader_fast<8>(p, ctl, base, s_aff, grp, gt, t_begin, t_end, ts, co0, ci0, PD, PX);
+      else wgrad_loader_fast<16>(p, ctl, base, s_aff, grp, gt, t_begin, t_end, ts, co0, ci0, PD, PX);
     } else {
-      wgrad_loader(p, ctl, base, s_aff, grp, gt, t_begin, t_end, co0, ci0, PD, PX);
+      wgrad_loader(p, ctl, base, s_aff, grp, gt, t_begin, t_end, ts, co0, ci0, PD, PX);
     }
     if (warp < kNumEpiWarps && t_end > t_begin) {
       // ===================== epilogue: TMEM -> atomics into dW (OIHW) =====================
@@ -463,7 +689,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const WgradTcPara
       uint32_t st = 0, ph = 0;
       const int n_pass = p.x3 ? 3 : 1;
       const uint32_t xmul = p.x3 ? 2u : 1u;
-      for (int tile = t_begin; tile < t_end; ++tile) {
+      for (int tile = t_begin; tile < t_end; tile += ts) {
         mbar_wait(smem_u32(&ctl->full[st]), ph);
         tc_fence_after();
        for (int ps = 0; ps < n_pass; ++ps) {
@@ -522,6 +748,12 @@ int wgrad_plan(const ab_conv_t* d, WgradTcParams* p, int* smem_bytes) {
   p->N = d->N; p->H = d->H; p->W = d->W; p->Cout = d->Cout; p->Cin = p->S.Ctot;
   p->taps_h = d->ks_h; p->taps_w = d->ks_w; p->dil = d->dil;
   p->x3 = d->math == AB_MATH_TF32X3 ? 1 : 0;
+  {
+    const char* e = getenv("ATOMAI_B200_WGRAD_LOADER");
+    p->legacy_loader = (e && e[0] == '0') ? 1 : 0;
+    const char* o = getenv("ATOMAI_B200_WGRAD_ORDER");
+    p->interleave = (o && o[0] == '0') ? 0 : 1;
+  }
   AB_CHECK(d->ks_w <= 4 && d->ks_h <= 4, "wgrad_tc: kernel %dx%d too large", d->ks_h, d->ks_w);
   p->tiles_h = (d->H + kTileH - 1) / kTileH;
   p->tiles_w = (d->W + kTileW - 1) / kTileW;

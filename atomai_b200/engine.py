@@ -11,6 +11,7 @@ normalisation) and a *pending* 2x2 max-pool.  Consumers apply both while loading
 BatchNorm outputs, pooled tensors and torch.cat results are never written to HBM
 (atomai/nets/fcnn.py:117-142 materialises all of them).
 """
+import os
 from typing import List, Optional, Sequence, Union
 
 import torch
@@ -19,10 +20,25 @@ from . import ops
 from .ops import ACT_LRELU, ACT_TANH, MATH_FP32, MATH_TF32, MATH_TF32X3, Source
 
 _MATH = {"mode": MATH_TF32X3, "wgrad_tc": True,   # default: the mode that meets the fp32 tolerances
-         "wgrad": MATH_TF32}                        # weight-gradient contraction (None: same mode)
+         "wgrad": MATH_TF32,                        # weight-gradient contraction (None: same mode)
+         "fuse_up": False}                          # 2x upsampling on load (False: written out)
 
 
 _MODES = {"fp32": MATH_FP32, "tf32": MATH_TF32, "tf32x3": MATH_TF32X3}
+if os.environ.get("ATOMAI_B200_FUSE_UP", "0") == "1":     # A/B switch for benchmarking
+    _MATH["fuse_up"] = True
+
+
+def set_fusion(upsample: Optional[bool] = None) -> None:
+    """upsample=True: `F.interpolate(scale_factor=2)` of an UpsampleBlock is NOT written out; the
+    convolution that consumes it (and its weight-gradient kernel) interpolates the (H/2, W/2)
+    tensor while staging its input tile (descriptor code `pool = 2 / 3`).  Measured on the bench
+    workload (32 x 512^2, round 2): the fit cycle takes 25.6 ms fused against 23.7 ms with the
+    upsampled tensor materialised — four dependent loads + the interpolation per staged element in
+    the register-staged loaders cost more than the 0.8 ms `upsample_fwd` pass they replace, and
+    the layer loses its TMA-staged path — so the default is False."""
+    if upsample is not None:
+        _MATH["fuse_up"] = bool(upsample)
 
 
 def set_math(mode: str = "tf32x3", wgrad_tc: Optional[bool] = None,
@@ -60,13 +76,15 @@ def get_math() -> str:
 
 
 class Act:
-    """Activation handle: NHWC tensor + pending affine + pending pool (see module docstring)."""
-    __slots__ = ("t", "scale", "shift", "pool", "parent", "grad", "grad_owned", "extra",
+    """Activation handle: NHWC tensor + pending affine + pending pool / 2x upsampling (see module
+    docstring)."""
+    __slots__ = ("t", "scale", "shift", "pool", "up", "parent", "grad", "grad_owned", "extra",
                  "needs_grad")
 
-    def __init__(self, t, scale=None, shift=None, pool=False, parent=None, needs_grad=True):
+    def __init__(self, t, scale=None, shift=None, pool=False, parent=None, needs_grad=True, up=None):
         self.t, self.scale, self.shift, self.pool = t, scale, shift, pool
-        self.parent = parent          # set for lazy-pooled views: gradients go to the parent
+        self.up = up                  # None | 'bilinear' | 'nearest': pending 2x upsampling
+        self.parent = parent          # set for lazy pooled / upsampled views: gradients go to the parent
         self.grad = None              # d loss / d (affine(a)), full resolution of t
         self.grad_owned = False       # True: grad buffer is exclusively ours (in-place add ok)
         self.extra = None             # DilatedBlock direct taps (d loss / d a and d pre)
@@ -75,6 +93,8 @@ class Act:
     @property
     def shape(self):                  # logical NHWC shape seen by a consumer
         n, h, w, c = self.t.shape
+        if self.up:
+            return (n, 2 * h, 2 * w, c)
         return (n, h // 2, w // 2, c) if self.pool else (n, h, w, c)
 
     @property
@@ -82,10 +102,12 @@ class Act:
         return self.t.shape[3]
 
     def source(self) -> Source:
-        return Source(self.t, self.scale, self.shift, self.pool)
+        code = ops.SRC_POOL if self.pool else (
+            0 if not self.up else (ops.SRC_UP_BILINEAR if self.up == "bilinear" else ops.SRC_UP_NEAREST))
+        return Source(self.t, self.scale, self.shift, code)
 
     def pending(self) -> bool:
-        return self.pool or self.scale is not None
+        return bool(self.pool) or self.up is not None or self.scale is not None
 
 
 def _acc_grad(act: Act, g: torch.Tensor, owned: bool) -> None:
@@ -314,6 +336,8 @@ class Tape:
                     continue
                 if s.pool:
                     self._pool_grad(s.parent, view)
+                elif s.up:
+                    self._up_grad(s, view)
                 else:
                     _acc_grad(s, view, True)
 
@@ -324,7 +348,7 @@ class Tape:
         if not acc:
             tgt.grad = torch.empty(tgt.t.shape, device=gp.device, dtype=torch.float32)
             tgt.grad_owned = True
-        elif not (tgt.grad_owned and tgt.grad.is_contiguous()):
+        elif not tgt.grad_owned:      # (an owned channel-slice view is accumulated into in place)
             own = torch.empty(tgt.t.shape, device=gp.device, dtype=torch.float32)
             ops.add_slice(tgt.grad, own, False)
             tgt.grad, tgt.grad_owned = own, True
@@ -333,33 +357,32 @@ class Tape:
     # ------------------------------------------------------------------ pooling / upsampling
     def pool(self, x: Act) -> Act:
         """F.max_pool2d(x, 2, 2) as a pending transform (atomai/nets/fcnn.py:123-127)."""
-        if x.pool:
+        if x.pool or x.up:
             x = self.materialize(x)
         assert x.t.shape[1] % 2 == 0 and x.t.shape[2] % 2 == 0, \
             "2x2 max-pool needs even spatial dimensions"
         return Act(x.t, x.scale, x.shift, pool=True, parent=x, needs_grad=x.needs_grad)
 
     def upsample(self, x: Act, mode: str = "bilinear") -> Act:
-        """F.interpolate(scale_factor=2, mode) (atomai/nets/blocks.py:130-131)."""
-        if x.pending():
+        """F.interpolate(scale_factor=2, mode) (atomai/nets/blocks.py:130-131) as a PENDING
+        transform: the consuming convolution interpolates while it stages its input tile
+        (forward, dgrad's source routing and the weight gradient), so the 4x larger tensor is
+        never written.  Other consumers materialise it (`materialize`)."""
+        if x.pool or x.up:
             x = self.materialize(x)
-        n, h, w, c = x.t.shape
-        out_t = torch.empty((n, 2 * h, 2 * w, c), device=x.t.device, dtype=torch.float32)
-        bil = mode == "bilinear"
-        ops.upsample_fwd(x.t, out_t, bil)
-        out = Act(out_t, needs_grad=x.needs_grad)
-        if self.record:
-            self.ops.append(("up", (x, out, bil)))
-        return out
+        assert mode in ("bilinear", "nearest")
+        if not _MATH["fuse_up"]:
+            return self.materialize(Act(x.t, x.scale, x.shift, parent=x, needs_grad=x.needs_grad, up=mode))
+        return Act(x.t, x.scale, x.shift, parent=x, needs_grad=x.needs_grad, up=mode)
 
-    def _up_bwd(self, rec) -> None:
-        x, out, bil = rec
-        if not x.needs_grad or out.grad is None:
+    @staticmethod
+    def _up_grad(s: Act, g: torch.Tensor) -> None:
+        """parent.grad (+)= upsample^T(g) (g: gradient w.r.t. the upsampled, affine'd values)."""
+        x = s.parent
+        if not x.needs_grad:
             return
-        g = out.grad
         dx = torch.empty(x.t.shape, device=g.device, dtype=torch.float32)
-        ops.upsample_bwd(g, dx, bil)
-        out.grad = None
+        ops.upsample_bwd(g, dx, s.up == "bilinear")
         _acc_grad(x, dx, True)
 
     def materialize(self, x: Act, nchw: bool = False) -> Act:
@@ -368,7 +391,15 @@ class Tape:
             return x
         n, h, w, c = x.shape
         dev = x.t.device
-        if x.pool:
+        if x.up:
+            assert not nchw
+            src = x.t
+            if x.scale is not None:       # affine and interpolation commute (weights sum to one)
+                src = torch.empty(x.t.shape, device=dev, dtype=torch.float32)
+                ops.affine(x.t, x.scale, x.shift, src)
+            out_t = torch.empty((n, h, w, c), device=dev, dtype=torch.float32)
+            ops.upsample_fwd(src, out_t, x.up == "bilinear")
+        elif x.pool:
             assert not nchw
             out_t = torch.empty((n, h, w, c), device=dev, dtype=torch.float32)
             ops.pool_fwd(x.t, x.scale, x.shift, out_t)
@@ -396,6 +427,8 @@ class Tape:
         out.grad = None
         if x.pool:
             self._pool_grad(x.parent, g)
+        elif x.up:
+            self._up_grad(x, g)
         else:
             _acc_grad(x, g, owned)
 
@@ -714,8 +747,6 @@ class Tape:
         for kind, rec in reversed(self.ops):
             if kind == "conv":
                 self._conv_bwd(rec)
-            elif kind == "up":
-                self._up_bwd(rec)
             elif kind == "mat":
                 self._mat_bwd(rec)
             elif kind == "dsum":

@@ -33,12 +33,17 @@ def _ld(t: torch.Tensor) -> int:
     return ld
 
 
+SRC_PLAIN, SRC_POOL, SRC_UP_BILINEAR, SRC_UP_NEAREST = 0, 1, 2, 3
+
+
 class Source:
-    """One conv input: NHWC tensor + optional pending BN affine + optional pending 2x2 pool."""
+    """One conv input: NHWC tensor + optional pending BN affine + optional on-load resampling
+    (`pool`: False/0 none, True/1 2x2 max-pool of a (2H, 2W) tensor, 2 / 3 bilinear / nearest 2x
+    upsampling of a (H/2, W/2) tensor)."""
     __slots__ = ("t", "scale", "shift", "pool")
 
     def __init__(self, t, scale=None, shift=None, pool=False):
-        self.t, self.scale, self.shift, self.pool = t, scale, shift, bool(pool)
+        self.t, self.scale, self.shift, self.pool = t, scale, shift, int(pool)
 
     @property
     def C(self):
@@ -58,10 +63,12 @@ def conv_desc(srcs: Sequence[Source], N, H, W, Cout, ks=(3, 3), dil=1, lrelu=1.0
         e.shift = ptr(s.shift)
         e.C = s.t.shape[3]
         e.ld = _ld(s.t)
-        e.pool = 1 if s.pool else 0
+        e.pool = int(s.pool)
         sh, sw = s.t.shape[1], s.t.shape[2]
-        if s.pool:
+        if s.pool == SRC_POOL:
             assert (sh, sw) == (2 * H, 2 * W), f"pooled source must be {(2*H, 2*W)}, got {(sh, sw)}"
+        elif s.pool in (SRC_UP_BILINEAR, SRC_UP_NEAREST):
+            assert (2 * sh, 2 * sw) == (H, W), f"upsampled source must be {(H//2, W//2)}, got {(sh, sw)}"
         else:
             assert (sh, sw) == (H, W), f"source spatial {(sh, sw)} != {(H, W)}"
         assert s.t.shape[0] == N

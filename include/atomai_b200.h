@@ -41,16 +41,18 @@ extern "C" {
 #define AB_WMODE_DGRAD 1 /* flipped + transposed weights for data-gradient */
 
 /* One input source of a convolution.  The loader applies, in this order:
- * per-channel affine (BatchNorm normalise-on-load), 2x2 max-pool, zero padding.
- * Replaces the separate BatchNorm2d / F.max_pool2d / torch.cat passes of
- * atomai/nets/blocks.py:73 and atomai/nets/fcnn.py:123-138. */
+ * per-channel affine (BatchNorm normalise-on-load), 2x2 max-pool OR 2x upsampling, zero padding.
+ * Replaces the separate BatchNorm2d / F.max_pool2d / F.interpolate / torch.cat passes of
+ * atomai/nets/blocks.py:73,130-131 and atomai/nets/fcnn.py:123-138. */
 typedef struct {
   const float* ptr;   /* NHWC base                                          */
   const float* scale; /* [C] or NULL                                        */
   const float* shift; /* [C] or NULL                                        */
   int32_t C;          /* channels taken from this source                    */
   int32_t ld;         /* pixel stride in floats                             */
-  int32_t pool;       /* 1: source is (2H,2W); 2x2 max taken after affine   */
+  int32_t pool;       /* 1: source is (2H,2W); 2x2 max taken after affine;
+                         2 / 3: source is (H/2,W/2); bilinear (align_corners=0) /
+                         nearest 2x upsampling on load (H, W even)          */
   int32_t reserved;
 } ab_src_t;
 
