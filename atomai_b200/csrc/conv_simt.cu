@@ -196,7 +196,28 @@ __global__ void __launch_bounds__(256) conv_pix_kernel(const ConvSimtParams p, i
       ssum[k] += acc[k];
       ssq[k] = fmaf(acc[k], acc[k], ssq[k]);
     }
-    if (!p.out_nchw) {
+    constexpr int QP = CO % 4 == 0 ? CO / 4 : 1;     // float4 per pixel
+    const int64_t pix0 = pix - (threadIdx.x & 31);
+    if (!p.out_nchw && CO % 4 == 0 && CO >= 8 && CO <= 32 && p.Cout == CO && p.ld_out == CO &&
+        pix0 + 31 < npix) {
+      // dense NHWC output: stage the warp's 32 pixels in shared memory and write them as whole
+      // 512-byte runs (see conv_c1_kernel)
+      __shared__ float4 s_stage[8][32 * QP];
+      const int lane = threadIdx.x & 31;
+      float4* buf = s_stage[threadIdx.x >> 5];
+#pragma unroll
+      for (int k = 0; k < QP; ++k)
+        buf[lane * QP + (k ^ (lane & (QP - 1)))] =
+            make_float4(acc[4 * k], acc[4 * k + 1], acc[4 * k + 2], acc[4 * k + 3]);
+      __syncwarp();
+      float4* o4 = reinterpret_cast<float4*>(p.out + (size_t)pix0 * CO);
+#pragma unroll
+      for (int i = 0; i < QP; ++i) {
+        const int g = i * 32 + lane, row = g / QP, kk = g & (QP - 1);
+        o4[g] = buf[row * QP + (kk ^ (row & (QP - 1)))];
+      }
+      __syncwarp();
+    } else if (!p.out_nchw) {
       float* o = p.out + pix * p.ld_out;
       if (CO % 4 == 0 && p.Cout == CO && (p.ld_out & 3) == 0) {
 #pragma unroll
@@ -240,6 +261,11 @@ __global__ void __launch_bounds__(256, 2) conv_c1_kernel(const ConvSimtParams p)
   __shared__ float4 s_w[9 * CO / 4];            // [tap][co]
   __shared__ float4 s_b[CO / 4];
   __shared__ float s_red[2 * CO];
+  // per-warp staging for the output transpose: a lane's 2 pixels x CO channels -> the warp's 64
+  // consecutive pixels written as whole 512-byte runs (a lane-private store pattern touches 32
+  // different 128-byte lines per instruction)
+  constexpr int Q = 2 * CO / 4;                 // float4 per lane
+  __shared__ float4 s_stage[8][32 * Q];
   for (int i = threadIdx.x; i < 9 * CO; i += blockDim.x)
     reinterpret_cast<float*>(s_w)[i] = __ldg(p.w + i);          // packed [tap][Cin = 1][Cout]
   if (threadIdx.x < CO)
@@ -315,12 +341,34 @@ __global__ void __launch_bounds__(256, 2) conv_c1_kernel(const ConvSimtParams p)
       ssum[k] += a0[k] + a1[k];
       ssq[k] = fmaf(a0[k], a0[k], fmaf(a1[k], a1[k], ssq[k]));
     }
-    float* o = p.out + (((size_t)n * H + h) * W + w) * p.ld_out;
+    // whole warp in range, even W and a dense NHWC output: pair idx <-> pixels 2*idx, 2*idx + 1
+    const uint32_t idx0 = idx - (threadIdx.x & 31);
+    const bool dense = (W & 1) == 0 && p.ld_out == CO && (Q & (Q - 1)) == 0 && Q <= 8 &&
+                       idx0 + 31 < total;
+    if (dense) {
+      const int lane = threadIdx.x & 31;
+      float4* buf = s_stage[threadIdx.x >> 5];
 #pragma unroll
-    for (int k = 0; k < CO; k += 4) {
-      *reinterpret_cast<float4*>(o + k) = make_float4(a0[k], a0[k + 1], a0[k + 2], a0[k + 3]);
-      if (two)
-        *reinterpret_cast<float4*>(o + p.ld_out + k) = make_float4(a1[k], a1[k + 1], a1[k + 2], a1[k + 3]);
+      for (int k = 0; k < Q / 2; ++k) {
+        buf[lane * Q + ((k) ^ (lane & (Q - 1)))] = make_float4(a0[4 * k], a0[4 * k + 1], a0[4 * k + 2], a0[4 * k + 3]);
+        buf[lane * Q + ((k + Q / 2) ^ (lane & (Q - 1)))] = make_float4(a1[4 * k], a1[4 * k + 1], a1[4 * k + 2], a1[4 * k + 3]);
+      }
+      __syncwarp();
+      float4* o4 = reinterpret_cast<float4*>(p.out + (size_t)idx0 * 2 * CO);
+#pragma unroll
+      for (int i = 0; i < Q; ++i) {
+        const int g = i * 32 + lane, row = g / Q, kk = g & (Q - 1);
+        o4[g] = buf[row * Q + (kk ^ (row & (Q - 1)))];
+      }
+      __syncwarp();
+    } else {
+      float* o = p.out + (((size_t)n * H + h) * W + w) * p.ld_out;
+#pragma unroll
+      for (int k = 0; k < CO; k += 4) {
+        *reinterpret_cast<float4*>(o + k) = make_float4(a0[k], a0[k + 1], a0[k + 2], a0[k + 3]);
+        if (two)
+          *reinterpret_cast<float4*>(o + p.ld_out + k) = make_float4(a1[k], a1[k + 1], a1[k + 2], a1[k + 3]);
+      }
     }
   }
   if (p.stats) {
