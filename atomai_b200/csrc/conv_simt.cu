@@ -30,6 +30,7 @@ struct ConvSimtParams {
   int out_nchw;
   double* stats;
   int tiles_h, tiles_w;
+  int c0;          // thin-channel kernels: first output channel of this launch's channel block
 };
 
 __global__ void __launch_bounds__(F_THREADS) conv_simt_fwd_kernel(const ConvSimtParams p) {
@@ -145,15 +146,16 @@ __global__ void __launch_bounds__(256) conv_pix_kernel(const ConvSimtParams p, i
   extern __shared__ float s_w[];                 // [taps][Cin][CO] (zero padded to CO)
   __shared__ float s_red[2 * CO];
   const int taps = p.th * p.tw, Cin = p.S.Ctot;
+  const int c0 = p.c0, nco = min(CO, p.Cout - c0);     // this launch's channel block
   for (int i = threadIdx.x; i < taps * Cin * CO; i += blockDim.x) {
     const int co = i % CO, r = i / CO;
-    s_w[i] = co < p.Cout ? __ldg(p.w + (size_t)r * p.Cout + co) : 0.f;
+    s_w[i] = co < nco ? __ldg(p.w + (size_t)r * p.Cout + c0 + co) : 0.f;
   }
   if (threadIdx.x < 2 * CO) s_red[threadIdx.x] = 0.f;
   __syncthreads();
   float bias[CO];
 #pragma unroll
-  for (int k = 0; k < CO; ++k) bias[k] = (p.bias && k < p.Cout) ? __ldg(p.bias + k) : 0.f;
+  for (int k = 0; k < CO; ++k) bias[k] = (p.bias && k < nco) ? __ldg(p.bias + c0 + k) : 0.f;
   float ssum[CO], ssq[CO];
 #pragma unroll
   for (int k = 0; k < CO; ++k) { ssum[k] = 0.f; ssq[k] = 0.f; }
@@ -196,43 +198,22 @@ __global__ void __launch_bounds__(256) conv_pix_kernel(const ConvSimtParams p, i
       ssum[k] += acc[k];
       ssq[k] = fmaf(acc[k], acc[k], ssq[k]);
     }
-    constexpr int QP = CO % 4 == 0 ? CO / 4 : 1;     // float4 per pixel
-    const int64_t pix0 = pix - (threadIdx.x & 31);
-    if (!p.out_nchw && CO % 4 == 0 && CO >= 8 && CO <= 32 && p.Cout == CO && p.ld_out == CO &&
-        pix0 + 31 < npix) {
-      // dense NHWC output: stage the warp's 32 pixels in shared memory and write them as whole
-      // 512-byte runs (see conv_c1_kernel)
-      __shared__ float4 s_stage[8][32 * QP];
-      const int lane = threadIdx.x & 31;
-      float4* buf = s_stage[threadIdx.x >> 5];
-#pragma unroll
-      for (int k = 0; k < QP; ++k)
-        buf[lane * QP + (k ^ (lane & (QP - 1)))] =
-            make_float4(acc[4 * k], acc[4 * k + 1], acc[4 * k + 2], acc[4 * k + 3]);
-      __syncwarp();
-      float4* o4 = reinterpret_cast<float4*>(p.out + (size_t)pix0 * CO);
-#pragma unroll
-      for (int i = 0; i < QP; ++i) {
-        const int g = i * 32 + lane, row = g / QP, kk = g & (QP - 1);
-        o4[g] = buf[row * QP + (kk ^ (row & (QP - 1)))];
-      }
-      __syncwarp();
-    } else if (!p.out_nchw) {
-      float* o = p.out + pix * p.ld_out;
-      if (CO % 4 == 0 && p.Cout == CO && (p.ld_out & 3) == 0) {
+    if (!p.out_nchw) {
+      float* o = p.out + pix * p.ld_out + c0;
+      if (CO % 4 == 0 && nco == CO && (p.ld_out & 3) == 0 && (c0 & 3) == 0) {
 #pragma unroll
         for (int k = 0; k < CO; k += 4)
           *reinterpret_cast<float4*>(o + k) = make_float4(acc[k], acc[k + 1], acc[k + 2], acc[k + 3]);
       } else {
 #pragma unroll
         for (int k = 0; k < CO; ++k)
-          if (k < p.Cout) o[k] = acc[k];
+          if (k < nco) o[k] = acc[k];
       }
     } else {
       const size_t hw = (size_t)p.H * p.W;
 #pragma unroll
       for (int k = 0; k < CO; ++k)
-        if (k < p.Cout) p.out[((size_t)n * p.Cout + k) * hw + (size_t)h * p.W + w] = acc[k];
+        if (k < nco) p.out[((size_t)n * p.Cout + c0 + k) * hw + (size_t)h * p.W + w] = acc[k];
     }
   }
   if (p.stats) {
@@ -245,9 +226,9 @@ __global__ void __launch_bounds__(256) conv_pix_kernel(const ConvSimtParams p, i
       }
     }
     __syncthreads();
-    if (threadIdx.x < CO && threadIdx.x < p.Cout) {
-      atomicAdd(p.stats + threadIdx.x, (double)s_red[threadIdx.x]);
-      atomicAdd(p.stats + p.Cout + threadIdx.x, (double)s_red[CO + threadIdx.x]);
+    if (threadIdx.x < CO && threadIdx.x < nco) {
+      atomicAdd(p.stats + c0 + threadIdx.x, (double)s_red[threadIdx.x]);
+      atomicAdd(p.stats + p.Cout + c0 + threadIdx.x, (double)s_red[CO + threadIdx.x]);
     }
   }
 }
@@ -261,15 +242,11 @@ __global__ void __launch_bounds__(256, 2) conv_c1_kernel(const ConvSimtParams p)
   __shared__ float4 s_w[9 * CO / 4];            // [tap][co]
   __shared__ float4 s_b[CO / 4];
   __shared__ float s_red[2 * CO];
-  // per-warp staging for the output transpose: a lane's 2 pixels x CO channels -> the warp's 64
-  // consecutive pixels written as whole 512-byte runs (a lane-private store pattern touches 32
-  // different 128-byte lines per instruction)
-  constexpr int Q = 2 * CO / 4;                 // float4 per lane
-  __shared__ float4 s_stage[8][32 * Q];
-  for (int i = threadIdx.x; i < 9 * CO; i += blockDim.x)
-    reinterpret_cast<float*>(s_w)[i] = __ldg(p.w + i);          // packed [tap][Cin = 1][Cout]
+  const int c0 = p.c0;                                           // channel block of this launch
+  for (int i = threadIdx.x; i < 9 * CO; i += blockDim.x)         // packed [tap][Cin = 1][Cout]
+    reinterpret_cast<float*>(s_w)[i] = __ldg(p.w + (size_t)(i / CO) * p.Cout + c0 + (i % CO));
   if (threadIdx.x < CO)
-    reinterpret_cast<float*>(s_b)[threadIdx.x] = p.bias ? __ldg(p.bias + threadIdx.x) : 0.f;
+    reinterpret_cast<float*>(s_b)[threadIdx.x] = p.bias ? __ldg(p.bias + c0 + threadIdx.x) : 0.f;
   if (threadIdx.x < 2 * CO) s_red[threadIdx.x] = 0.f;
   __syncthreads();
   const SrcDev sd = p.S.s[0];
@@ -341,34 +318,12 @@ __global__ void __launch_bounds__(256, 2) conv_c1_kernel(const ConvSimtParams p)
       ssum[k] += a0[k] + a1[k];
       ssq[k] = fmaf(a0[k], a0[k], fmaf(a1[k], a1[k], ssq[k]));
     }
-    // whole warp in range, even W and a dense NHWC output: pair idx <-> pixels 2*idx, 2*idx + 1
-    const uint32_t idx0 = idx - (threadIdx.x & 31);
-    const bool dense = (W & 1) == 0 && p.ld_out == CO && (Q & (Q - 1)) == 0 && Q <= 8 &&
-                       idx0 + 31 < total;
-    if (dense) {
-      const int lane = threadIdx.x & 31;
-      float4* buf = s_stage[threadIdx.x >> 5];
+    float* o = p.out + (((size_t)n * H + h) * W + w) * p.ld_out + c0;
 #pragma unroll
-      for (int k = 0; k < Q / 2; ++k) {
-        buf[lane * Q + ((k) ^ (lane & (Q - 1)))] = make_float4(a0[4 * k], a0[4 * k + 1], a0[4 * k + 2], a0[4 * k + 3]);
-        buf[lane * Q + ((k + Q / 2) ^ (lane & (Q - 1)))] = make_float4(a1[4 * k], a1[4 * k + 1], a1[4 * k + 2], a1[4 * k + 3]);
-      }
-      __syncwarp();
-      float4* o4 = reinterpret_cast<float4*>(p.out + (size_t)idx0 * 2 * CO);
-#pragma unroll
-      for (int i = 0; i < Q; ++i) {
-        const int g = i * 32 + lane, row = g / Q, kk = g & (Q - 1);
-        o4[g] = buf[row * Q + (kk ^ (row & (Q - 1)))];
-      }
-      __syncwarp();
-    } else {
-      float* o = p.out + (((size_t)n * H + h) * W + w) * p.ld_out;
-#pragma unroll
-      for (int k = 0; k < CO; k += 4) {
-        *reinterpret_cast<float4*>(o + k) = make_float4(a0[k], a0[k + 1], a0[k + 2], a0[k + 3]);
-        if (two)
-          *reinterpret_cast<float4*>(o + p.ld_out + k) = make_float4(a1[k], a1[k + 1], a1[k + 2], a1[k + 3]);
-      }
+    for (int k = 0; k < CO; k += 4) {
+      *reinterpret_cast<float4*>(o + k) = make_float4(a0[k], a0[k + 1], a0[k + 2], a0[k + 3]);
+      if (two)
+        *reinterpret_cast<float4*>(o + p.ld_out + k) = make_float4(a1[k], a1[k + 1], a1[k + 2], a1[k + 3]);
     }
   }
   if (p.stats) {
@@ -382,8 +337,8 @@ __global__ void __launch_bounds__(256, 2) conv_c1_kernel(const ConvSimtParams p)
     }
     __syncthreads();
     if (threadIdx.x < CO) {
-      atomicAdd(p.stats + threadIdx.x, (double)s_red[threadIdx.x]);
-      atomicAdd(p.stats + p.Cout + threadIdx.x, (double)s_red[CO + threadIdx.x]);
+      atomicAdd(p.stats + c0 + threadIdx.x, (double)s_red[threadIdx.x]);
+      atomicAdd(p.stats + p.Cout + c0 + threadIdx.x, (double)s_red[CO + threadIdx.x]);
     }
   }
 }
@@ -727,16 +682,33 @@ int ab_conv_simt_fwd(const ab_conv_t* d, const float* w, const float* bias, floa
   // thin-channel specialisations (first layer, pixel-wise head and its data-gradient)
   {
     const int Cin = p.S.Ctot, taps = d->ks_h * d->ks_w;
-    if (Cin == 1 && d->ks_h == 3 && d->ks_w == 3 && d->Cout == 16 && p.S.nsrc == 1 &&
-        !p.S.s[0].pool && !d->out_nchw && ld_y % 4 == 0 && ((uintptr_t)y & 15) == 0 &&
-        d->N * (int64_t)d->H * d->W > 0)
-      return launch_conv_c1<16>(p, stream);
-    if (taps * Cin <= 64 && d->N * (int64_t)d->H * d->W > 0) {
-      if (d->Cout <= 4) return launch_conv_pix<4>(p, stream);
-      if (d->Cout == 8) return launch_conv_pix<8>(p, stream);
-      if (d->Cout == 16) return launch_conv_pix<16>(p, stream);
-      if (d->Cout == 32) return launch_conv_pix<32>(p, stream);
+    p.c0 = 0;
+    if (Cin == 1 && d->ks_h == 3 && d->ks_w == 3 && d->Cout % 16 == 0 && d->Cout <= 256 &&
+        p.S.nsrc == 1 && !p.S.s[0].pool && !d->out_nchw && ld_y % 4 == 0 && ((uintptr_t)y & 15) == 0 &&
+        d->N * (int64_t)d->H * d->W > 0) {
+      // first layer of every net (Unet 1 -> 16, ImSpec 1 -> 64, VAE 1 -> 128): one launch per block
+      // of 16 output channels, the single-channel input stays in L2 between them
+      for (p.c0 = 0; p.c0 < d->Cout; p.c0 += 16)
+        if (launch_conv_c1<16>(p, stream)) return 1;
+      return 0;
     }
+    if (d->N * (int64_t)d->H * d->W > 0) {
+      // pixel-wise kernels: weights in shared memory ([taps][Cin][CO] floats), all CO outputs of a
+      // pixel in registers.  Heads with <= 4 outputs take any Cin up to 1024 taps*channels (the
+      // rDecoder's 128 -> 1 output layer); wider outputs from <= 64 taps*channels run as blocks of
+      // 32 channels (the 1 -> 128 data-gradient of that layer)
+      if (d->Cout <= 4 && taps * Cin <= 1024) return launch_conv_pix<4>(p, stream);
+      if (taps * Cin <= 64) {
+        if (d->Cout == 8) return launch_conv_pix<8>(p, stream);
+        if (d->Cout == 16) return launch_conv_pix<16>(p, stream);
+        if (d->Cout % 32 == 0 && d->Cout <= 256 && !d->out_nchw) {
+          for (p.c0 = 0; p.c0 < d->Cout; p.c0 += 32)
+            if (launch_conv_pix<32>(p, stream)) return 1;
+          return 0;
+        }
+      }
+    }
+    p.c0 = 0;
   }
   const int ph = d->dil * (d->ks_h >> 1), pw = d->dil * (d->ks_w >> 1);
   const int smem = (F_CIT * (F_TH + 2 * ph) * (F_TW + 2 * pw) + d->ks_h * d->ks_w * F_CIT * F_COT) *

@@ -4,6 +4,7 @@
 //   * coord_latent fused with transform_coordinates (rVAE spatial decoder, first layer).
 // Reference call sites: atomai/nets/ed.py:64,273-274,503-505 (Linear), :672-687 (coord_latent),
 // atomai/utils/coords.py:47-83, atomai/models/dgm/rvae.py:118-145, atomai/nets/gp.py:14-26.
+#include <cstdlib>
 #include "common.cuh"
 
 namespace {
@@ -96,6 +97,122 @@ __global__ void bias_fill_kernel(float* C, int64_t c_sm, int M, int N, const flo
     const int n = (int)(i % N);
     C[(i / N) * c_sm + n] = bias ? bias[n] : 0.f;
   }
+}
+
+
+// ---------------------------------------------------------------- skinny nn.Linear (O <= 16)
+// The latent heads of the VAE / ImSpec encoders (atomai/nets/ed.py:64,273-274: 262144..524288
+// inputs -> 2..13 outputs) are pure HBM streams over the activations: B x K floats read once,
+// a handful of outputs.  The 64x64 GEMM tile above wastes 59/64 of its B-operand lanes on them and
+// reads x in 64-byte pieces (measured 312-482 us per call, 27-31 % of an rVAE / ImSpec step);
+// these kernels read x / write dx as whole rows of float4 and keep the O-wide side in shared
+// memory or registers.
+constexpr int SK_T = 256;          // threads
+constexpr int SK_KS = 1024;        // k per CTA (one float4 per thread)
+constexpr int SK_MAXO = 16;
+
+// y[b][o] (+)= sum_{k in slice} x[b][k] w[o][k]: CTA = one k-slice, thread = 4 k, loop over rows;
+// per row a warp reduces its O partial sums with shuffles and adds them into y (pre-filled with the
+// bias by the caller)
+__global__ void __launch_bounds__(SK_T) skinny_fwd_kernel(const float* __restrict__ x,
+                                                           const float* __restrict__ w,
+                                                           float* __restrict__ y, int B, int K, int O) {
+  const int k = blockIdx.x * SK_KS + threadIdx.x * 4;
+  const bool in = k < K;                     // K % 4 == 0: a thread's 4 k are all in or all out
+  float4 wv[SK_MAXO];
+#pragma unroll
+  for (int o = 0; o < SK_MAXO; ++o)
+    wv[o] = (in && o < O) ? __ldg(reinterpret_cast<const float4*>(w + (size_t)o * K + k))
+                          : make_float4(0.f, 0.f, 0.f, 0.f);
+  __shared__ float s_part[SK_T / 32][SK_MAXO];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int b = blockIdx.y; b < B; b += gridDim.y) {
+    const float4 xv = in ? __ldg(reinterpret_cast<const float4*>(x + (size_t)b * K + k))
+                         : make_float4(0.f, 0.f, 0.f, 0.f);
+    float acc[SK_MAXO];
+#pragma unroll
+    for (int o = 0; o < SK_MAXO; ++o)
+      acc[o] = fmaf(xv.x, wv[o].x, fmaf(xv.y, wv[o].y, fmaf(xv.z, wv[o].z, xv.w * wv[o].w)));
+#pragma unroll
+    for (int o = 0; o < SK_MAXO; ++o) {
+      if (o < O) {
+        float a = acc[o];
+#pragma unroll
+        for (int sft = 16; sft >= 1; sft >>= 1) a += __shfl_xor_sync(0xffffffffu, a, sft);
+        if (lane == 0) s_part[warp][o] = a;
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < O) {
+      float t = 0.f;
+#pragma unroll
+      for (int wi = 0; wi < SK_T / 32; ++wi) t += s_part[wi][threadIdx.x];
+      atomicAdd(y + (size_t)b * O + threadIdx.x, t);
+    }
+    __syncthreads();
+  }
+}
+
+// dx[b][k] = sum_o dy[b][o] w[o][k]   and   dw[o][k] = sum_b dy[b][o] x[b][k]  in ONE pass over the
+// rows: a thread owns 4 consecutive k (its w in registers), dy lives in shared memory
+constexpr int SK_TB = 128, SK_KSB = 512;   // backward: 128 threads x 4 k (two O-wide float4 sets per thread)
+template <int MAXO>
+__global__ void __launch_bounds__(SK_TB) skinny_bwd_kernel(const float* __restrict__ x,
+                                                           const float* __restrict__ w,
+                                                           const float* __restrict__ dy,
+                                                           float* __restrict__ dx,
+                                                           float* __restrict__ dw, int B, int K, int O) {
+  extern __shared__ float s_dy[];            // [B][O]
+  for (int i = threadIdx.x; i < B * O; i += SK_TB) s_dy[i] = __ldg(dy + i);
+  __syncthreads();
+  const int k = blockIdx.x * SK_KSB + threadIdx.x * 4;
+  if (k >= K) return;
+  float4 wv[MAXO], gw[MAXO];
+#pragma unroll
+  for (int o = 0; o < MAXO; ++o) {
+    wv[o] = (dx && o < O) ? __ldg(reinterpret_cast<const float4*>(w + (size_t)o * K + k))
+                          : make_float4(0.f, 0.f, 0.f, 0.f);
+    gw[o] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  constexpr int RB = 4;                      // rows in flight
+  for (int b0 = 0; b0 < B; b0 += RB) {
+    float4 xv[RB];
+    if (dw) {
+#pragma unroll
+      for (int r = 0; r < RB; ++r)
+        xv[r] = b0 + r < B ? __ldg(reinterpret_cast<const float4*>(x + (size_t)(b0 + r) * K + k))
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int r = 0; r < RB; ++r) {
+      if (b0 + r >= B) break;
+      const float* d = s_dy + (b0 + r) * O;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int o = 0; o < MAXO; ++o) {
+        if (o < O) {
+          const float g = d[o];
+          if (dw) {
+            gw[o].x = fmaf(g, xv[r].x, gw[o].x); gw[o].y = fmaf(g, xv[r].y, gw[o].y);
+            gw[o].z = fmaf(g, xv[r].z, gw[o].z); gw[o].w = fmaf(g, xv[r].w, gw[o].w);
+          }
+          acc.x = fmaf(g, wv[o].x, acc.x); acc.y = fmaf(g, wv[o].y, acc.y);
+          acc.z = fmaf(g, wv[o].z, acc.z); acc.w = fmaf(g, wv[o].w, acc.w);
+        }
+      }
+      if (dx) *reinterpret_cast<float4*>(dx + (size_t)(b0 + r) * K + k) = acc;
+    }
+  }
+  if (dw) {
+#pragma unroll
+    for (int o = 0; o < MAXO; ++o)
+      if (o < O) *reinterpret_cast<float4*>(dw + (size_t)o * K + k) = gw[o];
+  }
+}
+
+inline bool skinny_ok(const void* a, const void* b, const void* c, int B, int K, int O) {
+  const auto al = [](const void* p) { return p == nullptr || ((uintptr_t)p & 15) == 0; };
+  return O >= 1 && O <= SK_MAXO && K % 4 == 0 && K >= 4 * SK_KS && B >= 1 && al(a) && al(b) && al(c);
 }
 
 // ---------------------------------------------------------------- coord_latent
@@ -244,6 +361,18 @@ int atomai_b200_gemm(const float* A, int64_t a_sm, int64_t a_sk, const float* B,
 // y[B][O] = x[B][K] W[O][K]^T + b   — nn.Linear forward
 int atomai_b200_linear_fwd(const float* x, const float* w, const float* b, float* y, int B, int K,
                            int O, void* stream) {
+  if (skinny_ok(x, w, nullptr, B, K, O) && !getenv("ATOMAI_B200_NO_SKINNY")) {
+    // y = bias, then every k-slice CTA adds its partial sums
+    bias_fill_kernel<<<(B * O + 255) / 256, 256, 0, (cudaStream_t)stream>>>(y, O, B, O, b);
+    AB_LAUNCH_CHECK();
+    const int slices = (K + SK_KS - 1) / SK_KS;
+    int rows = (4 * ab_num_sms() + slices - 1) / slices;      // row groups: >= 4 CTAs per SM
+    if (rows > B) rows = B;
+    if (rows < 1) rows = 1;
+    skinny_fwd_kernel<<<dim3(slices, rows), SK_T, 0, (cudaStream_t)stream>>>(x, w, y, B, K, O);
+    AB_LAUNCH_CHECK();
+    return 0;
+  }
   // split K so that roughly 2 waves of CTAs exist even for a 100 x 5 output
   const int tiles = ((B + TM - 1) / TM) * ((O + TN - 1) / TN);
   int split = (2 * ab_num_sms() + tiles - 1) / tiles;
@@ -256,6 +385,19 @@ int atomai_b200_linear_fwd(const float* x, const float* w, const float* b, float
 // dx[B][K] = dy[B][O] W[O][K];  dW[O][K] = dy^T x;  db[O] = sum_b dy   (all overwrite)
 int atomai_b200_linear_bwd(const float* x, const float* w, const float* dy, float* dx, float* dw,
                            float* db, int B, int K, int O, void* stream) {
+  if (skinny_ok(x, w, dx, B, K, O) && ((uintptr_t)dw & 15) == 0 && (size_t)B * O * 4 <= 48 * 1024 &&
+      (dx || dw) && !getenv("ATOMAI_B200_NO_SKINNY")) {
+    const int slices = (K + SK_KSB - 1) / SK_KSB;
+    if (O <= 8)
+      skinny_bwd_kernel<8><<<slices, SK_TB, (size_t)B * O * 4, (cudaStream_t)stream>>>(x, w, dy, dx, dw,
+                                                                                      B, K, O);
+    else
+      skinny_bwd_kernel<16><<<slices, SK_TB, (size_t)B * O * 4, (cudaStream_t)stream>>>(x, w, dy, dx, dw,
+                                                                                       B, K, O);
+    AB_LAUNCH_CHECK();
+    if (db && ab_colsum(dy, B, O, db, (cudaStream_t)stream)) return 1;
+    return 0;
+  }
   if (dx) {
     if (atomai_b200_gemm(dy, O, 1, w, K, 1, dx, K, B, K, O, nullptr, AB_ACT_LRELU, 1.f, 0, 1, stream))
       return 1;

@@ -63,6 +63,10 @@ struct WgradTcParams {
   int dy_bytes;          // bytes of one dy tile inside a stage
   int cob;               // output channels per CTA (128, or 64 when two stages would not fit)
   int interleave;        // tile order (see the kernel)
+  int l2_prefetch;       // experiment (ATOMAI_B200_WGRAD_PF=1): loaders prefetch their next tile into L2;
+                         // measured SLOWER (4.37 vs 3.89 ms over the Unet's 15 layers): the loaders are
+                         // bound by instruction issue / the LSU pipe, not by DRAM latency — default off
+  int rt_loader;         // bring-up only (ATOMAI_B200_WGRAD_LOADER=1): run-time element loader everywhere
   int legacy_loader;     // bring-up only (ATOMAI_B200_WGRAD_LOADER=0): the thread = pixel loaders
 };
 
@@ -419,6 +423,36 @@ __device__ __forceinline__ void wgrad_loader_elem(const WgradTcParams& p, Ctl* c
     const int h_org = h0 - p.dil * (p.taps_h >> 1), w_org = w0 - p.dil * (p.taps_w >> 1);
     const bool interior = h_org >= 0 && w_org >= 0 && h_org + p.THp <= H && w_org + p.TWp <= W;
     bool waited = false;
+    if (p.l2_prefetch) {
+      // experiment, default off: pull the group's NEXT tile into L2 (one request per 32-byte sector)
+      const int nt = tile + n_groups * ts;
+      if (nt < t_end && !(j & 1)) {
+        const int n2 = (int)fdiv(nt, tpi, mulTpi);
+        const int rem2 = nt - n2 * tpi;
+        const int th2 = (int)fdiv(rem2, p.tiles_w, mulTw);
+        const int tw2 = rem2 - th2 * p.tiles_w;
+        const int ho2 = th2 * kTileH - p.dil * (p.taps_h >> 1), wo2 = tw2 * kTileW - p.dil * (p.taps_w >> 1);
+        if (!pool) {
+          for (int u = 0; u < ux_total; ++u) {
+            const uint32_t q = (uint32_t)(q0 + u * QS);
+            const uint32_t hh = fdiv(q, p.TWp, mulT), ww = q - hh * p.TWp;
+            const int ghc = min(max(ho2 + (int)hh, 0), H - 1), gwc = min(max(wo2 + (int)ww, 0), W - 1);
+            prefetch_l2(xsrc + ((size_t)(n2 * H + ghc) * W + gwc) * xld);
+          }
+        }
+      }
+      if (nt < t_end && !(jd & 1)) {
+        const int n2 = (int)fdiv(nt, tpi, mulTpi);
+        const int rem2 = nt - n2 * tpi;
+        const int th2 = (int)fdiv(rem2, p.tiles_w, mulTw);
+        const int tw2 = rem2 - th2 * p.tiles_w;
+        for (int u = 0; u < PD; ++u) {
+          const int pd = pd0 + u * QD;
+          const int gh = min(th2 * kTileH + (pd >> 3), H - 1), gw = min(tw2 * kTileW + (pd & 7), W - 1);
+          prefetch_l2(dsrc + ((size_t)(n2 * H + gh) * W + gw) * p.ld_dy);
+        }
+      }
+    }
     // ---------------- x halo elements, XB at a time
     for (int ub = 0; ub < ux_total; ub += XB) {
       float4 v[XB];
@@ -564,6 +598,175 @@ __device__ __forceinline__ void wgrad_loader_elem(const WgradTcParams& p, Ctl* c
   }
 }
 
+// Compile-time specialisation of the element-mapped loader for un-pooled sources (ncu source view
+// of the run-time version on c6.0: 1260 warp instructions per tile and warp, 79 per 16-byte
+// element — per-element validity branches with their BSYNCs, the halo index arithmetic and
+// constant-bank reloads).  UX = halo elements per thread (only the LAST one can be absent:
+// HP is not a multiple of the pixel stride QS), UD = dy elements per thread, X3 = split operands.
+// The halo offsets of a thread's elements are loop constants held in registers, the affine is
+// applied unconditionally (scale 1 / shift 0 without BatchNorm), interior tiles take a path
+// without clamps or masks.
+template <int UX, int UD, bool X3>
+__device__ __forceinline__ void wgrad_loader_ct(const WgradTcParams& p, Ctl* ctl, uint32_t base,
+                                                int grp, int gt, int t_begin, int t_end, int ts,
+                                                int co0, int ci0, int PX) {
+  constexpr int PD = UD;
+  const int lane = threadIdx.x & 31;
+  const bool stacked = p.taps_w > 1;
+  const int H = p.H, W = p.W, HP = p.HP;
+  const int tpi = p.tiles_w * p.tiles_h;
+  const uint32_t mulTpi = fdiv_mul(tpi), mulTw = fdiv_mul(p.tiles_w), mulT = fdiv_mul(p.TWp);
+  const uint32_t S = p.n_stages;
+  const int n_groups = S >= (uint32_t)kGroups ? kGroups : 2;
+  if (grp >= n_groups) return;
+  const uint32_t xlo_off = p.x_bytes, dlo_off = p.dy_bytes;
+  const int j = gt & (PX - 1);
+  const int lx = 31 - __clz(PX);
+  const int QS = kGroupThreads >> lx, q0 = gt >> lx;
+  int cx = ci0 + j * 4;
+  const SrcDev* sp = &p.S.s[0];
+  if (p.S.nsrc > 1 && cx >= p.S.s[0].C) { sp = &p.S.s[1]; cx -= p.S.s[0].C; }
+  float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (sp->scale != nullptr) {
+    sc = __ldg(reinterpret_cast<const float4*>(sp->scale + cx));
+    sh = __ldg(reinterpret_cast<const float4*>(sp->shift + cx));
+  }
+  const float* xsrc = sp->ptr + cx;
+  const uint32_t xld = sp->ld;
+  uint32_t pix[UX];
+#pragma unroll
+  for (int u = 0; u < UX; ++u) {
+    const uint32_t q = min((uint32_t)(q0 + u * QS), (uint32_t)(HP - 1));
+    const uint32_t hh = fdiv(q, p.TWp, mulT), ww = q - hh * p.TWp;
+    pix[u] = (hh * (uint32_t)W + ww) * xld;
+  }
+  const bool last_valid = q0 + (UX - 1) * QS < HP;
+  const uint32_t x_dst0 = (uint32_t)q0 * 128 + (stacked ? 0u : (uint32_t)(j >> 3) * p.x_chunk) +
+                          (((uint32_t)(j & 7) << 4) ^ ((uint32_t)(q0 & 3) << 5));
+  const uint32_t x_step = (uint32_t)QS * 128;
+  constexpr int ld_ = UD == 4 ? 2 : (UD == 8 ? 3 : (UD == 16 ? 4 : 5));
+  const int jd = gt & (PD - 1);
+  constexpr int QD = kGroupThreads >> ld_;
+  const int pd0 = gt >> ld_;
+  const uint32_t d_rel = p.x_bytes * (X3 ? 2 : 1) + (p.fs ? p.dpad * 1024 : 0);
+  const uint32_t d_dst0 = d_rel + (uint32_t)pd0 * 128 + (uint32_t)(jd >> 3) * kChunk +
+                          (((uint32_t)(jd & 7) << 4) ^ ((uint32_t)(pd0 & 3) << 5));
+  constexpr uint32_t d_step = (uint32_t)QD * 128;
+  const float* dsrc = p.dy + co0 + jd * 4;
+  const uint32_t dld = p.ld_dy;
+  uint32_t st = grp % S, ph = ((grp / S) & 1) ^ 1;
+  for (int tile = t_begin + grp * ts; tile < t_end; tile += n_groups * ts) {
+    const uint32_t x0 = base + st * p.stage_bytes;
+    const int n = (int)fdiv(tile, tpi, mulTpi);
+    const int rem = tile - n * tpi;
+    const int th_i = (int)fdiv(rem, p.tiles_w, mulTw);
+    const int tw_i = rem - th_i * p.tiles_w;
+    const int h0 = th_i * kTileH, w0 = tw_i * kTileW;
+    const int h_org = h0 - p.dil * (p.taps_h >> 1), w_org = w0 - p.dil * (p.taps_w >> 1);
+    const bool interior = h_org >= 0 && w_org >= 0 && h_org + p.THp <= H && w_org + p.TWp <= W;
+    const bool dfull = h0 + kTileH <= H && w0 + kTileW <= W;
+    float4 v[UX];
+    if (interior) {
+      const float* tb = xsrc + ((size_t)(n * H + h_org) * W + w_org) * xld;
+#pragma unroll
+      for (int u = 0; u < UX; ++u) {
+        if (u < UX - 1 || last_valid) v[u] = __ldg(reinterpret_cast<const float4*>(tb + pix[u]));
+      }
+#pragma unroll
+      for (int u = 0; u < UX; ++u) {
+        v[u].x = fmaf(v[u].x, sc.x, sh.x); v[u].y = fmaf(v[u].y, sc.y, sh.y);
+        v[u].z = fmaf(v[u].z, sc.z, sh.z); v[u].w = fmaf(v[u].w, sc.w, sh.w);
+      }
+    } else {
+      uint32_t okm = 0;
+#pragma unroll
+      for (int u = 0; u < UX; ++u) {
+        const uint32_t q = min((uint32_t)(q0 + u * QS), (uint32_t)(HP - 1));   // border tiles: recompute
+        const uint32_t hh = fdiv(q, p.TWp, mulT), ww = q - hh * p.TWp;
+        const int gh = h_org + (int)hh, gw = w_org + (int)ww;
+        const bool ok = (unsigned)gh < (unsigned)H && (unsigned)gw < (unsigned)W;
+        const int ghc = min(max(gh, 0), H - 1), gwc = min(max(gw, 0), W - 1);
+        if (u < UX - 1 || last_valid)
+          v[u] = __ldg(reinterpret_cast<const float4*>(xsrc + ((size_t)(n * H + ghc) * W + gwc) * xld));
+        okm |= (ok ? 1u : 0u) << u;
+      }
+#pragma unroll
+      for (int u = 0; u < UX; ++u) {
+        const bool ok = (okm >> u) & 1u;
+        v[u].x = ok ? fmaf(v[u].x, sc.x, sh.x) : 0.f; v[u].y = ok ? fmaf(v[u].y, sc.y, sh.y) : 0.f;
+        v[u].z = ok ? fmaf(v[u].z, sc.z, sh.z) : 0.f; v[u].w = ok ? fmaf(v[u].w, sc.w, sh.w) : 0.f;
+      }
+    }
+    // first batch of dy elements rides along with the x loads
+    constexpr int DB = 4;
+    float4 dv[DB];
+    uint32_t dokm = 0;
+    auto load_dy = [&](int ub) {
+      dokm = 0;
+      const size_t img = (size_t)n * H;
+#pragma unroll
+      for (int k = 0; k < DB; ++k) {
+        const int pd = pd0 + (ub + k) * QD;
+        const int gh = h0 + (pd >> 3), gw = w0 + (pd & 7);
+        if (dfull) {
+          dv[k] = __ldg(reinterpret_cast<const float4*>(dsrc + ((img + gh) * W + gw) * dld));
+          dokm |= 1u << k;
+        } else {
+          const bool ok = gh < H && gw < W;
+          dv[k] = __ldg(reinterpret_cast<const float4*>(dsrc + ((img + min(gh, H - 1)) * W + min(gw, W - 1)) * dld));
+          dokm |= (ok ? 1u : 0u) << k;
+        }
+      }
+    };
+    auto store_dy = [&](int ub) {
+#pragma unroll
+      for (int k = 0; k < DB; ++k) {
+        const uint32_t msk = ((dokm >> k) & 1u) ? 0xFFFFFFFFu : 0u;
+        const uint32_t dst = x0 + d_dst0 + (uint32_t)(ub + k) * d_step;
+        sts128u(dst, tf32b(dv[k].x) & msk, tf32b(dv[k].y) & msk, tf32b(dv[k].z) & msk, tf32b(dv[k].w) & msk);
+        if (X3) {
+          const float4 l = part4(dv[k], true);
+          sts128u(dst + dlo_off, tf32b(l.x) & msk, tf32b(l.y) & msk, tf32b(l.z) & msk, tf32b(l.w) & msk);
+        }
+      }
+    };
+    load_dy(0);
+    mbar_wait(smem_u32(&ctl->empty[st]), ph);
+#pragma unroll
+    for (int u = 0; u < UX; ++u) {
+      if (u < UX - 1 || last_valid) {
+        const uint32_t dst = x0 + x_dst0 + (uint32_t)u * x_step;
+        sts128u(dst, tf32b(v[u].x), tf32b(v[u].y), tf32b(v[u].z), tf32b(v[u].w));
+        if (X3) {
+          const float4 l = part4(v[u], true);
+          sts128u(dst + xlo_off, tf32b(l.x), tf32b(l.y), tf32b(l.z), tf32b(l.w));
+        }
+      }
+    }
+    store_dy(0);
+#pragma unroll
+    for (int ub = DB; ub < UD; ub += DB) {
+      load_dy(ub);
+      store_dy(ub);
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(smem_u32(&ctl->full[st]));
+    st += n_groups;
+    while (st >= S) { st -= S; ph ^= 1; }
+  }
+}
+
+template <int UX, bool X3>
+__device__ __forceinline__ void wgrad_loader_ct_ud(const WgradTcParams& p, Ctl* ctl, uint32_t base,
+                                                   int grp, int gt, int t_begin, int t_end, int ts,
+                                                   int co0, int ci0, int PD, int PX) {
+  if (PD == 4) wgrad_loader_ct<UX, 4, X3>(p, ctl, base, grp, gt, t_begin, t_end, ts, co0, ci0, PX);
+  else if (PD == 8) wgrad_loader_ct<UX, 8, X3>(p, ctl, base, grp, gt, t_begin, t_end, ts, co0, ci0, PX);
+  else if (PD == 16) wgrad_loader_ct<UX, 16, X3>(p, ctl, base, grp, gt, t_begin, t_end, ts, co0, ci0, PX);
+  else wgrad_loader_ct<UX, 32, X3>(p, ctl, base, grp, gt, t_begin, t_end, ts, co0, ci0, PX);
+}
+
 __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const WgradTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   Ctl* ctl = reinterpret_cast<Ctl*>(smem);
@@ -637,7 +840,14 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const WgradTcPara
     if (pow2 && !p.legacy_loader) {
       // elements per thread per tile: pooled sources keep 4 loads per element in flight
       const int ux = (p.HP * PX + kGroupThreads - 1) / kGroupThreads;
-      if (pooled) wgrad_loader_elem<4>(p, ctl, base, grp, gt, t_begin, t_end, ts, co0, ci0, PD, PX);
+      const int qs = kGroupThreads / PX;
+      const int uxe = (p.HP + qs - 1) / qs;       // exact halo elements per thread
+      const bool ct = !pooled && !p.x3 && PD >= 4 && !p.rt_loader &&
+                      (uxe == 6 || uxe == 8 || uxe == 12);
+      if (ct && uxe == 6) wgrad_loader_ct_ud<6, false>(p, ctl, base, grp, gt, t_begin, t_end, ts, co0, ci0, PD, PX);
+      else if (ct && uxe == 8) wgrad_loader_ct_ud<8, false>(p, ctl, base, grp, gt, t_begin, t_end, ts, co0, ci0, PD, PX);
+      else if (ct && uxe == 12) wgrad_loader_ct_ud<12, false>(p, ctl, base, grp, gt, t_begin, t_end, ts, co0, ci0, PD, PX);
+      else if (pooled) wgrad_loader_elem<4>(p, ctl, base, grp, gt, t_begin, t_end, ts, co0, ci0, PD, PX);
       else if (ux <= 8) wgrad_loader_elem<8>(p, ctl, base, grp, gt, t_begin, t_end, ts, co0, ci0, PD, PX);
       else if (ux <= 12) wgrad_loader_elem<12>(p, ctl, base, grp, gt, t_begin, t_end, ts, co0, ci0, PD, PX);
       else wgrad_loader_elem<16>(p, ctl, base, grp, gt, t_begin, t_end, ts, co0, ci0, PD, PX);
@@ -751,8 +961,11 @@ int wgrad_plan(const ab_conv_t* d, WgradTcParams* p, int* smem_bytes) {
   {
     const char* e = getenv("ATOMAI_B200_WGRAD_LOADER");
     p->legacy_loader = (e && e[0] == '0') ? 1 : 0;
+    p->rt_loader = (e && e[0] == '1') ? 1 : 0;
     const char* o = getenv("ATOMAI_B200_WGRAD_ORDER");
     p->interleave = (o && o[0] == '0') ? 0 : 1;
+    const char* f = getenv("ATOMAI_B200_WGRAD_PF");
+    p->l2_prefetch = (f && f[0] == '1') ? 1 : 0;
   }
   AB_CHECK(d->ks_w <= 4 && d->ks_h <= 4, "wgrad_tc: kernel %dx%d too large", d->ks_h, d->ks_w);
   p->tiles_h = (d->H + kTileH - 1) / kTileH;

@@ -173,6 +173,11 @@ def run_group(name):
         conv_case("c1_dil2", M, 2, 24, 30, [1], 16, dil=2)
         conv_case("c1_big", M, 4, 256, 256, [1], 16)
         conv_case("px_16to3", M, 2, 40, 48, [16], 3, ks=1, lrelu=1.0, stats=False)
+        conv_case("c1_1to64_affine", M, 2, 40, 48, [1], 64, affine=True)      # ImSpec / VAE first layers
+        conv_case("c1_1to128", M, 2, 33, 29, [1], 128)
+        conv_case("pw_128to1", M, 2, 40, 48, [128], 1, ks=1, lrelu=1.0, stats=False)   # rDecoder output layer
+        conv_case("pw_1to128", M, 2, 40, 48, [1], 128, ks=1, lrelu=1.0, stats=False)   # ... and its dgrad
+        conv_case("pw_1to64_stats", M, 2, 24, 30, [1], 64, ks=1)
         conv_case("mid_24to20_dil2", M, 2, 33, 29, [24], 20, dil=2)
         conv_case("cat_affine_pool", M, 2, 16, 24, [8, 12], 16, affine=True, pool=True)
         conv_case("nchw_out", M, 2, 16, 24, [8], 16, nchw_out=True, stats=False)
