@@ -655,6 +655,53 @@ __global__ void __launch_bounds__(kT) upsample_fwd_vec_kernel(const float* __res
   }
 }
 
+// One thread per LOW-res pixel and 4 channels: the 2 x 2 output block it covers comes from its
+// 3 x 3 (edge-clamped) neighbourhood — 9 loads and one set of index arithmetic per four outputs
+// (the per-output kernel above spends 4 loads and three integer divisions on each).  Same
+// expression per output as up_src / the scalar kernel, so results are bit-identical.
+__global__ void __launch_bounds__(kT) upsample_fwd_blk_kernel(const float* __restrict__ x, int ld_x,
+                                                                float* __restrict__ y, int ld_y, int h,
+                                                                int w, int bilinear, uint32_t total,
+                                                                VIdx ix) {
+  const int W = 2 * w;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    uint32_t pix; int c4; ix.split(i, pix, c4);
+    const uint32_t iw = pix % (uint32_t)w, r = pix / (uint32_t)w, ih = r % (uint32_t)h, n = r / (uint32_t)h;
+    const float* xb = x + (size_t)n * h * w * ld_x + c4 * 4;
+    float* yb = y + ((size_t)(n * 2 * h + 2 * ih) * W + 2 * iw) * ld_y + c4 * 4;
+    const size_t yrow = (size_t)W * ld_y;
+    if (!bilinear) {
+      const float4 v = ld4(xb + ((size_t)ih * w + iw) * ld_x);
+      *reinterpret_cast<float4*>(yb) = v;
+      *reinterpret_cast<float4*>(yb + ld_y) = v;
+      *reinterpret_cast<float4*>(yb + yrow) = v;
+      *reinterpret_cast<float4*>(yb + yrow + ld_y) = v;
+      continue;
+    }
+    const int hm = ih > 0 ? (int)ih - 1 : 0, hp = (int)ih + 1 < h ? (int)ih + 1 : h - 1;
+    const int wm = iw > 0 ? (int)iw - 1 : 0, wp = (int)iw + 1 < w ? (int)iw + 1 : w - 1;
+    const float* rm = xb + (size_t)hm * w * ld_x;
+    const float* r0 = xb + (size_t)ih * w * ld_x;
+    const float* rp = xb + (size_t)hp * w * ld_x;
+    const float4 mm = ld4(rm + (size_t)wm * ld_x), m0 = ld4(rm + (size_t)iw * ld_x), mp = ld4(rm + (size_t)wp * ld_x);
+    const float4 zm = ld4(r0 + (size_t)wm * ld_x), z0 = ld4(r0 + (size_t)iw * ld_x), zp = ld4(r0 + (size_t)wp * ld_x);
+    const float4 pm = ld4(rp + (size_t)wm * ld_x), p0 = ld4(rp + (size_t)iw * ld_x), pp = ld4(rp + (size_t)wp * ld_x);
+    // even output index 2i: (x[i-1], x[i], l = 0.75)  [i = 0: l = 0];  odd 2i+1: (x[i], x[i+1], l = 0.25)
+    const float lhe = ih > 0 ? 0.75f : 0.f, lwe = iw > 0 ? 0.75f : 0.f;
+    auto mix = [](float a, float b, float c, float d, float lh, float lw) {
+      return (1.f - lh) * ((1.f - lw) * a + lw * b) + lh * ((1.f - lw) * c + lw * d);
+    };
+    auto mix4 = [&](float4 a, float4 b, float4 c, float4 d, float lh, float lw) {
+      return make_float4(mix(a.x, b.x, c.x, d.x, lh, lw), mix(a.y, b.y, c.y, d.y, lh, lw),
+                         mix(a.z, b.z, c.z, d.z, lh, lw), mix(a.w, b.w, c.w, d.w, lh, lw));
+    };
+    *reinterpret_cast<float4*>(yb) = mix4(mm, m0, zm, z0, lhe, lwe);
+    *reinterpret_cast<float4*>(yb + ld_y) = mix4(m0, mp, z0, zp, lhe, 0.25f);
+    *reinterpret_cast<float4*>(yb + yrow) = mix4(zm, z0, pm, p0, 0.25f, lwe);
+    *reinterpret_cast<float4*>(yb + yrow + ld_y) = mix4(z0, zp, p0, pp, 0.25f, 0.25f);
+  }
+}
+
 __global__ void __launch_bounds__(kT) upsample_bwd_vec_kernel(const float* __restrict__ dy, int ld_dy, float* __restrict__ dx, int ld_dx,
                                         int h, int w, int bilinear, uint32_t total, VIdx ix) {
   const int H = 2 * h, W = 2 * w;
@@ -820,8 +867,9 @@ int atomai_b200_upsample2x_fwd(const float* x, int ld_x, float* y, int ld_y, int
   const int64_t total = (int64_t)N * 4 * h * w * C;
   if (total == 0) return 0;
   if (vec_ok(C, {x, y}, {ld_x, ld_y}, total / 4)) {
-    upsample_fwd_vec_kernel<<<grid_for(total / 4), kT, 0, STREAM>>>(x, ld_x, y, ld_y, h, w, bilinear,
-                                                                  (uint32_t)(total / 4), make_vidx(C));
+    const int64_t lo = (int64_t)N * h * w * (C / 4);        // one thread per low-res float4
+    upsample_fwd_blk_kernel<<<grid_for(lo), kT, 0, STREAM>>>(x, ld_x, y, ld_y, h, w, bilinear,
+                                                            (uint32_t)lo, make_vidx(C));
     AB_LAUNCH_CHECK();
     return 0;
   }

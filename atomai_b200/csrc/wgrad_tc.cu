@@ -757,6 +757,166 @@ __device__ __forceinline__ void wgrad_loader_ct(const WgradTcParams& p, Ctl* ctl
   }
 }
 
+// Batched variant of wgrad_loader_ct for the shapes whose elements do not fit the register file
+// at once: pooled sources (four loads per element: 2x2 max of the affine'd window) and the 1x1
+// layers with 128 input channels per CTA (32 elements per thread).  XB elements are in flight;
+// halo offsets are recomputed per element (4 integer instructions), everything else as above.
+template <int UX, int XB, int UD, bool POOL>
+__device__ __forceinline__ void wgrad_loader_ctb(const WgradTcParams& p, Ctl* ctl, uint32_t base,
+                                                 int grp, int gt, int t_begin, int t_end, int ts,
+                                                 int co0, int ci0, int PX) {
+  constexpr int PD = UD;
+  const int lane = threadIdx.x & 31;
+  const bool stacked = p.taps_w > 1;
+  const int H = p.H, W = p.W, HP = p.HP;
+  const int tpi = p.tiles_w * p.tiles_h;
+  const uint32_t mulTpi = fdiv_mul(tpi), mulTw = fdiv_mul(p.tiles_w), mulT = fdiv_mul(p.TWp);
+  const uint32_t S = p.n_stages;
+  const int n_groups = S >= (uint32_t)kGroups ? kGroups : 2;
+  if (grp >= n_groups) return;
+  const int j = gt & (PX - 1);
+  const int lx = 31 - __clz(PX);
+  const int QS = kGroupThreads >> lx, q0 = gt >> lx;
+  int cx = ci0 + j * 4;
+  const SrcDev* sp = &p.S.s[0];
+  if (p.S.nsrc > 1 && cx >= p.S.s[0].C) { sp = &p.S.s[1]; cx -= p.S.s[0].C; }
+  float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (sp->scale != nullptr) {
+    sc = __ldg(reinterpret_cast<const float4*>(sp->scale + cx));
+    sh = __ldg(reinterpret_cast<const float4*>(sp->shift + cx));
+  }
+  const float* xsrc = sp->ptr + cx;
+  const uint32_t xld = sp->ld;
+  const bool last_valid = q0 + (UX - 1) * QS < HP;
+  const uint32_t x_dst0 = (uint32_t)q0 * 128 + (stacked ? 0u : (uint32_t)(j >> 3) * p.x_chunk) +
+                          (((uint32_t)(j & 7) << 4) ^ ((uint32_t)(q0 & 3) << 5));
+  const uint32_t x_step = (uint32_t)QS * 128;
+  constexpr int ld_ = UD == 4 ? 2 : (UD == 8 ? 3 : (UD == 16 ? 4 : 5));
+  const int jd = gt & (PD - 1);
+  constexpr int QD = kGroupThreads >> ld_;
+  const int pd0 = gt >> ld_;
+  const uint32_t d_rel = p.x_bytes + (p.fs ? p.dpad * 1024 : 0);
+  const uint32_t d_dst0 = d_rel + (uint32_t)pd0 * 128 + (uint32_t)(jd >> 3) * kChunk +
+                          (((uint32_t)(jd & 7) << 4) ^ ((uint32_t)(pd0 & 3) << 5));
+  constexpr uint32_t d_step = (uint32_t)QD * 128;
+  const float* dsrc = p.dy + co0 + jd * 4;
+  const uint32_t dld = p.ld_dy;
+  const int Hs = POOL ? 2 * H : H, Ws = POOL ? 2 * W : W;       // source extent
+  const size_t rs = (size_t)Ws * xld;
+  uint32_t st = grp % S, ph = ((grp / S) & 1) ^ 1;
+  for (int tile = t_begin + grp * ts; tile < t_end; tile += n_groups * ts) {
+    const uint32_t x0 = base + st * p.stage_bytes;
+    const int n = (int)fdiv(tile, tpi, mulTpi);
+    const int rem = tile - n * tpi;
+    const int th_i = (int)fdiv(rem, p.tiles_w, mulTw);
+    const int tw_i = rem - th_i * p.tiles_w;
+    const int h0 = th_i * kTileH, w0 = tw_i * kTileW;
+    const int h_org = h0 - p.dil * (p.taps_h >> 1), w_org = w0 - p.dil * (p.taps_w >> 1);
+    const bool interior = h_org >= 0 && w_org >= 0 && h_org + p.THp <= H && w_org + p.TWp <= W;
+    const bool dfull = h0 + kTileH <= H && w0 + kTileW <= W;
+    const float* img = xsrc + (size_t)n * Hs * rs;
+    constexpr int DB = 4;
+    float4 dv[DB];
+    uint32_t dokm = 0;
+    auto load_dy = [&](int ub) {
+      dokm = 0;
+      const size_t im = (size_t)n * H;
+#pragma unroll
+      for (int k = 0; k < DB; ++k) {
+        const int pd = pd0 + (ub + k) * QD;
+        const int gh = h0 + (pd >> 3), gw = w0 + (pd & 7);
+        const bool ok = dfull || (gh < H && gw < W);
+        dv[k] = __ldg(reinterpret_cast<const float4*>(dsrc + ((im + min(gh, H - 1)) * W + min(gw, W - 1)) * dld));
+        dokm |= (ok ? 1u : 0u) << k;
+      }
+    };
+    auto store_dy = [&](int ub) {
+#pragma unroll
+      for (int k = 0; k < DB; ++k) {
+        const uint32_t msk = ((dokm >> k) & 1u) ? 0xFFFFFFFFu : 0u;
+        sts128u(x0 + d_dst0 + (uint32_t)(ub + k) * d_step, tf32b(dv[k].x) & msk, tf32b(dv[k].y) & msk,
+                tf32b(dv[k].z) & msk, tf32b(dv[k].w) & msk);
+      }
+    };
+#pragma unroll
+    for (int ub = 0; ub < UX; ub += XB) {
+      float4 v[XB];
+      uint32_t okm = 0;
+#pragma unroll
+      for (int k = 0; k < XB; ++k) {
+        const int u = ub + k;
+        if (u < UX && (u < UX - 1 || last_valid)) {
+          const uint32_t q = (uint32_t)(q0 + u * QS);
+          const uint32_t hh = fdiv(q, p.TWp, mulT), ww = q - hh * p.TWp;
+          const int gh = h_org + (int)hh, gw = w_org + (int)ww;
+          const bool ok = interior || ((unsigned)gh < (unsigned)H && (unsigned)gw < (unsigned)W);
+          const int ghc = interior ? gh : min(max(gh, 0), H - 1);
+          const int gwc = interior ? gw : min(max(gw, 0), W - 1);
+          okm |= (ok ? 1u : 0u) << k;
+          if (!POOL) {
+            v[k] = __ldg(reinterpret_cast<const float4*>(img + (size_t)ghc * rs + (size_t)gwc * xld));
+          } else {
+            const float* q0p = img + (size_t)(2 * ghc) * rs + (size_t)(2 * gwc) * xld;
+            const float4 a0 = __ldg(reinterpret_cast<const float4*>(q0p));
+            const float4 a1 = __ldg(reinterpret_cast<const float4*>(q0p + xld));
+            const float4 a2 = __ldg(reinterpret_cast<const float4*>(q0p + rs));
+            const float4 a3 = __ldg(reinterpret_cast<const float4*>(q0p + rs + xld));
+            // affine BEFORE the max (a negative BatchNorm scale flips the order)
+            v[k].x = fmaxf(fmaxf(fmaf(a0.x, sc.x, sh.x), fmaf(a1.x, sc.x, sh.x)),
+                           fmaxf(fmaf(a2.x, sc.x, sh.x), fmaf(a3.x, sc.x, sh.x)));
+            v[k].y = fmaxf(fmaxf(fmaf(a0.y, sc.y, sh.y), fmaf(a1.y, sc.y, sh.y)),
+                           fmaxf(fmaf(a2.y, sc.y, sh.y), fmaf(a3.y, sc.y, sh.y)));
+            v[k].z = fmaxf(fmaxf(fmaf(a0.z, sc.z, sh.z), fmaf(a1.z, sc.z, sh.z)),
+                           fmaxf(fmaf(a2.z, sc.z, sh.z), fmaf(a3.z, sc.z, sh.z)));
+            v[k].w = fmaxf(fmaxf(fmaf(a0.w, sc.w, sh.w), fmaf(a1.w, sc.w, sh.w)),
+                           fmaxf(fmaf(a2.w, sc.w, sh.w), fmaf(a3.w, sc.w, sh.w)));
+          }
+        }
+      }
+      if (ub == 0) {
+        load_dy(0);
+        mbar_wait(smem_u32(&ctl->empty[st]), ph);
+      }
+#pragma unroll
+      for (int k = 0; k < XB; ++k) {
+        const int u = ub + k;
+        if (u < UX && (u < UX - 1 || last_valid)) {
+          const bool ok = (okm >> k) & 1u;
+          float4 r = v[k];
+          if (!POOL) {
+            r.x = fmaf(r.x, sc.x, sh.x); r.y = fmaf(r.y, sc.y, sh.y);
+            r.z = fmaf(r.z, sc.z, sh.z); r.w = fmaf(r.w, sc.w, sh.w);
+          }
+          const uint32_t m = ok ? 0xFFFFFFFFu : 0u;
+          sts128u(x0 + x_dst0 + (uint32_t)u * x_step, tf32b(r.x) & m, tf32b(r.y) & m, tf32b(r.z) & m,
+                  tf32b(r.w) & m);
+        }
+      }
+      if (ub == 0) store_dy(0);
+    }
+#pragma unroll
+    for (int ub = DB; ub < UD; ub += DB) {
+      load_dy(ub);
+      store_dy(ub);
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(smem_u32(&ctl->full[st]));
+    st += n_groups;
+    while (st >= S) { st -= S; ph ^= 1; }
+  }
+}
+
+template <int UX, int XB, bool POOL>
+__device__ __forceinline__ void wgrad_loader_ctb_ud(const WgradTcParams& p, Ctl* ctl, uint32_t base,
+                                                    int grp, int gt, int t_begin, int t_end, int ts,
+                                                    int co0, int ci0, int PD, int PX) {
+  if (PD == 4) wgrad_loader_ctb<UX, XB, 4, POOL>(p, ctl, base, grp, gt, t_begin, t_end, ts, co0, ci0, PX);
+  else if (PD == 8) wgrad_loader_ctb<UX, XB, 8, POOL>(p, ctl, base, grp, gt, t_begin, t_end, ts, co0, ci0, PX);
+  else if (PD == 16) wgrad_loader_ctb<UX, XB, 16, POOL>(p, ctl, base, grp, gt, t_begin, t_end, ts, co0, ci0, PX);
+  else wgrad_loader_ctb<UX, XB, 32, POOL>(p, ctl, base, grp, gt, t_begin, t_end, ts, co0, ci0, PX);
+}
+
 template <int UX, bool X3>
 __device__ __forceinline__ void wgrad_loader_ct_ud(const WgradTcParams& p, Ctl* ctl, uint32_t base,
                                                    int grp, int gt, int t_begin, int t_end, int ts,
@@ -840,6 +1000,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const WgradTcPara
     if (pow2 && !p.legacy_loader) {
       // elements per thread per tile: pooled sources keep 4 loads per element in flight
       const int ux = (p.HP * PX + kGroupThreads - 1) / kGroupThreads;
+      const bool all_pooled = p.S.s[0].pool == 1 && (p.S.nsrc == 1 || p.S.s[1].pool == 1);
       const int qs = kGroupThreads / PX;
       const int uxe = (p.HP + qs - 1) / qs;       // exact halo elements per thread
       const bool ct = !pooled && !p.x3 && PD >= 4 && !p.rt_loader &&
@@ -847,6 +1008,14 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const WgradTcPara
       if (ct && uxe == 6) wgrad_loader_ct_ud<6, false>(p, ctl, base, grp, gt, t_begin, t_end, ts, co0, ci0, PD, PX);
       else if (ct && uxe == 8) wgrad_loader_ct_ud<8, false>(p, ctl, base, grp, gt, t_begin, t_end, ts, co0, ci0, PD, PX);
       else if (ct && uxe == 12) wgrad_loader_ct_ud<12, false>(p, ctl, base, grp, gt, t_begin, t_end, ts, co0, ci0, PD, PX);
+      else if (!p.x3 && PD >= 4 && !p.rt_loader && !pooled && uxe == 32)
+        wgrad_loader_ctb_ud<32, 4, false>(p, ctl, base, grp, gt, t_begin, t_end, ts, co0, ci0, PD, PX);
+      else if (!p.x3 && PD >= 4 && !p.rt_loader && !pooled && uxe == 16)
+        wgrad_loader_ctb_ud<16, 8, false>(p, ctl, base, grp, gt, t_begin, t_end, ts, co0, ci0, PD, PX);
+      else if (!p.x3 && PD >= 4 && !p.rt_loader && all_pooled && uxe == 6)
+        wgrad_loader_ctb_ud<6, 3, true>(p, ctl, base, grp, gt, t_begin, t_end, ts, co0, ci0, PD, PX);
+      else if (!p.x3 && PD >= 4 && !p.rt_loader && all_pooled && uxe == 12)
+        wgrad_loader_ctb_ud<12, 3, true>(p, ctl, base, grp, gt, t_begin, t_end, ts, co0, ci0, PD, PX);
       else if (pooled) wgrad_loader_elem<4>(p, ctl, base, grp, gt, t_begin, t_end, ts, co0, ci0, PD, PX);
       else if (ux <= 8) wgrad_loader_elem<8>(p, ctl, base, grp, gt, t_begin, t_end, ts, co0, ci0, PD, PX);
       else if (ux <= 12) wgrad_loader_elem<12>(p, ctl, base, grp, gt, t_begin, t_end, ts, co0, ci0, PD, PX);
