@@ -346,6 +346,23 @@ __device__ __forceinline__ float4 load_up4(const float* __restrict__ ptr_c, int 
   return lerp2_4(a, b, c, d, lh, lw);
 }
 
+static __device__ __noinline__ float4 load_up4_noinline(const float* __restrict__ ptr_c, int ld, int mode,
+                                                 int n, int h, int w, int H, int W) {
+  return load_up4(ptr_c, ld, mode, n, h, w, H, W);
+}
+static __device__ __noinline__ float load_up1_noinline(const float* __restrict__ ptr_c, int ld, int mode,
+                                                int n, int h, int w, int H, int W) {
+  const int Hl = H >> 1, Wl = W >> 1;
+  int h0, h1, w0, w1;
+  float lh, lw;
+  up2_coord(h, Hl, mode == AB_SRC_UP_BILINEAR, h0, h1, lh);
+  up2_coord(w, Wl, mode == AB_SRC_UP_BILINEAR, w0, w1, lw);
+  const float* r0 = ptr_c + (size_t)(n * Hl + h0) * Wl * ld;
+  const float* r1 = ptr_c + (size_t)(n * Hl + h1) * Wl * ld;
+  return lerp2(__ldg(r0 + (size_t)w0 * ld), __ldg(r0 + (size_t)w1 * ld), __ldg(r1 + (size_t)w0 * ld),
+               __ldg(r1 + (size_t)w1 * ld), lh, lw);
+}
+
 // 4 consecutive channels [c, c+4) of the logical (post-affine, post-pool, zero padded)
 // input at pixel (n, h, w) of an H x W grid.  c must be a multiple of 4 and every source's
 // C a multiple of 4 on this vector path.
@@ -364,7 +381,9 @@ __device__ __forceinline__ float4 load_src4(const SrcSet& S, int n, int h, int w
     sh = __ldg(reinterpret_cast<const float4*>(s->shift + c));
   }
   if (s->pool >= AB_SRC_UP_BILINEAR) {
-    const float4 v = load_up4(s->ptr + c, s->ld, s->pool, n, h, w, H, W);
+    // out of line: inlined, the four extra loads and the interpolation cost the thin-channel
+    // kernels 12-20 registers (conv_pix<16>: 128 -> 148, one CTA per SM instead of two)
+    const float4 v = load_up4_noinline(s->ptr + c, s->ld, s->pool, n, h, w, H, W);
     r.x = fmaf(v.x, sc.x, sh.x);
     r.y = fmaf(v.y, sc.y, sh.y);
     r.z = fmaf(v.z, sc.z, sh.z);
@@ -409,18 +428,8 @@ __device__ __forceinline__ float load_src1(const SrcSet& S, int n, int h, int w,
     sc = __ldg(s->scale + c);
     sh = __ldg(s->shift + c);
   }
-  if (s->pool >= AB_SRC_UP_BILINEAR) {
-    const int Hl = H >> 1, Wl = W >> 1;
-    int h0, h1, w0, w1;
-    float lh, lw;
-    up2_coord(h, Hl, s->pool == AB_SRC_UP_BILINEAR, h0, h1, lh);
-    up2_coord(w, Wl, s->pool == AB_SRC_UP_BILINEAR, w0, w1, lw);
-    const float* r0 = s->ptr + (size_t)(n * Hl + h0) * Wl * s->ld + c;
-    const float* r1 = s->ptr + (size_t)(n * Hl + h1) * Wl * s->ld + c;
-    const float v = lerp2(__ldg(r0 + (size_t)w0 * s->ld), __ldg(r0 + (size_t)w1 * s->ld),
-                          __ldg(r1 + (size_t)w0 * s->ld), __ldg(r1 + (size_t)w1 * s->ld), lh, lw);
-    return fmaf(v, sc, sh);
-  }
+  if (s->pool >= AB_SRC_UP_BILINEAR)
+    return fmaf(load_up1_noinline(s->ptr + c, s->ld, s->pool, n, h, w, H, W), sc, sh);
   if (!s->pool) {
     return fmaf(__ldg(s->ptr + ((size_t)(n * H + h) * W + w) * s->ld + c), sc, sh);
   }

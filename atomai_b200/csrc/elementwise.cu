@@ -482,7 +482,6 @@ __device__ __forceinline__ float4 f4max(float4 a, float4 b) {
   return make_float4(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z), fmaxf(a.w, b.w));
 }
 __device__ __forceinline__ float4 f4add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
-__device__ __forceinline__ float4 f4scale(float4 a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
 
 __global__ void __launch_bounds__(kT) affine_vec_kernel(const float* __restrict__ a, int ld_a, const float* scale,
                                   const float* shift, float* __restrict__ y, int ld_y, uint32_t total, VIdx ix) {
@@ -625,33 +624,6 @@ __global__ void __launch_bounds__(kT) pool_bwd_vec_kernel(const float* __restric
       float4* q = reinterpret_cast<float4*>(df + (base + off[k]) * ld_df + c4 * 4);
       *q = accumulate ? f4add(*q, o[k]) : o[k];
     }
-  }
-}
-
-__global__ void __launch_bounds__(kT) upsample_fwd_vec_kernel(const float* __restrict__ x, int ld_x, float* __restrict__ y, int ld_y,
-                                        int h, int w, int bilinear, uint32_t total, VIdx ix) {
-  const int H = 2 * h, W = 2 * w;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    uint32_t pix; int c4; ix.split(i, pix, c4);
-    const uint32_t ow = pix % W, r = pix / W, oh = r % H, n = r / H;
-    const float* xb = x + (size_t)n * h * w * ld_x + c4 * 4;
-    float4 v;
-    if (bilinear) {
-      int h0, h1, w0, w1; float lh, lw;
-      up_src((int)oh, h, h0, h1, lh);
-      up_src((int)ow, w, w0, w1, lw);
-      const float4 x00 = ld4(xb + ((size_t)h0 * w + w0) * ld_x), x01 = ld4(xb + ((size_t)h0 * w + w1) * ld_x);
-      const float4 x10 = ld4(xb + ((size_t)h1 * w + w0) * ld_x), x11 = ld4(xb + ((size_t)h1 * w + w1) * ld_x);
-      const float a0 = (1.f - lh) * (1.f - lw), a1 = (1.f - lh) * lw, a2 = lh * (1.f - lw), a3 = lh * lw;
-      v.x = (1.f - lh) * ((1.f - lw) * x00.x + lw * x01.x) + lh * ((1.f - lw) * x10.x + lw * x11.x);
-      v.y = (1.f - lh) * ((1.f - lw) * x00.y + lw * x01.y) + lh * ((1.f - lw) * x10.y + lw * x11.y);
-      v.z = (1.f - lh) * ((1.f - lw) * x00.z + lw * x01.z) + lh * ((1.f - lw) * x10.z + lw * x11.z);
-      v.w = (1.f - lh) * ((1.f - lw) * x00.w + lw * x01.w) + lh * ((1.f - lw) * x10.w + lw * x11.w);
-      (void)a0; (void)a1; (void)a2; (void)a3;
-    } else {
-      v = ld4(xb + ((size_t)(oh >> 1) * w + (ow >> 1)) * ld_x);
-    }
-    *reinterpret_cast<float4*>(y + (size_t)pix * ld_y + c4 * 4) = v;
   }
 }
 

@@ -227,14 +227,21 @@ __device__ __forceinline__ void grid_xy(const CoordDev& d, int p, float& gx, flo
   gx = d.H > 1 ? -1.f + 2.f * i / (float)(d.H - 1) : -1.f;
   gy = d.W > 1 ? 1.f - 2.f * j / (float)(d.W - 1) : 1.f;
 }
-__device__ __forceinline__ void xform(const CoordDev& d, int b, float gx, float gy, float& x,
-                                      float& y, float& c, float& s) {
-  c = 1.f; s = 0.f;
-  if (d.phi) { sincosf(d.phi[b], &s, &c); }
+// per-sample part of transform_coordinates (hoisted out of the pixel loops: sincosf alone was a
+// third of the instructions of these kernels)
+struct Xf { float c, s, tx, ty; };
+__device__ __forceinline__ Xf xform_setup(const CoordDev& d, int b) {
+  Xf t; t.c = 1.f; t.s = 0.f; t.tx = 0.f; t.ty = 0.f;
+  if (d.phi) { sincosf(d.phi[b], &t.s, &t.c); }
+  if (d.dx) { t.tx = d.dx[b * 2]; t.ty = d.dx[b * 2 + 1]; }
+  return t;
+}
+__device__ __forceinline__ void xform(const CoordDev& d, const Xf& t, float gx, float gy, float& x,
+                                      float& y) {
   // coord @ [[c, s], [-s, c]] + dx  (atomai/utils/coords.py:78-83)
-  x = gx * c - gy * s;
-  y = gx * s + gy * c;
-  if (d.dx) { x += d.dx[b * 2]; y += d.dx[b * 2 + 1]; }
+  x = gx * t.c - gy * t.s;
+  y = gx * t.s + gy * t.c;
+  if (d.dx) { x += t.tx; y += t.ty; }
 }
 
 // grid: (pixel chunks, B); block 128 threads = hidden lanes (hid <= 1024 handled by a loop)
@@ -248,14 +255,25 @@ __global__ void coord_latent_fwd_kernel(const CoordDev d, float* __restrict__ h0
   }
   __syncthreads();
   const int p0 = blockIdx.x * px_per_cta, p1 = min(HW, p0 + px_per_cta);
+  const Xf t = xform_setup(d, b);
+  // (the common hid <= blockDim case keeps the thread's two coordinate weights in registers)
+  const int h_own = threadIdx.x < d.hid ? threadIdx.x : 0;
+  const float w0 = d.wc[h_own * 2], w1 = d.wc[h_own * 2 + 1], hz = s_hz[h_own];
   for (int p = p0; p < p1; ++p) {
-    float gx, gy, x, y, c, s;
+    float gx, gy, x, y;
     grid_xy(d, p, gx, gy);
-    xform(d, b, gx, gy, x, y, c, s);
+    xform(d, t, gx, gy, x, y);
     float* o = h0 + ((int64_t)b * HW + p) * d.hid;
-    for (int h = threadIdx.x; h < d.hid; h += blockDim.x) {
-      float v = fmaf(d.wc[h * 2], x, fmaf(d.wc[h * 2 + 1], y, s_hz[h]));
-      o[h] = d.tanh_act ? tanhf(v) : v;
+    if (d.hid <= (int)blockDim.x) {
+      if (threadIdx.x < d.hid) {
+        const float v = fmaf(w0, x, fmaf(w1, y, hz));
+        o[threadIdx.x] = d.tanh_act ? tanhf(v) : v;
+      }
+    } else {
+      for (int h = threadIdx.x; h < d.hid; h += blockDim.x) {
+        float v = fmaf(d.wc[h * 2], x, fmaf(d.wc[h * 2 + 1], y, s_hz[h]));
+        o[h] = d.tanh_act ? tanhf(v) : v;
+      }
     }
   }
 }
@@ -269,10 +287,12 @@ __global__ void coord_latent_bwd_kernel(const CoordDev d, const float* __restric
   float a_dx = 0.f, a_dy = 0.f, a_phi = 0.f;
   // per hidden lane partials (thread h owns lanes h, h+blockDim, ...; hid <= 4*blockDim)
   float s0[4] = {0, 0, 0, 0}, sx[4] = {0, 0, 0, 0}, sy[4] = {0, 0, 0, 0};
+  const Xf t = xform_setup(d, b);
+  const float c = t.c, s = t.s;
   for (int p = p0; p < p1; ++p) {
-    float gx, gy, x, y, c, s;
+    float gx, gy, x, y;
     grid_xy(d, p, gx, gy);
-    xform(d, b, gx, gy, x, y, c, s);
+    xform(d, t, gx, gy, x, y);
     const float* g = dpre + ((int64_t)b * HW + p) * d.hid;
     float px = 0.f, py = 0.f;
     int u = 0;
