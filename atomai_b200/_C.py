@@ -87,6 +87,8 @@ SIGNATURES = {
     "atomai_b200_pool2x2_fwd": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "atomai_b200_pool2x2_bwd": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i,
                                      _vp]),
+    "atomai_b200_pool2x2_bwd_bn": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i,
+                                     _vp, _vp, _vp, _vp]),
     "atomai_b200_affine_res_act": (_i, [_vp, _i, _vp, _vp, _vp, _i, _f, _vp, _i, _i64, _i, _vp]),
     "atomai_b200_lrelu_mask_bwd": (_i, [_vp, _i, _vp, _i, _f, _vp, _i, _i64, _i, _vp]),
     "atomai_b200_resize_fwd": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),

@@ -600,10 +600,22 @@ __device__ __forceinline__ void pick4(float v0, float v1, float v2, float v3, fl
   o0 = best == 0 ? g : 0.f; o1 = best == 1 ? g : 0.f; o2 = best == 2 ? g : 0.f; o3 = best == 3 ? g : 0.f;
 }
 
+// STATS: the gradient written here is the LAST contribution to d loss / d BN-output of this
+// tensor, so the BatchNorm-backward reductions (sum dY, sum dY*xhat — bn_bwd_reduce) ride along
+// and that separate pass over dY and a is not needed.  Requires C4 to be a power of two dividing
+// the block (a thread's channel quad is then a loop constant).
+template <bool STATS>
 __global__ void __launch_bounds__(kT) pool_bwd_vec_kernel(const float* __restrict__ dp, int ld_dp, const float* __restrict__ a, int ld_a,
                                     const float* scale, const float* shift, float* __restrict__ df, int ld_df,
-                                    int accumulate, int Ho, int Wo, uint32_t total, VIdx ix) {
+                                    int accumulate, int Ho, int Wo, uint32_t total, VIdx ix,
+                                    const float* mean, const float* invstd, double* sums) {
   const int W2 = 2 * Wo;
+  float4 s1 = make_float4(0, 0, 0, 0), s2 = s1, mu = s1, is = s1;
+  if (STATS) {
+    const int c4 = (int)(threadIdx.x & (uint32_t)(ix.C4 - 1));
+    mu = ld4(mean + c4 * 4);
+    is = ld4(invstd + c4 * 4);
+  }
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     uint32_t pix; int c4; ix.split(i, pix, c4);
     const uint32_t wo = pix % Wo, r = pix / Wo, ho = r % Ho, n = r / Ho;
@@ -611,9 +623,12 @@ __global__ void __launch_bounds__(kT) pool_bwd_vec_kernel(const float* __restric
     if (scale) { sc = ld4(scale + c4 * 4); sh = ld4(shift + c4 * 4); }
     const size_t base = ((size_t)n * 2 * Ho + 2 * ho) * W2 + 2 * wo;
     const size_t off[4] = {0, 1, (size_t)W2, (size_t)W2 + 1};
-    float4 v[4], o[4];
+    float4 raw[4], v[4], o[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) v[k] = f4fma(ld4(a + (base + off[k]) * ld_a + c4 * 4), sc, sh);
+    for (int k = 0; k < 4; ++k) {
+      raw[k] = ld4(a + (base + off[k]) * ld_a + c4 * 4);
+      v[k] = f4fma(raw[k], sc, sh);
+    }
     const float4 g = ld4(dp + (size_t)pix * ld_dp + c4 * 4);
     pick4(v[0].x, v[1].x, v[2].x, v[3].x, g.x, o[0].x, o[1].x, o[2].x, o[3].x);
     pick4(v[0].y, v[1].y, v[2].y, v[3].y, g.y, o[0].y, o[1].y, o[2].y, o[3].y);
@@ -622,8 +637,18 @@ __global__ void __launch_bounds__(kT) pool_bwd_vec_kernel(const float* __restric
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       float4* q = reinterpret_cast<float4*>(df + (base + off[k]) * ld_df + c4 * 4);
-      *q = accumulate ? f4add(*q, o[k]) : o[k];
+      const float4 t = accumulate ? f4add(*q, o[k]) : o[k];
+      *q = t;
+      if (STATS) {
+        s1 = f4add(s1, t);
+        s2.x = fmaf(t.x, (raw[k].x - mu.x) * is.x, s2.x); s2.y = fmaf(t.y, (raw[k].y - mu.y) * is.y, s2.y);
+        s2.z = fmaf(t.z, (raw[k].z - mu.z) * is.z, s2.z); s2.w = fmaf(t.w, (raw[k].w - mu.w) * is.w, s2.w);
+      }
     }
+  }
+  if (STATS) {
+    const int C4 = ix.C4, cx = threadIdx.x & (C4 - 1), py = threadIdx.x / C4;
+    block_chan_reduce_vec(s1, s2, cx, py, C4, kT / C4, C4, sums, sums + C4 * 4);
   }
 }
 
@@ -816,22 +841,42 @@ int atomai_b200_pool2x2_fwd(const float* a, int ld_a, const float* scale, const 
   return 0;
 }
 
-int atomai_b200_pool2x2_bwd(const float* dp, int ld_dp, const float* a, int ld_a,
-                            const float* scale, const float* shift, float* dfull, int ld_df,
-                            int accumulate, int N, int Ho, int Wo, int C, void* stream) {
+int atomai_b200_pool2x2_bwd_bn(const float* dp, int ld_dp, const float* a, int ld_a,
+                               const float* scale, const float* shift, float* dfull, int ld_df,
+                               int accumulate, int N, int Ho, int Wo, int C, const float* mean,
+                               const float* invstd, double* sums, void* stream) {
   const int64_t total = (int64_t)N * Ho * Wo * C;
   if (total == 0) return 0;
+  const bool stats = sums != nullptr;
+  AB_CHECK(!stats || (mean && invstd), "pool2x2_bwd_bn: statistics need mean and invstd");
   if (vec_ok(C, {dp, a, dfull, scale, shift}, {ld_dp, ld_a, ld_df}, total / 4)) {
-    pool_bwd_vec_kernel<<<grid_for(total / 4), kT, 0, STREAM>>>(dp, ld_dp, a, ld_a, scale, shift, dfull,
-                                                              ld_df, accumulate, Ho, Wo,
-                                                              (uint32_t)(total / 4), make_vidx(C));
+    const VIdx ix = make_vidx(C);
+    if (stats) {
+      AB_CHECK(ix.shift >= 0 && ix.C4 <= kT && ((uintptr_t)mean & 15) == 0 && ((uintptr_t)invstd & 15) == 0,
+               "pool2x2_bwd_bn: fused statistics need C/4 = power of two <= %d (C=%d)", kT, C);
+      pool_bwd_vec_kernel<true><<<grid_for(total / 4), kT, 0, STREAM>>>(
+          dp, ld_dp, a, ld_a, scale, shift, dfull, ld_df, accumulate, Ho, Wo, (uint32_t)(total / 4), ix,
+          mean, invstd, sums);
+    } else {
+      pool_bwd_vec_kernel<false><<<grid_for(total / 4), kT, 0, STREAM>>>(
+          dp, ld_dp, a, ld_a, scale, shift, dfull, ld_df, accumulate, Ho, Wo, (uint32_t)(total / 4), ix,
+          nullptr, nullptr, nullptr);
+    }
     AB_LAUNCH_CHECK();
     return 0;
   }
+  AB_CHECK(!stats, "pool2x2_bwd_bn: fused statistics need the float4 path (C=%d)", C);
   pool_bwd_kernel<<<grid_for(total), kT, 0, STREAM>>>(dp, ld_dp, a, ld_a, scale, shift, dfull,
                                                       ld_df, accumulate, N, Ho, Wo, C);
   AB_LAUNCH_CHECK();
   return 0;
+}
+
+int atomai_b200_pool2x2_bwd(const float* dp, int ld_dp, const float* a, int ld_a,
+                            const float* scale, const float* shift, float* dfull, int ld_df,
+                            int accumulate, int N, int Ho, int Wo, int C, void* stream) {
+  return atomai_b200_pool2x2_bwd_bn(dp, ld_dp, a, ld_a, scale, shift, dfull, ld_df, accumulate, N, Ho,
+                                    Wo, C, nullptr, nullptr, nullptr, stream);
 }
 
 int atomai_b200_upsample2x_fwd(const float* x, int ld_x, float* y, int ld_y, int N, int h, int w,

@@ -79,7 +79,7 @@ class Act:
     """Activation handle: NHWC tensor + pending affine + pending pool / 2x upsampling (see module
     docstring)."""
     __slots__ = ("t", "scale", "shift", "pool", "up", "parent", "grad", "grad_owned", "extra",
-                 "needs_grad")
+                 "needs_grad", "prod", "bn_sums")
 
     def __init__(self, t, scale=None, shift=None, pool=False, parent=None, needs_grad=True, up=None):
         self.t, self.scale, self.shift, self.pool = t, scale, shift, pool
@@ -89,6 +89,11 @@ class Act:
         self.grad_owned = False       # True: grad buffer is exclusively ours (in-place add ok)
         self.extra = None             # DilatedBlock direct taps (d loss / d a and d pre)
         self.needs_grad = needs_grad
+        self.prod = None              # (mean, invstd) of the BatchNorm this tensor feeds — NOT the
+                                      # record itself: Act <-> record cycles would keep every
+                                      # activation alive until the cyclic GC runs
+        self.bn_sums = None           # BatchNorm-backward sums of `grad`, when the kernel that
+                                      # finished `grad` computed them on the way (pool backward)
 
     @property
     def shape(self):                  # logical NHWC shape seen by a consumer
@@ -114,6 +119,7 @@ def _acc_grad(act: Act, g: torch.Tensor, owned: bool) -> None:
     """act.grad (+)= g.  g may be a channel-slice view; `owned` says whether the caller hands over
     exclusive ownership of g's memory.  A buffer that is not exclusively ours (e.g. the gradient of
     a DilatedBlock sum shared by all its layers) is never written in place."""
+    act.bn_sums = None                # any further contribution invalidates fused statistics
     if act.grad is None:
         act.grad, act.grad_owned = g, owned
         return
@@ -267,6 +273,8 @@ class Tape:
                 act, slope, math, mean, invstd, scale, count
             r.needs_in_grad = any(s.needs_grad for s in srcs)
             r.drop = drop
+            if bn_mod is not None and mean is not None:
+                out.prod = (mean, invstd)
             assert not (bn_mod is not None and not use_batch_stats), \
                 "backward through eval-mode BatchNorm is not supported"
             assert not out_nchw or True
@@ -285,8 +293,11 @@ class Tape:
         sums = None
         if r.bn is not None:
             assert dy is not None, "BatchNorm output has no gradient"
-            sums = torch.zeros(2 * cout, device=dev, dtype=torch.float64)
-            ops.bn_bwd_reduce(dy, a, r.mean, r.invstd, sums)
+            sums = out.bn_sums
+            out.bn_sums = None
+            if sums is None:
+                sums = torch.zeros(2 * cout, device=dev, dtype=torch.float64)
+                ops.bn_bwd_reduce(dy, a, r.mean, r.invstd, sums)
             # gamma/beta gradients come from the LOCAL sums (the gradient bucket sums them over
             # ranks like every other parameter, as torch's SyncBatchNorm does); only the dx
             # formula needs the global sums.
@@ -352,7 +363,17 @@ class Tape:
             own = torch.empty(tgt.t.shape, device=gp.device, dtype=torch.float32)
             ops.add_slice(tgt.grad, own, False)
             tgt.grad, tgt.grad_owned = own, True
-        ops.pool_bwd(gp, tgt.t, tgt.scale, tgt.shift, tgt.grad, acc)
+        # The pooled consumer is normally the LAST one to deliver its gradient (it runs first in
+        # forward, so last in backward): let the scatter kernel also produce the BatchNorm-backward
+        # sums of the finished gradient; _acc_grad drops them again if something else follows.
+        sums = None
+        if tgt.prod is not None and ops.pool_bwd_stats_ok(tgt.C):
+            mean, invstd = tgt.prod
+            sums = torch.zeros(2 * tgt.C, device=gp.device, dtype=torch.float64)
+            ops.pool_bwd(gp, tgt.t, tgt.scale, tgt.shift, tgt.grad, acc, mean, invstd, sums)
+        else:
+            ops.pool_bwd(gp, tgt.t, tgt.scale, tgt.shift, tgt.grad, acc)
+        tgt.bn_sums = sums
 
     # ------------------------------------------------------------------ pooling / upsampling
     def pool(self, x: Act) -> Act:

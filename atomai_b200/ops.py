@@ -178,11 +178,17 @@ def pool_fwd(a, scale, shift, out) -> None:
                                         _ld(out), N, Ho, Wo, Cc, stream_ptr()))
 
 
-def pool_bwd(dp, a, scale, shift, dfull, accumulate) -> None:
+def pool_bwd(dp, a, scale, shift, dfull, accumulate, mean=None, invstd=None, sums=None) -> None:
+    """dfull (+)= unpool(dp); with `sums` also the BatchNorm-backward reductions of the result."""
     N, Ho, Wo, Cc = dp.shape
-    check(lib().atomai_b200_pool2x2_bwd(ptr(dp), _ld(dp), ptr(a), _ld(a), ptr(scale), ptr(shift),
-                                        ptr(dfull), _ld(dfull), 1 if accumulate else 0, N, Ho, Wo,
-                                        Cc, stream_ptr()))
+    check(lib().atomai_b200_pool2x2_bwd_bn(ptr(dp), _ld(dp), ptr(a), _ld(a), ptr(scale), ptr(shift),
+                                           ptr(dfull), _ld(dfull), 1 if accumulate else 0, N, Ho, Wo,
+                                           Cc, ptr(mean), ptr(invstd), ptr(sums), stream_ptr()))
+
+
+def pool_bwd_stats_ok(C: int) -> bool:
+    c4 = C // 4
+    return C % 4 == 0 and c4 >= 1 and (c4 & (c4 - 1)) == 0 and c4 <= 256
 
 
 def upsample_fwd(x, out, bilinear=True) -> None:

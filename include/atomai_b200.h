@@ -143,6 +143,13 @@ int atomai_b200_pool2x2_fwd(const float* a, int ld_a, const float* scale, const 
 int atomai_b200_pool2x2_bwd(const float* dp, int ld_dp, const float* a, int ld_a,
                             const float* scale, const float* shift, float* dfull, int ld_df,
                             int accumulate, int N, int Ho, int Wo, int C, void* stream);
+/* the same, and — when `sums` is given — the BatchNorm-backward reductions of the finished
+ * gradient (sums[0:C] += sum dY, sums[C:2C] += sum dY*xhat, as atomai_b200_bn_bwd_reduce) in the
+ * same pass: valid when this call is the last contribution to dfull.  C/4 a power of two. */
+int atomai_b200_pool2x2_bwd_bn(const float* dp, int ld_dp, const float* a, int ld_a,
+                               const float* scale, const float* shift, float* dfull, int ld_df,
+                               int accumulate, int N, int Ho, int Wo, int C, const float* mean,
+                               const float* invstd, double* sums, void* stream);
 int atomai_b200_upsample2x_fwd(const float* x, int ld_x, float* y, int ld_y, int N, int h, int w,
                                int C, int bilinear, void* stream);
 int atomai_b200_upsample2x_bwd(const float* dy, int ld_dy, float* dx, int ld_dx, int N, int h,
