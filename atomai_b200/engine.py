@@ -29,6 +29,9 @@ if os.environ.get("ATOMAI_B200_FUSE_UP", "0") == "1":     # A/B switch for bench
     _MATH["fuse_up"] = True
 
 
+_NO_POOLSTATS = os.environ.get("ATOMAI_B200_NO_POOLSTATS", "0") == "1"    # A/B switch (bring-up)
+
+
 def set_fusion(upsample: Optional[bool] = None) -> None:
     """upsample=True: `F.interpolate(scale_factor=2)` of an UpsampleBlock is NOT written out; the
     convolution that consumes it (and its weight-gradient kernel) interpolates the (H/2, W/2)
@@ -367,7 +370,7 @@ class Tape:
         # forward, so last in backward): let the scatter kernel also produce the BatchNorm-backward
         # sums of the finished gradient; _acc_grad drops them again if something else follows.
         sums = None
-        if tgt.prod is not None and ops.pool_bwd_stats_ok(tgt.C):
+        if tgt.prod is not None and ops.pool_bwd_stats_ok(tgt.C) and not _NO_POOLSTATS:
             mean, invstd = tgt.prod
             sums = torch.zeros(2 * tgt.C, device=gp.device, dtype=torch.float64)
             ops.pool_bwd(gp, tgt.t, tgt.scale, tgt.shift, tgt.grad, acc, mean, invstd, sums)

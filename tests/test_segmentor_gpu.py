@@ -61,8 +61,12 @@ def test_host_resident_data_prefetch_matches_device_resident(cuda, tmp_path):
         if alloc == 0:
             assert m.X_train[0].is_pinned()
         losses.append((list(m.loss_acc["train_loss"]), list(m.loss_acc["test_loss"])))
-    np.testing.assert_allclose(losses[0][0], losses[1][0], rtol=1e-5)
-    np.testing.assert_allclose(losses[0][1], losses[1][1], rtol=1e-5)
+    # Two runs of the same code are not bit-identical: the weight-gradient kernels flush their
+    # partial sums with fp32 atomics (order varies run to run, ~1e-7), and Adam's first steps turn
+    # a 1e-7 difference of a near-zero gradient into a full-size update (measured 4e-5 on the loss
+    # after 4 cycles).  A wrong or stale prefetched batch would move the loss by > 1e-2.
+    np.testing.assert_allclose(losses[0][0], losses[1][0], rtol=1e-3)
+    np.testing.assert_allclose(losses[0][1], losses[1][1], rtol=1e-3)
 
 
 def test_full_epoch_mode_and_binary_loss(cuda, tmp_path):
