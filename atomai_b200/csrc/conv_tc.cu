@@ -875,7 +875,25 @@ static int conv_tc_plan(const ab_conv_t* d, ConvTcParams* p, int* smem_bytes) {
   const int taps = d->ks_h * d->ks_w;
   p->x3 = d->math == AB_MATH_TF32X3 ? 1 : 0;
   p->w_bytes = taps * S.Ctot * d->Cout * 4 * (p->x3 ? 2 : 1);
-  const int budget = 212 * 1024;
+  // 1 CTA / SM: 227 KB of dynamic shared memory are addressable; ATOMAI_B200_SMEM_KB re-pins the
+  // plan budget (bring-up / sweeps only)
+  int budget = 212 * 1024;
+  if (const char* e = getenv("ATOMAI_B200_SMEM_KB")) {
+    const int kb = atoi(e);
+    if (kb >= 64 && kb <= 224) budget = kb * 1024;
+  }
+  // Operand-ring preference.  Every pipeline owns n_a/2 operand stages; with n_a = 2 the loader
+  // group and the issuing thread of a pipeline strictly alternate (stage -> MMA -> stage ...)
+  // and only the *other* pipeline hides the hand-over, which costs 1.6-1.75x the MMA time on the
+  // thin x3 layers (tf32x3 doubled the stage size and silently dropped them from n_a = 4 to 2).
+  // bit 0: resident-weight plans prefer n_a = 4 over a larger k-chunk / more raw TMA stages;
+  // bit 1: streamed-weight plans too (smaller k-chunk, more and smaller weight stages).
+  int na4 = 0;
+  if (const char* e = getenv("ATOMAI_B200_NA4")) na4 = atoi(e);
+  // TMA mode needs at least this many raw stages (two rings of min_nr/2), else the plan stays
+  // register-staged: with one raw stage per pipeline every k-chunk pays the full HBM latency
+  int min_nr = 2;
+  if (const char* e = getenv("ATOMAI_B200_MIN_NR")) min_nr = atoi(e) < 2 ? 2 : atoi(e);
   const int stats_bytes = (((kEpiGroups * kNumEpiWarps * 2 + 1) * d->Cout * 4 + 127) & ~127) + kCtlBytes + 128;
   // Try, in order of preference: (resident weights, 1 sub-tile), (streamed weights, 2 sub-tiles
   // so that every weight stage feeds M = 256), (streamed, 1 sub-tile).
@@ -897,6 +915,10 @@ static int conv_tc_plan(const ab_conv_t* d, ConvTcParams* p, int* smem_bytes) {
     p->THp = kTileH + d->dil * (d->ks_h - 1);
     p->TWp = kTileW * sub + d->dil * (d->ks_w - 1);
     p->HP = p->THp * p->TWp;
+    // pass 0 (only when this weight mode prefers deep operand rings) accepts a k-chunk only if
+    // it leaves room for n_a = 4; pass 1 is the plain "largest k-chunk with n_a >= 2" search
+    const bool want4 = (na4 & (resident ? 1 : 2)) != 0;
+    for (int pass = want4 ? 0 : 1; pass < 2 && !ok; ++pass)
     for (int KC = pick_kc(S.Ctot); KC >= 8 && !ok; KC >>= 1) {
       if (S.Ctot % KC != 0) continue;
       if (force_kc > 0 && KC != force_kc) continue;
@@ -906,19 +928,20 @@ static int conv_tc_plan(const ab_conv_t* d, ConvTcParams* p, int* smem_bytes) {
       const int want = (128 / P) % 128;  // plane stride mod 128 spreading the P planes over banks
       plane += ((want - plane % 128) + 128) % 128;
       const int a_stage = P * plane * (p->x3 ? 2 : 1);    // x3: + the bf16 correction planes
+      const int need_a = pass == 0 ? 4 : 2;
       int avail = budget - stats_bytes;
       int n_b = 0, b_stage = KC * d->Cout * 4 * (p->x3 ? 2 : 1);
       if (resident) {
         avail -= (p->w_bytes + 127) & ~127;
       } else {
-        // weight stages: cover ~1.5 us of L2 latency, leave room for >= 2 activation stages
-        n_b = ((avail - 2 * a_stage) / b_stage) & ~1;      // two rings of n_b/2 stages
+        // weight stages: cover ~1.5 us of L2 latency, leave room for the activation stages
+        n_b = ((avail - need_a * a_stage) / b_stage) & ~1;      // two rings of n_b/2 stages
         if (n_b > kMaxBStages) n_b = kMaxBStages;
         if (n_b < 4) continue;
         avail -= n_b * b_stage;
       }
       int na = avail / a_stage;
-      if (na < 2) continue;
+      if (na < need_a) continue;
       p->KC = KC; p->plane_bytes = plane; p->a_stage_bytes = a_stage; p->b_stage_bytes = b_stage;
       p->corr_off = P * plane;
       p->n_a = na > kMaxAStages ? kMaxAStages : na;
@@ -931,7 +954,8 @@ static int conv_tc_plan(const ab_conv_t* d, ConvTcParams* p, int* smem_bytes) {
     // the (KC, operand stages, raw stages) with the most raw bytes in flight
     if (ok && resident && use_tma && !S.s[0].pool && !(S.nsrc > 1 && S.s[1].pool)) {
       int best_bytes = 0;
-      for (int KC = pick_kc(S.Ctot); KC >= 16; KC >>= 1) {
+      const int tma_min_kc = getenv("ATOMAI_B200_TMA_KC8") ? 8 : 16;   // sweep hook: 32-byte box rows
+      for (int KC = pick_kc(S.Ctot); KC >= tma_min_kc; KC >>= 1) {
         if (S.Ctot % KC != 0 || (S.nsrc > 1 && S.s[0].C % KC != 0)) continue;
         if (force_kc > 0 && KC != force_kc) continue;
         const int P = KC / 4;
@@ -943,11 +967,13 @@ static int conv_tc_plan(const ab_conv_t* d, ConvTcParams* p, int* smem_bytes) {
         const int raw = p->HP * KC * 4;
         if (raw % 128 != 0) continue;
         const int avail = budget - stats_bytes - ((p->w_bytes + 127) & ~127);
-        for (int na = 4; na >= 2; na -= 2) {
+        for (int na = 4; na >= ((na4 & 1) ? 4 : 2); na -= 2) {
           int nr = ((avail - na * a_stage) / raw) & ~1;
           if (nr > kMaxRStages) nr = kMaxRStages;
-          if (nr < 2) continue;
-          const int score = nr * raw + (na == 4 ? 1 : 0);
+          if (nr < min_nr) continue;
+          // raw bytes in flight decide; with the n_a = 4 preference a double-buffered operand
+          // ring outranks any number of raw stages
+          const int score = nr * raw + (na == 4 ? ((na4 & 1) ? (1 << 24) : 1) : 0);
           if (score > best_bytes) {
             best_bytes = score;
             p->KC = KC; p->plane_bytes = plane; p->a_stage_bytes = a_stage;
@@ -969,6 +995,12 @@ static int conv_tc_plan(const ab_conv_t* d, ConvTcParams* p, int* smem_bytes) {
   *smem_bytes = stats_bytes + p->n_a * p->a_stage_bytes +
                 (p->w_resident ? ((p->w_bytes + 127) & ~127) : p->n_b * p->b_stage_bytes) +
                 p->n_r * p->raw_bytes + (p->tma ? 128 : 0);
+  if (getenv("ATOMAI_B200_PLAN_LOG"))
+    fprintf(stderr,
+            "conv_tc plan: %dx%d Cin=%d Cout=%d taps=%d x3=%d | resident=%d sub=%d KC=%d n_a=%d "
+            "n_b=%d tma=%d n_r=%d a_stage=%d smem=%d\n",
+            d->H, d->W, S.Ctot, d->Cout, taps, p->x3, p->w_resident, p->sub, p->KC, p->n_a, p->n_b,
+            p->tma, p->n_r, p->a_stage_bytes, *smem_bytes);
   return 0;
 }
 
