@@ -875,25 +875,32 @@ static int conv_tc_plan(const ab_conv_t* d, ConvTcParams* p, int* smem_bytes) {
   const int taps = d->ks_h * d->ks_w;
   p->x3 = d->math == AB_MATH_TF32X3 ? 1 : 0;
   p->w_bytes = taps * S.Ctot * d->Cout * 4 * (p->x3 ? 2 : 1);
-  // 1 CTA / SM: 227 KB of dynamic shared memory are addressable; ATOMAI_B200_SMEM_KB re-pins the
-  // plan budget (bring-up / sweeps only)
-  int budget = 212 * 1024;
+  // 1 CTA / SM: 227 KB of dynamic shared memory are addressable (226 KB opted in below);
+  // ATOMAI_B200_SMEM_KB re-pins the plan budget (sweeps only)
+  int budget = 224 * 1024;
   if (const char* e = getenv("ATOMAI_B200_SMEM_KB")) {
     const int kb = atoi(e);
     if (kb >= 64 && kb <= 224) budget = kb * 1024;
   }
-  // Operand-ring preference.  Every pipeline owns n_a/2 operand stages; with n_a = 2 the loader
-  // group and the issuing thread of a pipeline strictly alternate (stage -> MMA -> stage ...)
-  // and only the *other* pipeline hides the hand-over, which costs 1.6-1.75x the MMA time on the
-  // thin x3 layers (tf32x3 doubled the stage size and silently dropped them from n_a = 4 to 2).
-  // bit 0: resident-weight plans prefer n_a = 4 over a larger k-chunk / more raw TMA stages;
-  // bit 1: streamed-weight plans too (smaller k-chunk, more and smaller weight stages).
-  int na4 = 0;
+  // Operand-ring preference (measured, tools/plan_ab.py, profiles/r02_plan_ab.md).  Every
+  // pipeline owns n_a/2 operand stages; with n_a = 2 the loader group and the issuing thread of
+  // a pipeline strictly alternate (stage -> MMA -> stage ...) and only the *other* pipeline hides
+  // the hand-over.  tf32x3 doubled the stage size and had silently dropped most 3x3 layers from
+  // n_a = 4 to 2: c6.0 977 -> 753 us, c2.1/c5.1 285 -> 226 us, c4.0 316 -> 272 us with the
+  // deeper ring.  It does NOT pay to buy the deeper ring with 8-channel k-chunks when the
+  // loaders are the heavy side (pooled sources, register-staged resident layers: c3.0 154 -> 170,
+  // c5.0 512 -> 528 us), so pass 0 of the search only drops to KC = 8 for streamed-weight layers
+  // with plain sources (bn.1 150 -> 136 us).
+  // bit 0: resident-weight plans prefer n_a = 4 over more raw TMA stages;
+  // bit 1: streamed-weight plans prefer n_a = 4 over a larger k-chunk / more weight stages.
+  int na4 = 3;
   if (const char* e = getenv("ATOMAI_B200_NA4")) na4 = atoi(e);
   // TMA mode needs at least this many raw stages (two rings of min_nr/2), else the plan stays
   // register-staged: with one raw stage per pipeline every k-chunk pays the full HBM latency
-  int min_nr = 2;
+  int min_nr = 4;
   if (const char* e = getenv("ATOMAI_B200_MIN_NR")) min_nr = atoi(e) < 2 ? 2 : atoi(e);
+  bool any_pool = false;
+  for (int i = 0; i < S.nsrc; ++i) any_pool = any_pool || S.s[i].pool != 0;
   const int stats_bytes = (((kEpiGroups * kNumEpiWarps * 2 + 1) * d->Cout * 4 + 127) & ~127) + kCtlBytes + 128;
   // Try, in order of preference: (resident weights, 1 sub-tile), (streamed weights, 2 sub-tiles
   // so that every weight stage feeds M = 256), (streamed, 1 sub-tile).
@@ -929,6 +936,7 @@ static int conv_tc_plan(const ab_conv_t* d, ConvTcParams* p, int* smem_bytes) {
       plane += ((want - plane % 128) + 128) % 128;
       const int a_stage = P * plane * (p->x3 ? 2 : 1);    // x3: + the bf16 correction planes
       const int need_a = pass == 0 ? 4 : 2;
+      if (pass == 0 && KC < 16 && (resident || any_pool)) continue;
       int avail = budget - stats_bytes;
       int n_b = 0, b_stage = KC * d->Cout * 4 * (p->x3 ? 2 : 1);
       if (resident) {
