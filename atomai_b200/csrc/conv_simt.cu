@@ -409,6 +409,153 @@ __global__ void __launch_bounds__(256, 2) conv_c1_kernel(const ConvSimtParams p)
   }
 }
 
+// First layer, tile version (dilation 1): a CTA of 8 warps owns a 64 x 16 output tile whose
+// 66 x 18 input halo tile (affine applied, zero padded) sits in shared memory; the NEXT tile's
+// halo is fetched into registers before the current one is computed.  Lane l of a warp = pixel
+// l >> 2 of an 8-pixel run x channel quad l & 3, so every STG.128 of a warp writes 8 whole pixels
+// = 512 contiguous bytes (the pair-per-thread kernel above writes 16-byte pieces 128 bytes apart:
+// 51 % excess sectors in the ncu capture), the thread's 9 x 4 weights live in registers for the
+// whole kernel, and walking down the 16 rows costs 3 broadcast LDS per 36 FFMA.  Accumulation
+// order per output (bias, then taps 0..8 with fmaf) is the pair kernel's: results are identical.
+constexpr int C1T_W = 64, C1T_H = 16, C1T_PW = C1T_W + 2, C1T_PH = C1T_H + 2;
+constexpr int C1T_ELEMS = C1T_PW * C1T_PH, C1T_PER_THREAD = (C1T_ELEMS + 255) / 256;
+
+struct C1Tile { int n, h0, w0; };
+__device__ __forceinline__ C1Tile c1_tile(int tile, int tiles_w, int tiles_hw) {
+  C1Tile t;
+  t.n = tile / tiles_hw;
+  const int rem = tile - t.n * tiles_hw;
+  const int th = rem / tiles_w;
+  t.h0 = th * C1T_H;
+  t.w0 = (rem - th * tiles_w) * C1T_W;
+  return t;
+}
+// halo tile of `t` -> registers (element e = tid + i*256 of the 66 x 18 tile)
+__device__ __forceinline__ void c1_fetch(const SrcDev& sd, float sc, float sh, int H, int W,
+                                         const C1Tile& t, float (&r)[C1T_PER_THREAD]) {
+#pragma unroll
+  for (int i = 0; i < C1T_PER_THREAD; ++i) {
+    const int e = threadIdx.x + i * 256;
+    const int row = e / C1T_PW, col = e - row * C1T_PW;
+    const int gh = t.h0 - 1 + row, gw = t.w0 - 1 + col;
+    const bool ok = e < C1T_ELEMS && (unsigned)gh < (unsigned)H && (unsigned)gw < (unsigned)W;
+    r[i] = ok ? fmaf(__ldg(sd.ptr + (((size_t)t.n * H + gh) * W + gw) * sd.ld), sc, sh) : 0.f;
+  }
+}
+__device__ __forceinline__ void c1_stage(float* s_x, const float (&r)[C1T_PER_THREAD]) {
+#pragma unroll
+  for (int i = 0; i < C1T_PER_THREAD; ++i) {
+    const int e = threadIdx.x + i * 256;
+    if (e < C1T_ELEMS) s_x[e] = r[i];
+  }
+}
+
+template <int FAST>
+__global__ void __launch_bounds__(256) conv_c1_tile_kernel(const ConvSimtParams p, int tiles_w,
+                                                           int tiles_hw, int num_tiles) {
+  __shared__ float s_x[C1T_ELEMS];
+  __shared__ float s_red[32];
+  const int c0 = p.c0;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int px = lane >> 2, q = lane & 3;
+  const int col = warp * 8 + px;                                   // column inside the tile
+  float wr[9][4], bq[4];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) wr[t][k] = __ldg(p.w + (size_t)t * p.Cout + c0 + q * 4 + k);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) bq[k] = p.bias ? __ldg(p.bias + c0 + q * 4 + k) : 0.f;
+  if (threadIdx.x < 32) s_red[threadIdx.x] = 0.f;
+  const SrcDev sd = p.S.s[0];
+  float sc = 1.f, sh = 0.f;
+  if (sd.scale) { sc = __ldg(sd.scale); sh = __ldg(sd.shift); }
+  const int H = p.H, W = p.W;
+  float ssum[4] = {0.f, 0.f, 0.f, 0.f}, ssq[4] = {0.f, 0.f, 0.f, 0.f};
+  float nxt[C1T_PER_THREAD];
+  int tile = blockIdx.x;
+  C1Tile cur = c1_tile(tile < num_tiles ? tile : 0, tiles_w, tiles_hw);
+  if (tile < num_tiles) c1_fetch(sd, sc, sh, H, W, cur, nxt);
+  for (; tile < num_tiles; tile += gridDim.x) {
+    __syncthreads();                     // every warp is done with the previous tile's halo
+    c1_stage(s_x, nxt);
+    __syncthreads();
+    const C1Tile me = cur;
+    const int tn = tile + gridDim.x;
+    if (tn < num_tiles) {
+      cur = c1_tile(tn, tiles_w, tiles_hw);
+      c1_fetch(sd, sc, sh, H, W, cur, nxt);
+    }
+    const int gw = me.w0 + col;
+    if (gw < W) {
+      const float* sp = s_x + col;
+      float x0[3], x1[3], x2[3];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) { x0[j] = sp[j]; x1[j] = sp[C1T_PW + j]; }
+      float* o = p.out + (((size_t)me.n * H + me.h0) * W + gw) * p.ld_out + c0 + q * 4;
+      const size_t row_stride = (size_t)W * p.ld_out;
+      const int rows = min(C1T_H, H - me.h0);
+#pragma unroll 4
+      for (int r = 0; r < rows; ++r) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) x2[j] = sp[(r + 2) * C1T_PW + j];
+        float a[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float v = bq[k];
+          v = fmaf(x0[0], wr[0][k], v); v = fmaf(x0[1], wr[1][k], v); v = fmaf(x0[2], wr[2][k], v);
+          v = fmaf(x1[0], wr[3][k], v); v = fmaf(x1[1], wr[4][k], v); v = fmaf(x1[2], wr[5][k], v);
+          v = fmaf(x2[0], wr[6][k], v); v = fmaf(x2[1], wr[7][k], v); v = fmaf(x2[2], wr[8][k], v);
+          v = FAST ? fmaxf(v, v * p.alpha) : act_f(v, p.act, p.alpha);
+          ssum[k] += v;
+          ssq[k] = fmaf(v, v, ssq[k]);
+          a[k] = v;
+        }
+        *reinterpret_cast<float4*>(o + r * row_stride) = make_float4(a[0], a[1], a[2], a[3]);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) { x0[j] = x1[j]; x1[j] = x2[j]; }
+      }
+    }
+  }
+  if (p.stats) {
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float a = ssum[k], b = ssq[k];
+#pragma unroll
+      for (int m = 4; m <= 16; m <<= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, m);
+        b += __shfl_xor_sync(0xffffffffu, b, m);
+      }
+      if (lane < 4) {
+        atomicAdd(&s_red[q * 4 + k], a);
+        atomicAdd(&s_red[16 + q * 4 + k], b);
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < 16) {
+      atomicAdd(p.stats + c0 + threadIdx.x, (double)s_red[threadIdx.x]);
+      atomicAdd(p.stats + p.Cout + c0 + threadIdx.x, (double)s_red[16 + threadIdx.x]);
+    }
+  }
+}
+
+int launch_conv_c1_tile(const ConvSimtParams& p, cudaStream_t stream) {
+  const int tiles_w = (p.W + C1T_W - 1) / C1T_W, tiles_h = (p.H + C1T_H - 1) / C1T_H;
+  const int64_t tiles = (int64_t)p.N * tiles_w * tiles_h;
+  AB_CHECK(tiles < (1ll << 31), "conv_c1: too many tiles");
+  int64_t blocks = tiles;
+  const int64_t cap = (int64_t)ab_num_sms() * 3;
+  if (blocks > cap) blocks = cap;
+  const bool fast = p.act == AB_ACT_LRELU && p.alpha >= 0.f && p.alpha <= 1.f;
+  if (fast)
+    conv_c1_tile_kernel<1><<<(unsigned)blocks, 256, 0, stream>>>(p, tiles_w, tiles_w * tiles_h, (int)tiles);
+  else
+    conv_c1_tile_kernel<0><<<(unsigned)blocks, 256, 0, stream>>>(p, tiles_w, tiles_w * tiles_h, (int)tiles);
+  AB_LAUNCH_CHECK();
+  return 0;
+}
+
 template <int CO>
 int launch_conv_c1(const ConvSimtParams& p, cudaStream_t stream) {
   const int64_t pairs = (int64_t)p.N * p.H * ((p.W + 1) / 2);
@@ -417,6 +564,107 @@ int launch_conv_c1(const ConvSimtParams& p, cudaStream_t stream) {
   const int64_t cap = (int64_t)ab_num_sms() * 16;
   if (blocks > cap) blocks = cap;
   conv_c1_kernel<CO><<<(unsigned)blocks, 256, 0, stream>>>(p);
+  AB_LAUNCH_CHECK();
+  return 0;
+}
+
+// Pixel-wise 1x1 convolution onto 16 channels from a few (<= 8) input channels — the data
+// gradient of the classification head (nb_classes -> 16) — in the quad-lane layout: lane = pixel
+// l >> 2 of an 8-pixel run x output quad l & 3.  The thread keeps its Cin x 4 weights in
+// registers, the 4 lanes of a pixel share its input loads (one broadcast request), and each
+// STG.128 of a warp writes 512 contiguous bytes (the thread-per-pixel kernel below writes 16-byte
+// pieces 64 bytes apart).  Same per-output fmaf order as conv_pix_kernel's direct path.
+template <int CIN_MAX>
+__global__ void __launch_bounds__(256) conv_pix_quad_kernel(const ConvSimtParams p) {
+  __shared__ float s_red[32];
+  const int lane = threadIdx.x & 31;
+  const int px = lane >> 2, q = lane & 3;
+  const int Cin = p.S.Ctot;
+  const SrcDev sd = p.S.s[0];
+  if (threadIdx.x < 32) s_red[threadIdx.x] = 0.f;
+  float wr[CIN_MAX][4], bq[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) bq[k] = p.bias ? __ldg(p.bias + q * 4 + k) : 0.f;
+#pragma unroll
+  for (int c = 0; c < CIN_MAX; ++c)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) wr[c][k] = c < Cin ? __ldg(p.w + (size_t)c * p.Cout + q * 4 + k) : 0.f;
+  if (sd.scale) {           // pending affine folded into weights and bias (as conv_pix_kernel does)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float t = 0.f;
+#pragma unroll
+      for (int c = 0; c < CIN_MAX; ++c)
+        if (c < Cin) t = fmaf(wr[c][k], __ldg(sd.shift + c), t);
+      bq[k] += t;
+    }
+#pragma unroll
+    for (int c = 0; c < CIN_MAX; ++c)
+      if (c < Cin) {
+        const float sc = __ldg(sd.scale + c);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) wr[c][k] *= sc;
+      }
+  }
+  const int64_t npix = (int64_t)p.N * p.H * p.W;
+  float ssum[4] = {0.f, 0.f, 0.f, 0.f}, ssq[4] = {0.f, 0.f, 0.f, 0.f};
+  const int64_t stride = (int64_t)gridDim.x * (blockDim.x >> 2);
+#pragma unroll 4
+  for (int64_t pix = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2; pix < npix; pix += stride) {
+    const float* xp = sd.ptr + pix * sd.ld;
+    float a[4] = {bq[0], bq[1], bq[2], bq[3]};
+#pragma unroll
+    for (int c = 0; c < CIN_MAX; ++c)
+      if (c < Cin) {
+        const float x = __ldg(xp + c);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) a[k] = fmaf(x, wr[c][k], a[k]);
+      }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      a[k] = act_f(a[k], p.act, p.alpha);
+      ssum[k] += a[k];
+      ssq[k] = fmaf(a[k], a[k], ssq[k]);
+    }
+    *reinterpret_cast<float4*>(p.out + pix * p.ld_out + q * 4) = make_float4(a[0], a[1], a[2], a[3]);
+  }
+  (void)px;
+  if (p.stats) {
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float a = ssum[k], b = ssq[k];
+#pragma unroll
+      for (int m = 4; m <= 16; m <<= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, m);
+        b += __shfl_xor_sync(0xffffffffu, b, m);
+      }
+      if (lane < 4) {
+        atomicAdd(&s_red[q * 4 + k], a);
+        atomicAdd(&s_red[16 + q * 4 + k], b);
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < 16) {
+      atomicAdd(p.stats + threadIdx.x, (double)s_red[threadIdx.x]);
+      atomicAdd(p.stats + p.Cout + threadIdx.x, (double)s_red[16 + threadIdx.x]);
+    }
+  }
+}
+
+static bool pix_quad_enabled() {
+  const char* e = getenv("ATOMAI_B200_PIX_QUAD");
+  return !(e && e[0] == '0');
+}
+
+int launch_conv_pix_quad(const ConvSimtParams& p, cudaStream_t stream) {
+  const int64_t npix = (int64_t)p.N * p.H * p.W;
+  int64_t blocks = (npix * 4 + 256 * 8 - 1) / (256 * 8);
+  const int64_t cap = (int64_t)ab_num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  if (p.S.Ctot <= 4) conv_pix_quad_kernel<4><<<(unsigned)blocks, 256, 0, stream>>>(p);
+  else conv_pix_quad_kernel<8><<<(unsigned)blocks, 256, 0, stream>>>(p);
   AB_LAUNCH_CHECK();
   return 0;
 }
@@ -591,6 +839,104 @@ __global__ void __launch_bounds__(256, 2) wgrad_c1_kernel(const WgradSimtParams 
     atomicAdd(p.dw + (size_t)(co0 + i / 9) * 9 + i % 9, s_acc[i]);   // OIHW with Cin = 1
 }
 
+// First-layer weight gradient, tile version (same CTA tile, halo staging and lane mapping as
+// conv_c1_tile_kernel): a thread accumulates dW[4 channels of its quad][9 taps] over its pixels,
+// so all 16 channels go in ONE pass over dy (the pair kernel above reads dy twice, 8 channels
+// per pass) with 512-byte coalesced LDG.128 rows.
+__global__ void __launch_bounds__(256) wgrad_c1_tile_kernel(const WgradSimtParams p, int tiles_w,
+                                                            int tiles_hw, int num_tiles) {
+  __shared__ float s_x[C1T_ELEMS];
+  __shared__ float s_acc[16 * 9];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int px = lane >> 2, q = lane & 3;
+  const int col = warp * 8 + px;
+  for (int i = threadIdx.x; i < 16 * 9; i += blockDim.x) s_acc[i] = 0.f;
+  const SrcDev sd = p.S.s[0];
+  float sc = 1.f, sh = 0.f;
+  if (sd.scale) { sc = __ldg(sd.scale); sh = __ldg(sd.shift); }
+  const int H = p.H, W = p.W;
+  float acc[4][9];
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+#pragma unroll
+    for (int t = 0; t < 9; ++t) acc[k][t] = 0.f;
+  float nxt[C1T_PER_THREAD];
+  int tile = blockIdx.x;
+  C1Tile cur = c1_tile(tile < num_tiles ? tile : 0, tiles_w, tiles_hw);
+  if (tile < num_tiles) c1_fetch(sd, sc, sh, H, W, cur, nxt);
+  for (; tile < num_tiles; tile += gridDim.x) {
+    __syncthreads();
+    c1_stage(s_x, nxt);
+    __syncthreads();
+    const C1Tile me = cur;
+    const int tn = tile + gridDim.x;
+    if (tn < num_tiles) {
+      cur = c1_tile(tn, tiles_w, tiles_hw);
+      c1_fetch(sd, sc, sh, H, W, cur, nxt);
+    }
+    const int gw = me.w0 + col;
+    if (gw < W) {
+      const float* sp = s_x + col;
+      float x0[3], x1[3], x2[3];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) { x0[j] = sp[j]; x1[j] = sp[C1T_PW + j]; }
+      const float* dyp = p.dy + (((size_t)me.n * H + me.h0) * W + gw) * p.ld_dy + q * 4;
+      const size_t row_stride = (size_t)W * p.ld_dy;
+      const int rows = min(C1T_H, H - me.h0);
+#pragma unroll 4
+      for (int r = 0; r < rows; ++r) {
+        const float4 d4 = __ldg(reinterpret_cast<const float4*>(dyp + r * row_stride));
+#pragma unroll
+        for (int j = 0; j < 3; ++j) x2[j] = sp[(r + 2) * C1T_PW + j];
+        const float dv[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            acc[k][j] = fmaf(dv[k], x0[j], acc[k][j]);
+            acc[k][3 + j] = fmaf(dv[k], x1[j], acc[k][3 + j]);
+            acc[k][6 + j] = fmaf(dv[k], x2[j], acc[k][6 + j]);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 3; ++j) { x0[j] = x1[j]; x1[j] = x2[j]; }
+      }
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      float v = acc[k][t];
+#pragma unroll
+      for (int m = 4; m <= 16; m <<= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+      if (lane < 4) atomicAdd(&s_acc[(q * 4 + k) * 9 + t], v);
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 16 * 9; i += blockDim.x) atomicAdd(p.dw + i, s_acc[i]);   // OIHW, Cin = 1
+}
+
+int launch_wgrad_c1_tile(const WgradSimtParams& p, cudaStream_t stream) {
+  const int tiles_w = (p.W + C1T_W - 1) / C1T_W, tiles_h = (p.H + C1T_H - 1) / C1T_H;
+  const int64_t tiles = (int64_t)p.N * tiles_w * tiles_h;
+  AB_CHECK(tiles < (1ll << 31), "wgrad_c1: too many tiles");
+  int64_t blocks = tiles;
+  const int64_t cap = (int64_t)ab_num_sms() * 3;
+  if (blocks > cap) blocks = cap;
+  wgrad_c1_tile_kernel<<<(unsigned)blocks, 256, 0, stream>>>(p, tiles_w, tiles_w * tiles_h, (int)tiles);
+  AB_LAUNCH_CHECK();
+  return 0;
+}
+
+// the tile kernels want dilation 1 and rows that fill most of the 64-pixel tile width
+static bool c1_tile_ok(int dil, int W) {
+  if (const char* e = getenv("ATOMAI_B200_C1_TILE"))
+    if (e[0] == '0') return false;
+  const int tiles_w = (W + C1T_W - 1) / C1T_W;
+  return dil == 1 && tiles_w * C1T_W - W <= W / 4;
+}
+
 template <int CO>
 int launch_wgrad_c1(const WgradSimtParams& p, cudaStream_t stream) {
   const int64_t pairs = (int64_t)p.N * p.H * ((p.W + 1) / 2);
@@ -689,6 +1035,66 @@ __global__ void __launch_bounds__(256) wgrad_small_kernel(const WgradSimtParams 
   }
 }
 
+// Weight gradient of a pixel-wise head with <= 4 outputs from 16 input channels (16 -> nb_classes,
+// 1x1), quad-lane layout: lane = pixel l >> 2 x input quad l & 3, so the 16-channel activation is
+// read with 512-byte coalesced LDG.128 rows (thread-per-pixel: four 16-byte pieces 64 bytes
+// apart per thread); the <= 4 dy values of a pixel are one broadcast request per quad.
+__global__ void __launch_bounds__(256) wgrad_pix_quad_kernel(const WgradSimtParams p) {
+  __shared__ float s_acc[4 * 16];
+  const int lane = threadIdx.x & 31;
+  const int q = lane & 3;
+  const int Cout = p.Cout;
+  const SrcDev sd = p.S.s[0];
+  if (threadIdx.x < 64) s_acc[threadIdx.x] = 0.f;
+  float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (sd.scale) {
+    sc = __ldg(reinterpret_cast<const float4*>(sd.scale + q * 4));
+    sh = __ldg(reinterpret_cast<const float4*>(sd.shift + q * 4));
+  }
+  float acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+  const int64_t stride = (int64_t)gridDim.x * (blockDim.x >> 2);
+#pragma unroll 4
+  for (int64_t pix = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2; pix < p.npix; pix += stride) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(sd.ptr + pix * sd.ld + q * 4));
+    const float x[4] = {fmaf(v.x, sc.x, sh.x), fmaf(v.y, sc.y, sh.y), fmaf(v.z, sc.z, sh.z),
+                        fmaf(v.w, sc.w, sh.w)};
+    const float* dyp = p.dy + pix * p.ld_dy;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const float d = a < Cout ? __ldg(dyp + a) : 0.f;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(d, x[b], acc[a][b]);
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      float v = acc[a][b];
+#pragma unroll
+      for (int m = 4; m <= 16; m <<= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+      if (lane < 4) atomicAdd(&s_acc[a * 16 + q * 4 + b], v);
+    }
+  __syncthreads();
+  if (threadIdx.x < 64 && (threadIdx.x >> 4) < Cout)                // OIHW with 1x1 taps
+    atomicAdd(p.dw + (size_t)(threadIdx.x >> 4) * 16 + (threadIdx.x & 15), s_acc[threadIdx.x]);
+}
+
+int launch_wgrad_pix_quad(const WgradSimtParams& p, cudaStream_t stream) {
+  int64_t blocks = (p.npix * 4 + 256 * 8 - 1) / (256 * 8);
+  const int64_t cap = (int64_t)ab_num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  wgrad_pix_quad_kernel<<<(unsigned)blocks, 256, 0, stream>>>(p);
+  AB_LAUNCH_CHECK();
+  return 0;
+}
+
 template <int CO, int CI, int TH, int TW>
 int launch_wgrad_small(const WgradSimtParams& p, cudaStream_t stream) {
   AB_CHECK(p.npix < (1ll << 32), "wgrad_small: too many pixels");
@@ -754,8 +1160,9 @@ int ab_conv_simt_fwd(const ab_conv_t* d, const float* w, const float* bias, floa
         d->N * (int64_t)d->H * d->W > 0) {
       // first layer of every net (Unet 1 -> 16, ImSpec 1 -> 64, VAE 1 -> 128): one launch per block
       // of 16 output channels, the single-channel input stays in L2 between them
+      const bool tile = c1_tile_ok(d->dil, d->W);
       for (p.c0 = 0; p.c0 < d->Cout; p.c0 += 16)
-        if (launch_conv_c1<16>(p, stream)) return 1;
+        if (tile ? launch_conv_c1_tile(p, stream) : launch_conv_c1<16>(p, stream)) return 1;
       return 0;
     }
     if (d->N * (int64_t)d->H * d->W > 0) {
@@ -766,6 +1173,9 @@ int ab_conv_simt_fwd(const ab_conv_t* d, const float* w, const float* bias, floa
       if (d->Cout <= 4 && taps * Cin <= 1024) return launch_conv_pix<4>(p, stream);
       if (taps * Cin <= 64) {
         if (d->Cout == 8) return launch_conv_pix<8>(p, stream);
+        if (d->Cout == 16 && taps == 1 && Cin <= 8 && p.S.nsrc == 1 && !p.S.s[0].pool && !d->out_nchw &&
+            ld_y % 4 == 0 && ((uintptr_t)y & 15) == 0 && pix_quad_enabled())
+          return launch_conv_pix_quad(p, stream);
         if (d->Cout == 16) return launch_conv_pix<16>(p, stream);
         if (d->Cout % 32 == 0 && d->Cout <= 256 && !d->out_nchw) {
           for (p.c0 = 0; p.c0 < d->Cout; p.c0 += 32)
@@ -807,10 +1217,15 @@ int ab_conv_simt_wgrad(const ab_conv_t* d, const float* dy, int ld_dy, float* dw
   p.px_per_cta = 0;
   if (p.S.Ctot == 1 && d->ks_w == 3 && d->ks_h == 3 && d->Cout == 16 && p.S.nsrc == 1 &&
       !p.S.s[0].pool && ld_dy % 4 == 0 && ((uintptr_t)dy & 15) == 0)
-    return launch_wgrad_c1<16>(p, stream);
+    return c1_tile_ok(d->dil, d->W) ? launch_wgrad_c1_tile(p, stream) : launch_wgrad_c1<16>(p, stream);
   if (p.S.Ctot <= 2 && d->ks_w == 3 && d->ks_h == 3) return launch_wgrad_small<8, 1, 3, 3>(p, stream);
   if (p.S.Ctot <= 2 && d->ks_w == 3 && d->ks_h == 1) return launch_wgrad_small<16, 1, 1, 3>(p, stream);
   if (p.S.Ctot <= 2 && d->ks_w == 1 && d->ks_h == 1) return launch_wgrad_small<16, 2, 1, 1>(p, stream);
+  if (d->Cout <= 4 && d->ks_w == 1 && d->ks_h == 1 && p.S.Ctot == 16 && p.S.nsrc == 1 && !p.S.s[0].pool &&
+      (p.S.s[0].ld & 3) == 0 && ((uintptr_t)p.S.s[0].ptr & 15) == 0 &&
+      (!p.S.s[0].scale || (((uintptr_t)p.S.s[0].scale | (uintptr_t)p.S.s[0].shift) & 15) == 0) &&
+      pix_quad_enabled())
+    return launch_wgrad_pix_quad(p, stream);
   if (d->Cout <= 4 && d->ks_w == 1 && d->ks_h == 1) return launch_wgrad_small<4, 16, 1, 1>(p, stream);
   if (d->Cout <= 4 && d->ks_w == 3 && d->ks_h == 3) return launch_wgrad_small<4, 4, 3, 3>(p, stream);
   if (d->Cout <= 4 && d->ks_w == 3 && d->ks_h == 1) return launch_wgrad_small<4, 4, 1, 3>(p, stream);
