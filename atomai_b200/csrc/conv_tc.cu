@@ -912,6 +912,11 @@ static int conv_tc_plan(const ab_conv_t* d, ConvTcParams* p, int* smem_bytes) {
   const char* e_tma = getenv("ATOMAI_B200_TMA");      // "0" pins the register-staged loaders
   const bool use_tma = !(e_tma && e_tma[0] == '0');
   bool ok = false;
+  // sweep hook ATOMAI_B200_RES_NA4=1: a resident-weight plan must reach n_a = 4, else the
+  // streamed-weight plans are tried first (the resident n_a = 2 plan stays the last resort)
+  const char* e_strict = getenv("ATOMAI_B200_RES_NA4");
+  const int strict0 = (e_strict && e_strict[0] == '1') ? 1 : 0;
+  for (int strict = strict0; strict >= 0 && !ok; --strict)
   for (int attempt = 0; attempt < 3 && !ok; ++attempt) {
     if (force_attempt >= 0 && attempt != force_attempt) continue;
     const int resident = attempt == 0;
@@ -950,6 +955,7 @@ static int conv_tc_plan(const ab_conv_t* d, ConvTcParams* p, int* smem_bytes) {
       }
       int na = avail / a_stage;
       if (na < need_a) continue;
+      if (strict && resident && (na < 4 || KC < 16)) continue;
       p->KC = KC; p->plane_bytes = plane; p->a_stage_bytes = a_stage; p->b_stage_bytes = b_stage;
       p->corr_off = P * plane;
       p->n_a = na > kMaxAStages ? kMaxAStages : na;

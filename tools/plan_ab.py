@@ -20,7 +20,12 @@ VARIANTS = [  # name, env
                     "ATOMAI_B200_TMA_KC8": "1"}),
     ("F na4=2 224", {"ATOMAI_B200_NA4": "2", "ATOMAI_B200_SMEM_KB": "224"}),
 ]
-KEYS = ["ATOMAI_B200_NA4", "ATOMAI_B200_SMEM_KB", "ATOMAI_B200_MIN_NR", "ATOMAI_B200_TMA_KC8"]
+KEYS = ["ATOMAI_B200_NA4", "ATOMAI_B200_SMEM_KB", "ATOMAI_B200_MIN_NR", "ATOMAI_B200_TMA_KC8",
+        "ATOMAI_B200_RES_NA4", "ATOMAI_B200_PLAN"]
+if os.environ.get("PLAN_AB_SET") == "res":     # resident n_a = 2 vs streamed n_a = 4 (c3.0, c5.0)
+    VARIANTS = [("A default", {}), ("G res_na4", {"ATOMAI_B200_RES_NA4": "1"}),
+                ("H streamed s1", {"ATOMAI_B200_PLAN": "2,16"}),
+                ("I res kc8 tma", {"ATOMAI_B200_NA4": "3", "ATOMAI_B200_TMA_KC8": "1", "ATOMAI_B200_PLAN": "0,8"})]
 
 
 def set_variant(env):
@@ -39,6 +44,8 @@ LAYERS = [  # name, H, [cins], cout, ks, pool
     ("u2", 128, [64], 32, 1, False), ("c5.0", 256, [32, 32], 32, 3, False),
     ("u3", 256, [32], 16, 1, False), ("c6.0", 512, [16, 16], 16, 3, False),
 ]
+if os.environ.get("PLAN_AB_SET") == "res":
+    LAYERS = [l for l in LAYERS if l[0] in ("c3.0", "c5.0", "c2.0")]
 MATH = ops.MATH_TF32X3
 dev = "cuda"
 
