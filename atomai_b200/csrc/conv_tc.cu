@@ -912,10 +912,16 @@ static int conv_tc_plan(const ab_conv_t* d, ConvTcParams* p, int* smem_bytes) {
   const char* e_tma = getenv("ATOMAI_B200_TMA");      // "0" pins the register-staged loaders
   const bool use_tma = !(e_tma && e_tma[0] == '0');
   bool ok = false;
-  // sweep hook ATOMAI_B200_RES_NA4=1: a resident-weight plan must reach n_a = 4, else the
-  // streamed-weight plans are tried first (the resident n_a = 2 plan stays the last resort)
+  // Resident weights that leave only n_a = 2 vs streamed weights with n_a = 4 (measured,
+  // profiles/r02_plan_ab.md): streaming wins only where the weight ring gets deep enough to cover
+  // the L2 latency — the two-source decoder convolution onto <= 32 channels (c5.0: 64 -> 32,
+  // 14 weight stages: 513 -> 425 us); with 6 stages it loses (c5.0 dgrad 339 -> 374, c3.0
+  // 155 -> 183 us).  So: for that layer class a resident plan must reach n_a = 4, else a streamed
+  // plan with >= 12 weight stages is preferred; the resident n_a = 2 plan stays the fallback.
+  // ATOMAI_B200_RES_NA4 = 0 disables, = 1 applies the rule to every layer (sweeps).
   const char* e_strict = getenv("ATOMAI_B200_RES_NA4");
-  const int strict0 = (e_strict && e_strict[0] == '1') ? 1 : 0;
+  int strict0 = (p->x3 && S.nsrc == 2 && !any_pool && taps == 9 && d->Cout <= 32) ? 1 : 0;
+  if (e_strict) strict0 = e_strict[0] == '1' ? 1 : 0;
   for (int strict = strict0; strict >= 0 && !ok; --strict)
   for (int attempt = 0; attempt < 3 && !ok; ++attempt) {
     if (force_attempt >= 0 && attempt != force_attempt) continue;
@@ -950,7 +956,7 @@ static int conv_tc_plan(const ab_conv_t* d, ConvTcParams* p, int* smem_bytes) {
         // weight stages: cover ~1.5 us of L2 latency, leave room for the activation stages
         n_b = ((avail - need_a * a_stage) / b_stage) & ~1;      // two rings of n_b/2 stages
         if (n_b > kMaxBStages) n_b = kMaxBStages;
-        if (n_b < 4) continue;
+        if (n_b < (strict ? 12 : 4)) continue;
         avail -= n_b * b_stage;
       }
       int na = avail / a_stage;
